@@ -1,0 +1,99 @@
+// Internal declarations shared by the translation units of libcts_sm100a.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/cts.h"
+
+struct cts_nccl_api;  // comm.cpp
+
+struct cts_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 148;
+  std::string err;
+  uint64_t launches = 0;
+  // reduction scratch (reduce.cu)
+  double* d_partials = nullptr;   // [kMaxMulti][kReduceBlocks]
+  double* d_result = nullptr;     // [kMaxMulti]
+  unsigned int* d_counter = nullptr;
+  double* h_result = nullptr;     // pinned [kMaxMulti]
+  bool red_window = false;
+  size_t red_offset = 0, red_count = 0;
+  // device-side pointer table scratch for kernels taking many operands
+  // communicator (comm.cpp)
+  void* nccl_comm = nullptr;
+  int rank = 0, nranks = 1;
+};
+
+constexpr int kReduceBlocks = 1184;  // 148 SMs x 8: fixed so that reductions are deterministic
+constexpr int kReduceThreads = 256;
+constexpr int kMaxMulti = 8;
+
+#define CTS_CHECK_CTX(ctx) \
+  do {                     \
+    if (!(ctx)) return CTS_EINVAL; \
+  } while (0)
+
+inline int cts_fail(cts_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define CTS_CUDA(ctx, expr)                                                                      \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return cts_fail((ctx), CTS_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+  } while (0)
+
+#define CTS_LAUNCH_CHECK(ctx)                                                                    \
+  do {                                                                                           \
+    (ctx)->launches++;                                                                           \
+    cudaError_t _e = cudaGetLastError();                                                         \
+    if (_e != cudaSuccess)                                                                       \
+      return cts_fail((ctx), CTS_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(_e) + \
+                                            " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+#define CTS_TRY(expr)        \
+  do {                       \
+    int _r = (expr);         \
+    if (_r != 0) return _r;  \
+  } while (0)
+
+inline size_t cts_sizeof(cts_dtype ft) { return ft == CTS_F64 ? 8 : 4; }
+inline bool cts_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- internal entry points used across translation units ------------------------------------
+// fused LSRK stage with the advection stencil (ops.cu); out-of-place in u.
+int cts_advection_fused_stage(cts_op_advection* op, void* u_out, const void* u_in, void* du, double A, double dtB,
+                              int compute_native);
+// fused implicit column stage (ops.cu):  U0 = K1(base, terms) ; Newton(1 iter, direct) ; writes U, T_imp_i [, temp]
+struct cts_fused_stage_args {
+  const void* base;
+  double c0;
+  int n_grp1, n_grp2;
+  double coef[CTS_MAX_TERMS];
+  const void* terms[CTS_MAX_TERMS];
+  int compute_native;
+  double dtgamma;
+  const cts_tridiag* W;  // stored W (ignored when matrix free)
+  void* U;               // out: stage value
+  void* T_imp;           // out: (U - U0)/dtγ, may be null
+  void* temp;            // out (optional): U0
+};
+int cts_column_fused_stage(cts_op_column* op, const cts_fused_stage_args* a);
+bool cts_column_fusable(const cts_op_column* op);
+bool cts_op_column_is_linear(const cts_op_column* op);
+bool cts_op_column_matrix_free(const cts_op_column* op);
+cts_ctx* cts_op_column_ctx(const cts_op_column* op);
+cts_ctx* cts_op_advection_ctx(const cts_op_advection* op);
+cts_dtype cts_op_column_dtype(const cts_op_column* op);
+cts_dtype cts_op_advection_dtype(const cts_op_advection* op);
+size_t cts_op_advection_n(const cts_op_advection* op);

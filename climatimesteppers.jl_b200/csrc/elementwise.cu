@@ -1,0 +1,350 @@
+// Element-wise state-update kernels (K1-K11 of SURVEY §2c).
+//
+// All of these are pure HBM streaming: (1+nnz) reads + 1 write per DOF, <= 2 flop/byte, so the design
+// rules are the memory ones: 128-bit coalesced accesses, every operand's load issued before the first
+// use (fully unrolled operand loop -> NT*UNROLL independent 16-byte requests in flight per thread),
+// grids sized from the problem (>= several waves of 148 SMs at the 2^27-DOF target size), no shared
+// memory.  Arithmetic uses __dmul_rn/__dadd_rn so nothing is contracted into FMAs: the results are
+// bit-identical to the reference's broadcast evaluation order.
+#include "cts_internal.h"
+#include "ew_device.cuh"
+
+using namespace cts_ew;
+
+namespace {
+
+template <typename T, typename C, int NT, int UNROLL>
+__global__ void __launch_bounds__(256) axpy_n_vec_kernel(const AxpyArgs<NT> a, size_t nvec) {
+  using V = typename Vec<T>::type;
+  constexpr int VN = Vec<T>::N;
+  constexpr int NTS = NT > 0 ? NT : 1;
+  const size_t tile = (size_t)blockIdx.x * (blockDim.x * UNROLL);
+  V vb[UNROLL];
+  V vt[NTS][UNROLL];
+  bool ok[UNROLL];
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    size_t i = tile + (size_t)u * blockDim.x + threadIdx.x;
+    ok[u] = i < nvec;
+    if (ok[u]) {
+      vb[u] = reinterpret_cast<const V*>(a.base)[i];
+#pragma unroll
+      for (int k = 0; k < NT; ++k) vt[k][u] = reinterpret_cast<const V*>(a.terms[k])[i];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    if (!ok[u]) continue;
+    size_t i = tile + (size_t)u * blockDim.x + threadIdx.x;
+    T eb[VN], eo[VN];
+    vec_unpack<T>(vb[u], eb);
+    T et[NTS][VN];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) vec_unpack<T>(vt[k][u], et[k]);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      T x[NTS];
+#pragma unroll
+      for (int k = 0; k < NT; ++k) x[k] = et[k][e];
+      eo[e] = axpy_combine<T, C, NT>(eb[e], x, a);
+    }
+    V vo = vec_pack<T>(eo);
+    reinterpret_cast<V*>(a.out)[i] = vo;
+    if (a.out2) reinterpret_cast<V*>(a.out2)[i] = vo;
+  }
+}
+
+// scalar variant for unaligned pointers and tails
+template <typename T, typename C, int NT>
+__global__ void __launch_bounds__(256) axpy_n_scalar_kernel(const AxpyArgs<NT> a, size_t begin, size_t n) {
+  constexpr int NTS = NT > 0 ? NT : 1;
+  size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T b = reinterpret_cast<const T*>(a.base)[i];
+  T x[NTS];
+#pragma unroll
+  for (int k = 0; k < NT; ++k) x[k] = reinterpret_cast<const T*>(a.terms[k])[i];
+  T o = axpy_combine<T, C, NT>(b, x, a);
+  reinterpret_cast<T*>(a.out)[i] = o;
+  if (a.out2) reinterpret_cast<T*>(a.out2)[i] = o;
+}
+
+template <typename T, typename C, int NT>
+int launch_axpy(cts_ctx* ctx, size_t n, void* out, void* out2, double c0, const void* base, int n1, const double* coef,
+                const void* const* terms) {
+  AxpyArgs<NT> a;
+  a.base = base;
+  a.out = out;
+  a.out2 = out2;
+  a.c0 = c0;
+  a.n1 = n1;
+  a.scale_base = (c0 != 1.0);
+  bool aligned = cts_aligned16(base) && cts_aligned16(out) && (!out2 || cts_aligned16(out2));
+  for (int k = 0; k < NT; ++k) {
+    a.terms[k] = terms[k];
+    a.coef[k] = coef[k];
+    aligned = aligned && cts_aligned16(terms[k]);
+  }
+  constexpr int VN = Vec<T>::N;
+  // more independent requests per thread when there are few operands
+  constexpr int UNROLL = (NT <= 1) ? 4 : (NT <= 4 ? 2 : 1);
+  size_t nvec = aligned ? n / VN : 0;
+  if (nvec > 0) {
+    size_t per_block = (size_t)256 * UNROLL;
+    size_t blocks = (nvec + per_block - 1) / per_block;
+    axpy_n_vec_kernel<T, C, NT, UNROLL><<<(unsigned)blocks, 256, 0, ctx->stream>>>(a, nvec);
+    CTS_LAUNCH_CHECK(ctx);
+  }
+  size_t done = nvec * VN;
+  if (done < n) {
+    size_t rem = n - done;
+    size_t blocks = (rem + 255) / 256;
+    axpy_n_scalar_kernel<T, C, NT><<<(unsigned)blocks, 256, 0, ctx->stream>>>(a, done, n);
+    CTS_LAUNCH_CHECK(ctx);
+  }
+  return CTS_OK;
+}
+
+template <typename T, typename C>
+int dispatch_axpy(cts_ctx* ctx, size_t n, void* out, void* out2, double c0, const void* base, int n1, int nt,
+                  const double* coef, const void* const* terms) {
+  switch (nt) {
+#define CASE(N) \
+  case N:       \
+    return launch_axpy<T, C, N>(ctx, n, out, out2, c0, base, n1, coef, terms);
+    CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
+        CASE(13) CASE(14) CASE(15) CASE(16)
+#undef CASE
+    default:
+      return cts_fail(ctx, CTS_EINVAL, "cts_axpy_n: more than CTS_MAX_TERMS operands");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic small element-wise kernels: out = f(a, b, c)
+// ---------------------------------------------------------------------------------------------
+template <typename T, int NIN, typename F>
+__global__ void __launch_bounds__(256) ew_vec_kernel(T* out, const T* a, const T* b, const T* c, size_t nvec, F f) {
+  using V = typename Vec<T>::type;
+  constexpr int VN = Vec<T>::N;
+  constexpr int UNROLL = 2;
+  const size_t tile = (size_t)blockIdx.x * (blockDim.x * UNROLL);
+  V va[UNROLL], vb[UNROLL], vc[UNROLL];
+  bool ok[UNROLL];
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    size_t i = tile + (size_t)u * blockDim.x + threadIdx.x;
+    ok[u] = i < nvec;
+    if (ok[u]) {
+      va[u] = reinterpret_cast<const V*>(a)[i];
+      if (NIN > 1) vb[u] = reinterpret_cast<const V*>(b)[i];
+      if (NIN > 2) vc[u] = reinterpret_cast<const V*>(c)[i];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    if (!ok[u]) continue;
+    size_t i = tile + (size_t)u * blockDim.x + threadIdx.x;
+    T ea[VN], eb[VN], ec[VN], eo[VN];
+    vec_unpack<T>(va[u], ea);
+    if (NIN > 1) vec_unpack<T>(vb[u], eb);
+    if (NIN > 2) vec_unpack<T>(vc[u], ec);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) eo[e] = f(ea[e], NIN > 1 ? eb[e] : T(0), NIN > 2 ? ec[e] : T(0));
+    reinterpret_cast<V*>(out)[i] = vec_pack<T>(eo);
+  }
+}
+
+template <typename T, int NIN, typename F>
+__global__ void __launch_bounds__(256) ew_scalar_kernel(T* out, const T* a, const T* b, const T* c, size_t begin,
+                                                         size_t n, F f) {
+  size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = f(a[i], NIN > 1 ? b[i] : T(0), NIN > 2 ? c[i] : T(0));
+}
+
+template <typename T, int NIN, typename F>
+int launch_ew(cts_ctx* ctx, size_t n, void* out, const void* a, const void* b, const void* c, F f) {
+  if (n == 0) return CTS_OK;
+  constexpr int VN = Vec<T>::N;
+  bool aligned = cts_aligned16(out) && cts_aligned16(a) && (NIN < 2 || cts_aligned16(b)) && (NIN < 3 || cts_aligned16(c));
+  size_t nvec = aligned ? n / VN : 0;
+  if (nvec > 0) {
+    size_t per_block = 256 * 2;
+    size_t blocks = (nvec + per_block - 1) / per_block;
+    ew_vec_kernel<T, NIN, F><<<(unsigned)blocks, 256, 0, ctx->stream>>>((T*)out, (const T*)a, (const T*)b, (const T*)c, nvec, f);
+    CTS_LAUNCH_CHECK(ctx);
+  }
+  size_t done = nvec * VN;
+  if (done < n) {
+    size_t blocks = (n - done + 255) / 256;
+    ew_scalar_kernel<T, NIN, F><<<(unsigned)blocks, 256, 0, ctx->stream>>>((T*)out, (const T*)a, (const T*)b, (const T*)c, done, n, f);
+    CTS_LAUNCH_CHECK(ctx);
+  }
+  return CTS_OK;
+}
+
+// functors ------------------------------------------------------------------------------------
+template <typename T>
+struct ResidualF {  // K3: (U0 + dtγ*r) - U'   evaluated in Float64 (dtγ is Float64, imex_ark.jl:122,297)
+  double dtg;
+  __device__ T operator()(T r, T U0, T Up) const {
+    return (T)__dsub_rn(__dadd_rn((double)U0, __dmul_rn(dtg, (double)r)), (double)Up);
+  }
+};
+template <typename T>
+struct SubF {  // K5: x - dx in the state precision
+  __device__ T operator()(T x, T dx, T) const { return op_sub(x, dx); }
+};
+template <typename T>
+struct TimpF {  // K6: (U - temp) / dtγ : subtraction in the state precision, division in Float64
+  double dtg;
+  __device__ T operator()(T U, T temp, T) const { return (T)__ddiv_rn((double)op_sub(U, temp), dtg); }
+};
+template <typename T>
+struct PerturbF {  // K7: x + ε*dx  (ε has the state eltype, newtons_method.jl:177-178)
+  T eps;
+  __device__ T operator()(T x, T dx, T) const { return op_add(x, op_mul(eps, dx)); }
+};
+template <typename T>
+struct QuotientF {  // K8: (f2 - f)/ε
+  T eps;
+  __device__ T operator()(T f2, T f, T) const { return op_div(op_sub(f2, f), eps); }
+};
+template <typename T, typename C>
+struct LsrkF {  // K10: u + (dt*B)*du
+  C dtB;
+  __device__ T operator()(T u, T du, T) const { return (T)op_add((C)u, op_mul(dtB, (C)du)); }
+};
+template <typename T>
+struct AxpbyF {  // y = a*x + b*y in Float64
+  double a, b;
+  __device__ T operator()(T x, T y, T) const { return (T)__dadd_rn(__dmul_rn(a, (double)x), __dmul_rn(b, (double)y)); }
+};
+template <typename T>
+struct ScaleF {  // y = a*x in Float64
+  double a;
+  __device__ T operator()(T x, T, T) const { return (T)__dmul_rn(a, (double)x); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int cts_axpy_n(cts_ctx* ctx, cts_dtype ft, size_t n, void* out, void* out2, double c0, const void* base, int n_grp1,
+               int n_grp2, const double* coef, const void* const* terms, int compute_native) {
+  CTS_CHECK_CTX(ctx);
+  if (n == 0) return CTS_OK;
+  if (!out || !base || n_grp1 < 0 || n_grp2 < 0) return cts_fail(ctx, CTS_EINVAL, "cts_axpy_n: bad arguments");
+  int nt = n_grp1 + n_grp2;
+  if (nt > 0 && (!coef || !terms)) return cts_fail(ctx, CTS_EINVAL, "cts_axpy_n: null coef/terms");
+  if (ft == CTS_F64) return dispatch_axpy<double, double>(ctx, n, out, out2, c0, base, n_grp1, nt, coef, terms);
+  if (compute_native) return dispatch_axpy<float, float>(ctx, n, out, out2, c0, base, n_grp1, nt, coef, terms);
+  return dispatch_axpy<float, double>(ctx, n, out, out2, c0, base, n_grp1, nt, coef, terms);
+}
+
+int cts_newton_residual(cts_ctx* ctx, cts_dtype ft, size_t n, void* r, const void* U0, double dtgamma, const void* Up) {
+  CTS_CHECK_CTX(ctx);
+  if (ft == CTS_F64) return launch_ew<double, 3>(ctx, n, r, r, U0, Up, ResidualF<double>{dtgamma});
+  return launch_ew<float, 3>(ctx, n, r, r, U0, Up, ResidualF<float>{dtgamma});
+}
+
+int cts_sub_inplace(cts_ctx* ctx, cts_dtype ft, size_t n, void* x, const void* dx) {
+  CTS_CHECK_CTX(ctx);
+  if (ft == CTS_F64) return launch_ew<double, 2>(ctx, n, x, x, dx, nullptr, SubF<double>{});
+  return launch_ew<float, 2>(ctx, n, x, x, dx, nullptr, SubF<float>{});
+}
+
+int cts_timp_from_stage(cts_ctx* ctx, cts_dtype ft, size_t n, void* T, const void* U, const void* temp, double dtgamma) {
+  CTS_CHECK_CTX(ctx);
+  if (ft == CTS_F64) return launch_ew<double, 2>(ctx, n, T, U, temp, nullptr, TimpF<double>{dtgamma});
+  return launch_ew<float, 2>(ctx, n, T, U, temp, nullptr, TimpF<float>{dtgamma});
+}
+
+int cts_jvp_perturb(cts_ctx* ctx, cts_dtype ft, size_t n, void* x2, const void* x, double eps, const void* dx) {
+  CTS_CHECK_CTX(ctx);
+  if (ft == CTS_F64) return launch_ew<double, 2>(ctx, n, x2, x, dx, nullptr, PerturbF<double>{eps});
+  return launch_ew<float, 2>(ctx, n, x2, x, dx, nullptr, PerturbF<float>{(float)eps});
+}
+
+int cts_jvp_quotient(cts_ctx* ctx, cts_dtype ft, size_t n, void* out, const void* f2, const void* f, double eps) {
+  CTS_CHECK_CTX(ctx);
+  if (ft == CTS_F64) return launch_ew<double, 2>(ctx, n, out, f2, f, nullptr, QuotientF<double>{eps});
+  return launch_ew<float, 2>(ctx, n, out, f2, f, nullptr, QuotientF<float>{(float)eps});
+}
+
+int cts_lsrk_update(cts_ctx* ctx, cts_dtype ft, size_t n, void* u, double dtB, const void* du, int compute_native) {
+  CTS_CHECK_CTX(ctx);
+  if (ft == CTS_F64) return launch_ew<double, 2>(ctx, n, u, u, du, nullptr, LsrkF<double, double>{dtB});
+  if (compute_native) return launch_ew<float, 2>(ctx, n, u, u, du, nullptr, LsrkF<float, float>{(float)dtB});
+  return launch_ew<float, 2>(ctx, n, u, u, du, nullptr, LsrkF<float, double>{dtB});
+}
+
+int cts_axpby(cts_ctx* ctx, cts_dtype ft, size_t n, double a, const void* x, double b, void* y) {
+  CTS_CHECK_CTX(ctx);
+  if (b == 0.0) {
+    if (ft == CTS_F64) return launch_ew<double, 1>(ctx, n, y, x, nullptr, nullptr, ScaleF<double>{a});
+    return launch_ew<float, 1>(ctx, n, y, x, nullptr, nullptr, ScaleF<float>{a});
+  }
+  if (ft == CTS_F64) return launch_ew<double, 2>(ctx, n, y, x, y, nullptr, AxpbyF<double>{a, b});
+  return launch_ew<float, 2>(ctx, n, y, x, y, nullptr, AxpbyF<float>{a, b});
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// GMRES helpers: y = x / denom, out = sum_j coef[j] V[j]
+// ---------------------------------------------------------------------------------------------
+namespace {
+template <typename T>
+struct DivF {
+  double denom;
+  __device__ T operator()(T x, T, T) const { return (T)__ddiv_rn((double)x, denom); }
+};
+
+constexpr int kLincombMax = 32;
+struct LincombArgs {
+  const void* V[kLincombMax];
+  double coef[kLincombMax];
+  int k;
+  int accumulate;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) lincomb_kernel(T* out, const LincombArgs a, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double acc = a.accumulate ? (double)out[i] : 0.0;
+  for (int j = 0; j < a.k; ++j) acc = __dadd_rn(acc, __dmul_rn(a.coef[j], (double)reinterpret_cast<const T*>(a.V[j])[i]));
+  out[i] = (T)acc;
+}
+}  // namespace
+
+extern "C" int cts_div_scalar(cts_ctx* ctx, cts_dtype ft, size_t n, void* y, const void* x, double denom) {
+  CTS_CHECK_CTX(ctx);
+  if (ft == CTS_F64) return launch_ew<double, 1>(ctx, n, y, x, nullptr, nullptr, DivF<double>{denom});
+  return launch_ew<float, 1>(ctx, n, y, x, nullptr, nullptr, DivF<float>{denom});
+}
+
+extern "C" int cts_lincomb(cts_ctx* ctx, cts_dtype ft, size_t n, void* out, int k, const double* coef,
+                           const void* const* V, int accumulate) {
+  CTS_CHECK_CTX(ctx);
+  if (!out || k < 0 || (k > 0 && (!coef || !V))) return cts_fail(ctx, CTS_EINVAL, "cts_lincomb: bad argument");
+  if (n == 0) return CTS_OK;
+  if (k == 0 && !accumulate) return cts_memset_zero(ctx, out, n * cts_sizeof(ft));
+  size_t blocks = (n + 255) / 256;
+  for (int j0 = 0; j0 < k; j0 += kLincombMax) {
+    LincombArgs a;
+    a.k = (k - j0 < kLincombMax) ? k - j0 : kLincombMax;
+    a.accumulate = (j0 > 0) || accumulate;
+    for (int j = 0; j < a.k; ++j) {
+      a.V[j] = V[j0 + j];
+      a.coef[j] = coef[j0 + j];
+    }
+    if (ft == CTS_F64)
+      lincomb_kernel<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)out, a, n);
+    else
+      lincomb_kernel<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)out, a, n);
+    CTS_LAUNCH_CHECK(ctx);
+  }
+  return CTS_OK;
+}

@@ -1,0 +1,644 @@
+// Library-native model operators (layer L5 of the reference: the user's T_exp!/T_imp!/Wfact/dss!) for the
+// synthetic benchmark problems of SURVEY §8d, and the fused kernels the solvers may substitute for a
+// sequence of hook calls when they recognise these operators:
+//   * cts_advection_fused_stage : K10f + K10 in one pass  (du = rhs(u) + A du ; u += dtB du), 4w B/DOF
+//   * cts_column_fused_stage    : K1 + K2 + T_imp + K3 + K4 + K5 + K6 of one implicit ARK/SSPRK stage
+//                                 in one pass over the column tile, (2+nnz)w [+3w for stored W] B/DOF
+// Both produce results bit-identical to the un-fused hook sequence (tests/test_gpu_parity.py).
+#include <cmath>
+
+#include "cts_internal.h"
+#include "ew_device.cuh"
+#include "tile_device.cuh"
+
+using namespace cts_tile;
+using cts_ew::AxpyArgs;
+using cts_ew::axpy_combine;
+using cts_ew::Vec;
+using cts_ew::vec_pack;
+using cts_ew::vec_unpack;
+
+// =============================================================================================
+// 1-D periodic upwind advection (config C2)
+//   rhs_i = (-c * (u_i - u_{i-1})) / dx            (state precision)
+//   du_i  = alpha * rhs_i + beta * du_i            (IncrementingODEFunction, problems.jl:77-85)
+// =============================================================================================
+struct cts_op_advection {
+  cts_ctx* ctx;
+  cts_dtype ft;
+  size_t n;
+  double c, dx;
+};
+
+namespace {
+
+template <typename T>
+__device__ __forceinline__ T adv_rhs(T uc, T ul, T negc, T dx) {
+  return rdiv(rmul(negc, rsub(uc, ul)), dx);
+}
+
+// FUSED: also performs the 2N register update u_out = u + dtB*du_new (lsrk.jl:65) in the compute type C.
+template <typename T, typename C, bool FUSED, bool VEC>
+__global__ void __launch_bounds__(256) advection_kernel(T* du, const T* u, T* u_out, size_t n, T negc, T dx, T alpha,
+                                                        T beta, C dtB) {
+  using V = typename Vec<T>::type;
+  constexpr int VN = VEC ? Vec<T>::N : 1;
+  const size_t nv = n / VN;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  T eu[VN], ed[VN];
+  if (VEC) {
+    T tu[Vec<T>::N], td[Vec<T>::N];
+    vec_unpack<T>(reinterpret_cast<const V*>(u)[i], tu);
+    vec_unpack<T>(reinterpret_cast<const V*>(du)[i], td);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      eu[e] = tu[e];
+      ed[e] = td[e];
+    }
+  } else {
+    eu[0] = u[i];
+    ed[0] = du[i];
+  }
+  const size_t first = i * VN;
+  T left = u[first == 0 ? n - 1 : first - 1];
+  T od[VN], ou[VN];
+#pragma unroll
+  for (int e = 0; e < VN; ++e) {
+    T rhs = adv_rhs<T>(eu[e], left, negc, dx);
+    od[e] = radd(rmul(alpha, rhs), rmul(beta, ed[e]));
+    if (FUSED) ou[e] = (T)cts_ew::op_add((C)eu[e], cts_ew::op_mul(dtB, (C)od[e]));
+    left = eu[e];
+  }
+  if (VEC) {
+    T td[Vec<T>::N], tu[Vec<T>::N];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      td[e] = od[e];
+      tu[e] = FUSED ? ou[e] : T(0);
+    }
+    reinterpret_cast<V*>(du)[i] = vec_pack<T>(td);
+    if (FUSED) reinterpret_cast<V*>(u_out)[i] = vec_pack<T>(tu);
+  } else {
+    du[i] = od[0];
+    if (FUSED) u_out[i] = ou[0];
+  }
+}
+
+template <typename T, typename C, bool FUSED>
+int launch_advection(cts_op_advection* op, void* du, const void* u, void* u_out, double alpha, double beta, double dtB) {
+  cts_ctx* ctx = op->ctx;
+  const size_t n = op->n;
+  constexpr int VN = Vec<T>::N;
+  bool vec = (n % VN) == 0 && cts_aligned16(du) && cts_aligned16(u) && (!FUSED || cts_aligned16(u_out));
+  T negc = (T)(-op->c), dx = (T)op->dx;
+  if (vec) {
+    size_t blocks = (n / VN + 255) / 256;
+    advection_kernel<T, C, FUSED, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>((T*)du, (const T*)u, (T*)u_out, n, negc, dx,
+                                                                                   (T)alpha, (T)beta, (C)dtB);
+  } else {
+    size_t blocks = (n + 255) / 256;
+    advection_kernel<T, C, FUSED, false><<<(unsigned)blocks, 256, 0, ctx->stream>>>((T*)du, (const T*)u, (T*)u_out, n, negc, dx,
+                                                                                    (T)alpha, (T)beta, (C)dtB);
+  }
+  CTS_LAUNCH_CHECK(ctx);
+  return CTS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cts_op_advection_create(cts_ctx* ctx, cts_dtype ft, size_t n, double c, double dx, cts_op_advection** out) {
+  CTS_CHECK_CTX(ctx);
+  if (!out || n < 2 || dx == 0.0) return cts_fail(ctx, CTS_EINVAL, "cts_op_advection_create: bad argument");
+  *out = new cts_op_advection{ctx, ft, n, c, dx};
+  return CTS_OK;
+}
+int cts_op_advection_destroy(cts_op_advection* op) {
+  delete op;
+  return CTS_OK;
+}
+int cts_op_advection_incr(void* vop, void* du, const void* u, double t, double alpha, double beta) {
+  auto* op = static_cast<cts_op_advection*>(vop);
+  if (!op || !du || !u || du == u) return CTS_EINVAL;
+  if (op->ft == CTS_F64) return launch_advection<double, double, false>(op, du, u, nullptr, alpha, beta, 0.0);
+  return launch_advection<float, float, false>(op, du, u, nullptr, alpha, beta, 0.0);
+}
+
+}  // extern "C"
+
+int cts_advection_fused_stage(cts_op_advection* op, void* u_out, const void* u_in, void* du, double A, double dtB,
+                              int compute_native) {
+  if (!op || u_out == u_in) return CTS_EINVAL;
+  if (op->ft == CTS_F64) return launch_advection<double, double, true>(op, du, u_in, u_out, 1.0, A, dtB);
+  if (compute_native) return launch_advection<float, float, true>(op, du, u_in, u_out, 1.0, A, dtB);
+  return launch_advection<float, double, true>(op, du, u_in, u_out, 1.0, A, dtB);
+}
+cts_ctx* cts_op_advection_ctx(const cts_op_advection* op) { return op->ctx; }
+cts_dtype cts_op_advection_dtype(const cts_op_advection* op) { return op->ft; }
+size_t cts_op_advection_n(const cts_op_advection* op) { return op->n; }
+
+// =============================================================================================
+// Column model (configs C3/C4/C5)
+// =============================================================================================
+struct cts_op_column {
+  cts_ctx* ctx;
+  cts_dtype ft;
+  cts_column_desc d;
+  size_t rows;   // ny_local + 2*halo
+  size_t ncols;  // rows*nx
+  bool matrix_free;
+};
+
+namespace {
+
+// per-column diffusion number a = K / dz^2 (state precision)
+template <typename T>
+__device__ __forceinline__ T col_a(T K, T dz) {
+  return rdiv(K, rmul(dz, dz));
+}
+// linear operator row: a*((um - 2 uc) + up)
+template <typename T>
+__device__ __forceinline__ T timp_linear(T a, T um, T uc, T up) {
+  return rmul(a, radd(rsub(um, rmul(T(2), uc)), up));
+}
+// nonlinear face diffusivity a*(1 + ubar^2), ubar = (ua+ub)/2
+template <typename T>
+__device__ __forceinline__ T kface(T a, T ua, T ub) {
+  T ubar = rmul(T(0.5), radd(ua, ub));
+  return rmul(a, radd(T(1), rmul(ubar, ubar)));
+}
+template <typename T>
+__device__ __forceinline__ T timp_nonlinear(T a, T um, T uc, T up) {
+  T fp = rmul(kface(a, uc, up), rsub(up, uc));
+  T fm = rmul(kface(a, um, uc), rsub(uc, um));
+  return rsub(fp, fm);
+}
+
+// T_imp: one thread per DOF vector; neighbours along the (contiguous) level axis.
+template <typename T, bool NONLINEAR>
+__global__ void __launch_bounds__(256) column_timp_kernel(T* __restrict__ out, const T* __restrict__ u,
+                                                          const T* __restrict__ Kcol, T dz, int nlev, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  size_t col = i / (size_t)nlev;
+  int lev = (int)(i - col * (size_t)nlev);
+  T a = col_a<T>(Kcol[col], dz);
+  T uc = u[i];
+  T um = lev > 0 ? u[i - 1] : T(0);
+  T up = lev < nlev - 1 ? u[i + 1] : T(0);
+  out[i] = NONLINEAR ? timp_nonlinear<T>(a, um, uc, up) : timp_linear<T>(a, um, uc, up);
+}
+
+// Wfact: W = dtγ J - I   (tridiagonal; frozen coefficients at u for the nonlinear operator)
+template <typename T, bool NONLINEAR>
+__global__ void __launch_bounds__(256) column_wfact_kernel(T* __restrict__ dl, T* __restrict__ d, T* __restrict__ du,
+                                                           const T* __restrict__ u, const T* __restrict__ Kcol, T dz,
+                                                           double dtg, int nlev, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  size_t col = i / (size_t)nlev;
+  int lev = (int)(i - col * (size_t)nlev);
+  T a = col_a<T>(Kcol[col], dz);
+  if (!NONLINEAR) {
+    double o = __dmul_rn(dtg, (double)a);
+    dl[i] = (T)o;
+    du[i] = (T)o;
+    d[i] = (T)__dsub_rn(__dmul_rn(-2.0, o), 1.0);
+  } else {
+    T uc = u[i];
+    T um = lev > 0 ? u[i - 1] : T(0);
+    T up = lev < nlev - 1 ? u[i + 1] : T(0);
+    double lo = __dmul_rn(dtg, (double)kface(a, um, uc));
+    double hi = __dmul_rn(dtg, (double)kface(a, uc, up));
+    dl[i] = (T)lo;
+    du[i] = (T)hi;
+    d[i] = (T)__dsub_rn(-__dadd_rn(lo, hi), 1.0);
+  }
+}
+
+// T_exp = S[lev]*g(t) + nu * (((uw + ue) + us) + un - 4 uc), owned rows only.
+template <typename T>
+__global__ void __launch_bounds__(256) column_texp_kernel(T* __restrict__ out, const T* __restrict__ u,
+                                                          const T* __restrict__ S, T g, T nu, int nlev, size_t nx,
+                                                          size_t ny_local, int halo, int has_src) {
+  const size_t row_elems = nx * (size_t)nlev;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // index within the owned rows
+  if (i >= ny_local * row_elems) return;
+  size_t jr = i / row_elems;          // owned row
+  size_t r = i - jr * row_elems;      // offset in the row
+  size_t ix = r / (size_t)nlev;
+  int lev = (int)(r - ix * (size_t)nlev);
+  size_t rows = ny_local + 2 * (size_t)halo;
+  size_t j = jr + (size_t)halo;       // row in the local array
+  size_t idx = j * row_elems + r;
+  T val = has_src ? rmul(S[lev], g) : T(0);
+  if (nu != T(0)) {
+    size_t ixw = ix == 0 ? nx - 1 : ix - 1, ixe = ix == nx - 1 ? 0 : ix + 1;
+    size_t js, jn;
+    if (halo) {
+      js = j - 1;
+      jn = j + 1;
+    } else {  // single-rank periodic wrap without ghost rows
+      js = j == 0 ? rows - 1 : j - 1;
+      jn = j == rows - 1 ? 0 : j + 1;
+    }
+    T uc = u[idx];
+    T uw = u[j * row_elems + ixw * (size_t)nlev + lev], ue = u[j * row_elems + ixe * (size_t)nlev + lev];
+    T us = u[js * row_elems + r], un = u[jn * row_elems + r];
+    T lap = rsub(radd(radd(radd(uw, ue), us), un), rmul(T(4), uc));
+    val = radd(val, rmul(nu, lap));
+  }
+  out[idx] = val;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused implicit stage for the LINEAR column operator, Newton max_iters = 1, direct solve:
+//   U0   = (c0*base + G1) + G2                        K1  (fused_increment.jl:220-236)
+//   r    = T_imp(U0)                                  user hook (linear diffusion)
+//   f    = (U0 + dtγ r) - U0                          K3  (imex_ark.jl:297, evaluated in Float64)
+//   dx   = W \ f                                      K4  (two-sided Thomas; W stored or regenerated)
+//   U    = U0 - dx                                    K5  (newtons_method.jl:651)
+//   Timp = (U - U0)/dtγ                               K6  (imex_ark.jl:269)
+// One CTA per 32-column tile; U0 is assembled straight from global memory with 128-bit loads into a
+// padded shared tile, the elimination runs out of shared memory, U / T_imp leave with 128-bit stores.
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+struct FusedArgs {
+  AxpyArgs<NT> ax;   // base/terms/coef (out/out2 unused)
+  void* U;
+  void* Timp;
+  void* temp;
+  const void* Kcol;
+  const void* dl;
+  const void* d;
+  const void* du;
+  double dtg;
+  double dz;
+  int nlev;
+  size_t ncols;
+  int pitch;
+};
+
+template <typename T, typename C, int NT, bool MATRIX_FREE>
+__global__ void __launch_bounds__(kTileThreads) column_fused_stage_kernel(const FusedArgs<NT> a) {
+  using V = typename Vec<T>::type;
+  constexpr int VN = Vec<T>::N;
+  constexpr int NTS = NT > 0 ? NT : 1;
+  extern __shared__ __align__(128) char smem[];
+  const int pitch = a.pitch;
+  const int tile_bytes = kTileCols * pitch;
+  char* sU0 = smem;
+  char* sr = smem + tile_bytes;
+  char* sfac = smem + 2 * tile_bytes;  // matrix-free: cp/lp scratch; stored: dl tile (du and d follow)
+  char* sdl = sfac;
+  char* sd = smem + 3 * tile_bytes;
+  char* sdu = smem + 4 * tile_bytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (MATRIX_FREE ? 3 : 5) * tile_bytes);
+
+  const int nlev = a.nlev;
+  const size_t col0 = (size_t)blockIdx.x * kTileCols;
+  const int nvalid = (int)((a.ncols - col0) < (size_t)kTileCols ? (a.ncols - col0) : (size_t)kTileCols);
+  const int col_bytes = nlev * (int)sizeof(T);
+  const size_t goff = col0 * (size_t)nlev;
+
+  if (!MATRIX_FREE) {  // W tiles arrive by bulk TMA while U0 is being assembled
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+      mbar_arrive_expect_tx(bar, (uint32_t)(3 * nvalid * col_bytes));
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nvalid) {
+      const int c = threadIdx.x;
+      const size_t g = goff + (size_t)c * nlev;
+      bulk_g2s(sdl + c * pitch, (const T*)a.dl + g, col_bytes, bar);
+      bulk_g2s(sd + c * pitch, (const T*)a.d + g, col_bytes, bar);
+      bulk_g2s(sdu + c * pitch, (const T*)a.du + g, col_bytes, bar);
+    }
+  }
+
+  // ---- phase A: U0 tile = K1(base, terms), coalesced 128-bit loads ------------------------------
+  const int cpc = col_bytes / 16;
+  const int total = nvalid * cpc;
+  for (int q = threadIdx.x; q < total; q += kTileThreads) {
+    const int col = q / cpc, k = q - col * cpc;
+    const size_t gi = (goff * sizeof(T) + (size_t)col * col_bytes + (size_t)k * 16) / 16;  // 16-byte vector index
+    V vb = reinterpret_cast<const V*>(a.ax.base)[gi];
+    V vt[NTS];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) vt[t] = reinterpret_cast<const V*>(a.ax.terms[t])[gi];
+    T eb[VN], eo[VN], et[NTS][VN];
+    vec_unpack<T>(vb, eb);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) vec_unpack<T>(vt[t], et[t]);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      T x[NTS];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) x[t] = et[t][e];
+      eo[e] = axpy_combine<T, C, NT>(eb[e], x, a.ax);
+    }
+    V vo = vec_pack<T>(eo);
+    *reinterpret_cast<V*>(sU0 + col * pitch + k * 16) = vo;
+    if (a.temp) reinterpret_cast<V*>(a.temp)[gi] = vo;
+  }
+  __syncthreads();
+
+  // ---- phase B: residual + two-sided Thomas, a lane pair per column -----------------------------
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = warp * 16 + (lane & 15);
+  const bool is_up = lane >= 16;
+  const bool valid = col < nvalid;
+  const int col_off = col * pitch;
+  T acol = T(0);
+  if (valid) {
+    acol = col_a<T>(((const T*)a.Kcol)[col0 + col], (T)a.dz);
+    const T* U0 = reinterpret_cast<const T*>(sU0 + col_off);
+    T* r = reinterpret_cast<T*>(sr + col_off);
+    const int m = nlev / 2;
+    const int lo = is_up ? m : 0, hi = is_up ? nlev : m;
+    T um = lo > 0 ? U0[lo - 1] : T(0);
+    T uc = U0[lo];
+    for (int l = lo; l < hi; ++l) {
+      T up = l < nlev - 1 ? U0[l + 1] : T(0);
+      T ti = timp_linear<T>(acol, um, uc, up);
+      r[l] = (T)__dsub_rn(__dadd_rn((double)uc, __dmul_rn(a.dtg, (double)ti)), (double)uc);
+      um = uc;
+      uc = up;
+    }
+  }
+  if (MATRIX_FREE) {
+    double o = __dmul_rn(a.dtg, (double)acol);
+    ConstRows<T> rows{(T)o, (T)__dsub_rn(__dmul_rn(-2.0, o), 1.0)};
+    babe_solve_lanepair<T>(rows, sfac, sr, col_off, nlev, is_up, valid);
+  } else {
+    mbar_wait(bar, 0);
+    StoredRows<T> rows{sdl, sd, sdu};
+    babe_solve_lanepair<T>(rows, is_up ? sdl : sdu, sr, col_off, nlev, is_up, valid);
+  }
+  __syncthreads();
+
+  // ---- phase C: U = U0 - dx ; Timp = (U - U0)/dtγ ; coalesced 128-bit stores -----------------------
+  for (int q = threadIdx.x; q < total; q += kTileThreads) {
+    const int c = q / cpc, k = q - c * cpc;
+    const size_t gi = (goff * sizeof(T) + (size_t)c * col_bytes + (size_t)k * 16) / 16;
+    T e0[VN], ex[VN], eU[VN], eT[VN];
+    vec_unpack<T>(*reinterpret_cast<const V*>(sU0 + c * pitch + k * 16), e0);
+    vec_unpack<T>(*reinterpret_cast<const V*>(sr + c * pitch + k * 16), ex);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      eU[e] = rsub(e0[e], ex[e]);
+      eT[e] = (T)__ddiv_rn((double)rsub(eU[e], e0[e]), a.dtg);
+    }
+    reinterpret_cast<V*>(a.U)[gi] = vec_pack<T>(eU);
+    if (a.Timp) reinterpret_cast<V*>(a.Timp)[gi] = vec_pack<T>(eT);
+  }
+}
+
+template <typename T, typename C, int NT>
+int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
+  cts_ctx* ctx = op->ctx;
+  FusedArgs<NT> a;
+  a.ax.base = s->base;
+  a.ax.out = nullptr;
+  a.ax.out2 = nullptr;
+  a.ax.c0 = s->c0;
+  a.ax.n1 = s->n_grp1;
+  a.ax.scale_base = s->c0 != 1.0;
+  for (int k = 0; k < NT; ++k) {
+    a.ax.terms[k] = s->terms[k];
+    a.ax.coef[k] = s->coef[k];
+  }
+  a.U = s->U;
+  a.Timp = s->T_imp;
+  a.temp = s->temp;
+  a.Kcol = op->d.K_col;
+  a.dtg = s->dtgamma;
+  a.dz = op->d.dz;
+  a.nlev = op->d.nlev;
+  a.ncols = op->ncols;
+  a.pitch = pitch_bytes(op->d.nlev, sizeof(T));
+  const bool mf = op->matrix_free;
+  if (!mf) {
+    if (!s->W) return cts_fail(ctx, CTS_EINVAL, "fused stage: stored W required");
+    a.dl = s->W->dl;
+    a.d = s->W->d;
+    a.du = s->W->du;
+  } else {
+    a.dl = a.d = a.du = nullptr;
+  }
+  size_t tiles = (op->ncols + kTileCols - 1) / kTileCols;
+  size_t smem = (size_t)(mf ? 3 : 5) * kTileCols * a.pitch + 16;
+  if (mf) {
+    auto k = column_fused_stage_kernel<T, C, NT, true>;
+    CTS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)tiles, kTileThreads, smem, ctx->stream>>>(a);
+  } else {
+    auto k = column_fused_stage_kernel<T, C, NT, false>;
+    CTS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)tiles, kTileThreads, smem, ctx->stream>>>(a);
+  }
+  CTS_LAUNCH_CHECK(ctx);
+  return CTS_OK;
+}
+
+template <typename T, typename C>
+int dispatch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
+  switch (s->n_grp1 + s->n_grp2) {
+#define CASE(N) \
+  case N:       \
+    return launch_fused<T, C, N>(op, s);
+    CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
+        CASE(13) CASE(14)
+#undef CASE
+    default:
+      return CTS_EUNSUPPORTED;
+  }
+}
+
+}  // namespace
+
+bool cts_column_fusable(const cts_op_column* op) {
+  const int vn = op->ft == CTS_F64 ? 2 : 4;
+  const int es = op->ft == CTS_F64 ? 8 : 4;
+  size_t smem = (size_t)5 * kTileCols * pitch_bytes(op->d.nlev, es) + 16;
+  return !op->d.nonlinear && op->d.nlev >= 2 * vn && (op->d.nlev % (2 * vn)) == 0 && smem <= 200 * 1024;
+}
+
+int cts_column_fused_stage(cts_op_column* op, const cts_fused_stage_args* s) {
+  if (!op || !s) return CTS_EINVAL;
+  if (!cts_column_fusable(op)) return CTS_EUNSUPPORTED;
+  bool aligned = cts_aligned16(s->base) && cts_aligned16(s->U) && (!s->T_imp || cts_aligned16(s->T_imp)) &&
+                 (!s->temp || cts_aligned16(s->temp));
+  for (int k = 0; k < s->n_grp1 + s->n_grp2; ++k) aligned = aligned && cts_aligned16(s->terms[k]);
+  if (!op->matrix_free && s->W)
+    aligned = aligned && cts_aligned16(s->W->dl) && cts_aligned16(s->W->d) && cts_aligned16(s->W->du);
+  if (!aligned) return CTS_EUNSUPPORTED;
+  if (op->ft == CTS_F64) return dispatch_fused<double, double>(op, s);
+  if (s->compute_native) return dispatch_fused<float, float>(op, s);
+  return dispatch_fused<float, double>(op, s);
+}
+
+bool cts_op_column_is_linear(const cts_op_column* op) { return !op->d.nonlinear; }
+bool cts_op_column_matrix_free(const cts_op_column* op) { return op->matrix_free; }
+cts_ctx* cts_op_column_ctx(const cts_op_column* op) { return op->ctx; }
+cts_dtype cts_op_column_dtype(const cts_op_column* op) { return op->ft; }
+
+extern "C" {
+
+int cts_op_column_create(cts_ctx* ctx, cts_dtype ft, const cts_column_desc* desc, cts_op_column** out) {
+  CTS_CHECK_CTX(ctx);
+  if (!out || !desc || desc->nlev < 1 || desc->nx < 1 || desc->ny_local < 1 || !desc->K_col || desc->dz == 0.0 ||
+      (desc->halo != 0 && desc->halo != 1))
+    return cts_fail(ctx, CTS_EINVAL, "cts_op_column_create: bad descriptor");
+  if (desc->halo == 0 && ctx->nranks > 1 && desc->nu != 0.0)
+    return cts_fail(ctx, CTS_EINVAL, "horizontal coupling across ranks needs halo = 1");
+  auto* op = new cts_op_column();
+  op->ctx = ctx;
+  op->ft = ft;
+  op->d = *desc;
+  op->rows = desc->ny_local + 2 * (size_t)desc->halo;
+  op->ncols = op->rows * desc->nx;
+  op->matrix_free = false;
+  *out = op;
+  return CTS_OK;
+}
+
+int cts_op_column_destroy(cts_op_column* op) {
+  delete op;
+  return CTS_OK;
+}
+
+size_t cts_op_column_ndof(const cts_op_column* op) { return op ? op->ncols * (size_t)op->d.nlev : 0; }
+
+int cts_op_column_set_matrix_free(cts_op_column* op, int enabled) {
+  if (!op) return CTS_EINVAL;
+  if (enabled && op->d.nonlinear) return cts_fail(op->ctx, CTS_EINVAL, "matrix-free W needs the linear operator");
+  op->matrix_free = enabled != 0;
+  return CTS_OK;
+}
+
+int cts_op_column_make_W(cts_op_column* op, cts_tridiag** W) {
+  if (!op || !W) return CTS_EINVAL;
+  size_t bytes = cts_op_column_ndof(op) * cts_sizeof(op->ft);
+  auto* w = new cts_tridiag();
+  w->nlev = op->d.nlev;
+  w->ncols = op->ncols;
+  int r = cts_alloc(op->ctx, bytes, &w->dl);
+  if (!r) r = cts_alloc(op->ctx, bytes, &w->d);
+  if (!r) r = cts_alloc(op->ctx, bytes, &w->du);
+  if (r) {
+    cts_op_column_free_W(op, w);
+    return r;
+  }
+  *W = w;
+  return CTS_OK;
+}
+
+int cts_op_column_free_W(cts_op_column* op, cts_tridiag* W) {
+  if (!op || !W) return CTS_EINVAL;
+  cts_free(op->ctx, W->dl);
+  cts_free(op->ctx, W->d);
+  cts_free(op->ctx, W->du);
+  delete W;
+  return CTS_OK;
+}
+
+int cts_op_column_T_imp(void* vop, void* du, const void* u, double t) {
+  auto* op = static_cast<cts_op_column*>(vop);
+  if (!op || !du || !u || du == u) return CTS_EINVAL;
+  cts_ctx* ctx = op->ctx;
+  size_t n = cts_op_column_ndof(op);
+  size_t blocks = (n + 255) / 256;
+  const int nl = op->d.nlev;
+  if (op->ft == CTS_F64) {
+    if (op->d.nonlinear)
+      column_timp_kernel<double, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)du, (const double*)u, (const double*)op->d.K_col, op->d.dz, nl, n);
+    else
+      column_timp_kernel<double, false><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)du, (const double*)u, (const double*)op->d.K_col, op->d.dz, nl, n);
+  } else {
+    if (op->d.nonlinear)
+      column_timp_kernel<float, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)du, (const float*)u, (const float*)op->d.K_col, (float)op->d.dz, nl, n);
+    else
+      column_timp_kernel<float, false><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)du, (const float*)u, (const float*)op->d.K_col, (float)op->d.dz, nl, n);
+  }
+  CTS_LAUNCH_CHECK(ctx);
+  return CTS_OK;
+}
+
+int cts_op_column_Wfact(void* vop, void* vW, const void* u, double dtgamma, double t) {
+  auto* op = static_cast<cts_op_column*>(vop);
+  auto* W = static_cast<cts_tridiag*>(vW);
+  if (!op || !W || !u) return CTS_EINVAL;
+  cts_ctx* ctx = op->ctx;
+  size_t n = cts_op_column_ndof(op);
+  size_t blocks = (n + 255) / 256;
+  const int nl = op->d.nlev;
+  if (op->ft == CTS_F64) {
+    if (op->d.nonlinear)
+      column_wfact_kernel<double, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)W->dl, (double*)W->d, (double*)W->du, (const double*)u, (const double*)op->d.K_col, op->d.dz, dtgamma, nl, n);
+    else
+      column_wfact_kernel<double, false><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)W->dl, (double*)W->d, (double*)W->du, (const double*)u, (const double*)op->d.K_col, op->d.dz, dtgamma, nl, n);
+  } else {
+    if (op->d.nonlinear)
+      column_wfact_kernel<float, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)W->dl, (float*)W->d, (float*)W->du, (const float*)u, (const float*)op->d.K_col, (float)op->d.dz, dtgamma, nl, n);
+    else
+      column_wfact_kernel<float, false><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)W->dl, (float*)W->d, (float*)W->du, (const float*)u, (const float*)op->d.K_col, (float)op->d.dz, dtgamma, nl, n);
+  }
+  CTS_LAUNCH_CHECK(ctx);
+  return CTS_OK;
+}
+
+int cts_op_column_ldiv(void* vop, void* x, const void* vW, const void* b) {
+  auto* op = static_cast<cts_op_column*>(vop);
+  if (!op || !vW) return CTS_EINVAL;
+  return cts_tridiag_solve_batched(op->ctx, op->ft, static_cast<const cts_tridiag*>(vW), b, x);
+}
+
+int cts_op_column_jac_mul(void* vop, void* y, const void* vW, const void* x) {
+  auto* op = static_cast<cts_op_column*>(vop);
+  if (!op || !vW) return CTS_EINVAL;
+  return cts_tridiag_matvec(op->ctx, op->ft, static_cast<const cts_tridiag*>(vW), x, y);
+}
+
+int cts_op_column_T_exp(void* vop, void* du_exp, void* du_lim, const void* u, double t) {
+  auto* op = static_cast<cts_op_column*>(vop);
+  if (!op || !du_exp || !u || du_exp == u) return CTS_EINVAL;
+  cts_ctx* ctx = op->ctx;
+  const cts_column_desc& d = op->d;
+  size_t n_owned = d.ny_local * d.nx * (size_t)d.nlev;
+  size_t blocks = (n_owned + 255) / 256;
+  // time factor of the source, evaluated once on the host in Float64 (docs/src/tutorials/imex_diffusion.md:65-69)
+  double g = 1.0 + 0.5 * sin(2.0 * M_PI * t);
+  int has_src = d.S_lev != nullptr;
+  if (op->ft == CTS_F64)
+    column_texp_kernel<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)du_exp, (const double*)u, (const double*)d.S_lev, g, d.nu, d.nlev, d.nx, d.ny_local, d.halo, has_src);
+  else
+    column_texp_kernel<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)du_exp, (const float*)u, (const float*)d.S_lev, (float)g, (float)d.nu, d.nlev, d.nx, d.ny_local, d.halo, has_src);
+  CTS_LAUNCH_CHECK(ctx);
+  return CTS_OK;
+}
+
+int cts_op_column_dss(void* vop, void* u, double t) {
+  auto* op = static_cast<cts_op_column*>(vop);
+  if (!op || !u) return CTS_EINVAL;
+  if (!op->d.halo) return CTS_OK;  // nothing is duplicated
+  cts_ctx* ctx = op->ctx;
+  const size_t row = op->d.nx * (size_t)op->d.nlev;
+  const size_t es = cts_sizeof(op->ft);
+  char* b = static_cast<char*>(u);
+  char* ghost_lo = b;
+  char* first = b + row * es;
+  char* last = b + op->d.ny_local * row * es;
+  char* ghost_hi = b + (op->d.ny_local + 1) * row * es;
+  if (ctx->nranks <= 1) {  // periodic in the slow horizontal axis: the neighbour is this rank
+    CTS_CUDA(ctx, cudaMemcpyAsync(ghost_lo, last, row * es, cudaMemcpyDeviceToDevice, ctx->stream));
+    CTS_CUDA(ctx, cudaMemcpyAsync(ghost_hi, first, row * es, cudaMemcpyDeviceToDevice, ctx->stream));
+    return CTS_OK;
+  }
+  return cts_halo_exchange(ctx, op->ft, row, first, last, ghost_lo, ghost_hi);
+}
+
+}  // extern "C"

@@ -1,0 +1,1090 @@
+// Host-side step engine: `step_u!` for IMEX-ARK (imex_ark.jl:69-308), IMEX-SSPRK (imex_ssprk.jl:95-220) and
+// LSRK-2N (lsrk.jl:56-67), `solve_newton!` / `solve_krylov!` (newtons_method.jl:465-665) and GMRES
+// (Krylov.jl v0.10 `gmres!`, restated from its published algorithm).
+//
+// The engine walks the stages exactly where the reference does, calling the user's hooks through C
+// function pointers between library kernels.  All state arithmetic happens in the kernels of
+// elementwise.cu / reduce.cu / tridiag.cu / ops.cu; this file only sequences them (O(1) host work per
+// call, everything stream-ordered; only reductions feeding host control flow synchronise).
+//
+// Fast paths: when the hooks ARE the library's own operators (compared by function address) the engine
+// substitutes fused kernels that are bit-identical to the hook sequence:
+//   - IMEX stage with the linear column operator, direct Newton, max_iters = 1  -> cts_column_fused_stage
+//   - LSRK stage with the advection operator                                     -> cts_advection_fused_stage
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <limits>
+
+#include "cts_internal.h"
+
+namespace {
+
+// ---- update-signal handlers (update_signal_handler.jl:88-99) -----------------------------------
+bool signal_is_a(int signal, int target) {
+  if (signal == target) return true;
+  // EndOfStep <: EndOfStage <: WithDSS
+  if (signal == CTS_SIG_END_OF_STEP) return target == CTS_SIG_END_OF_STAGE || target == CTS_SIG_WITH_DSS;
+  if (signal == CTS_SIG_END_OF_STAGE) return target == CTS_SIG_WITH_DSS;
+  return false;
+}
+bool needs_update(const cts_update_handler& h, int signal, double t = 0.0) {
+  if (h.fn) return h.fn(h.ud, signal, t) != 0;
+  return signal_is_a(signal, h.every_signal);
+}
+bool fires_on_new_timestep(const cts_update_handler& h) {
+  // async_utils.jl:85-88: a host handler (UpdateEveryN/UpdateEveryDt) declares its signal in every_signal too
+  return h.every_signal == CTS_SIG_NEW_TIMESTEP;
+}
+
+#define HOOK(ctx, expr)                                                        \
+  do {                                                                         \
+    int _r = (expr);                                                           \
+    if (_r != 0) return cts_fail((ctx), CTS_ECALLBACK, std::string("hook failed: ") + #expr + " -> " + std::to_string(_r)); \
+  } while (0)
+
+}  // namespace
+
+// =============================================================================================
+// Newton / Krylov
+// =============================================================================================
+struct cts_newton_cache {
+  cts_ctx* ctx = nullptr;
+  cts_dtype ft = CTS_F64;
+  size_t n = 0;
+  cts_newton_config cfg{};
+  void* dx = nullptr;
+  void* f = nullptr;
+  void* W = nullptr;
+  cts_ldiv_fn ldiv = nullptr;
+  cts_ldiv_fn jac_mul = nullptr;
+  void* ud = nullptr;
+  // Krylov workspace
+  void* x2 = nullptr;
+  void* f2 = nullptr;
+  void* w = nullptr;
+  void* q = nullptr;
+  std::vector<void*> V;
+  double ew_prev_norm_f = 0.0, ew_prev_rtol = 0.0;
+  cts_solver_stats stats{};
+};
+
+namespace {
+
+using ResidualFn = std::function<int(void* f, const void* x)>;
+using JacFn = std::function<int(void* W, const void* x)>;
+using PrepareFn = std::function<int(void* x)>;
+
+int newton_alloc(cts_newton_cache* c) {
+  size_t bytes = c->n * cts_sizeof(c->ft);
+  CTS_TRY(cts_alloc(c->ctx, bytes, &c->dx));
+  CTS_TRY(cts_alloc(c->ctx, bytes, &c->f));
+  if (c->cfg.use_krylov) {
+    CTS_TRY(cts_alloc(c->ctx, bytes, &c->w));
+    CTS_TRY(cts_alloc(c->ctx, bytes, &c->q));
+    if (c->cfg.jacobian_free_jvp) {
+      CTS_TRY(cts_alloc(c->ctx, bytes, &c->x2));
+      CTS_TRY(cts_alloc(c->ctx, bytes, &c->f2));
+    }
+    int mem = c->cfg.memory > 0 ? c->cfg.memory : 20;
+    for (int i = 0; i < mem; ++i) {
+      void* v = nullptr;
+      CTS_TRY(cts_alloc(c->ctx, bytes, &v));
+      c->V.push_back(v);
+    }
+  }
+  return CTS_OK;
+}
+
+void newton_free(cts_newton_cache* c) {
+  for (void* p : {c->dx, c->f, c->x2, c->f2, c->w, c->q})
+    if (p) cts_free(c->ctx, p);
+  for (void* v : c->V) cts_free(c->ctx, v);
+  c->V.clear();
+}
+
+double eps_of(cts_dtype ft) { return ft == CTS_F64 ? std::numeric_limits<double>::epsilon() : (double)std::numeric_limits<float>::epsilon(); }
+double round_to(cts_dtype ft, double v) { return ft == CTS_F64 ? v : (double)(float)v; }
+
+size_t global_length(const cts_ctx* ctx, size_t n) {
+  size_t local = ctx->red_window ? ctx->red_count : n;
+  return local * (size_t)ctx->nranks;
+}
+
+// Krylov.jl sym_givens (real case): [c s; s -c][a; b] = [rho; 0]
+void sym_givens(double a, double b, double& c, double& s, double& rho) {
+  if (b == 0) {
+    c = (a == 0) ? 1.0 : std::copysign(1.0, a);
+    s = 0.0;
+    rho = std::fabs(a);
+  } else if (a == 0) {
+    c = 0.0;
+    s = std::copysign(1.0, b);
+    rho = std::fabs(b);
+  } else if (std::fabs(b) > std::fabs(a)) {
+    double t = a / b;
+    s = std::copysign(1.0, b) / std::sqrt(1 + t * t);
+    c = s * t;
+    rho = b / s;
+  } else {
+    double t = b / a;
+    c = std::copysign(1.0, a) / std::sqrt(1 + t * t);
+    s = c * t;
+    rho = a / c;
+  }
+}
+
+// ForwardDiffJVP step (newtons_method.jl:107-135,177)
+int jvp_step(cts_newton_cache* c, const void* dx, const void* x, double* eps_out) {
+  cts_ctx* ctx = c->ctx;
+  double e = 0, ndx = 0;
+  const double se = std::sqrt(eps_of(c->ft));
+  CTS_TRY(cts_nrm2(ctx, c->ft, c->n, dx, &ndx));
+  if (c->cfg.jvp_step_kind == 1) {
+    e = se / ndx;
+  } else if (c->cfg.jvp_step_kind == 2) {
+    double nx = 0;
+    CTS_TRY(cts_nrm2(ctx, c->ft, c->n, x, &nx));
+    e = std::sqrt(eps_of(c->ft) * (1 + nx)) / ndx;
+  } else {
+    double s1 = 0;
+    CTS_TRY(cts_sum1pabs(ctx, c->ft, c->n, x, &s1));
+    e = se * s1 / ((double)global_length(ctx, c->n) * ndx);
+  }
+  double adj = c->cfg.jvp_step_adjustment == 0.0 ? 1.0 : c->cfg.jvp_step_adjustment;
+  *eps_out = round_to(c->ft, round_to(c->ft, adj) * round_to(c->ft, e));
+  return CTS_OK;
+}
+
+int get_rtol(cts_newton_cache* c, const void* f, int n_iter, double* rtol_out) {
+  const cts_newton_config& k = c->cfg;
+  if (k.forcing_kind == CTS_FORCING_CONSTANT) {
+    *rtol_out = round_to(c->ft, k.forcing_rtol);
+    return CTS_OK;
+  }
+  double norm_f = 0;
+  CTS_TRY(cts_nrm2(c->ctx, c->ft, c->n, f, &norm_f));
+  double rtol;
+  if (n_iter == 0) {
+    rtol = k.ew_initial_rtol;
+  } else {
+    rtol = k.ew_gamma * std::pow(norm_f / c->ew_prev_norm_f, k.ew_alpha);
+    double min_rtol = k.ew_gamma * std::pow(c->ew_prev_rtol, k.ew_alpha);
+    if (min_rtol > k.ew_min_rtol_threshold) rtol = std::max(rtol, min_rtol);
+  }
+  rtol = std::min(rtol, k.ew_max_rtol);
+  c->ew_prev_norm_f = norm_f;
+  c->ew_prev_rtol = rtol;
+  *rtol_out = rtol;
+  return CTS_OK;
+}
+
+// GMRES (left preconditioned, no restart; vectors beyond `memory` are appended)
+int gmres(cts_newton_cache* c, const std::function<int(void* out, const void* v)>& matvec,
+          const std::function<int(void* out, const void* w)>* precond, const void* b, void* x, double rtol) {
+  cts_ctx* ctx = c->ctx;
+  const cts_dtype ft = c->ft;
+  const size_t n = c->n, bytes = n * cts_sizeof(ft);
+  void* w = c->w;
+  void* q = c->q;
+  // r0 = M^-1 b
+  const void* r0 = b;
+  if (precond) {
+    CTS_TRY((*precond)(q, b));
+    r0 = q;
+  }
+  double beta = 0;
+  CTS_TRY(cts_nrm2(ctx, ft, n, r0, &beta));
+  if (beta == 0) {  // "x = 0 is a zero-residual solution"
+    CTS_TRY(cts_memset_zero(ctx, x, bytes));
+    return CTS_OK;
+  }
+  double rNorm = beta;
+  const double eps_tol = 0.0 + rtol * beta;
+  const double btol = std::pow(eps_of(ft), 0.75);
+  const size_t itmax = c->cfg.itmax > 0 ? (size_t)c->cfg.itmax : 2 * global_length(ctx, n);
+  auto ensure_vec = [&](size_t k) -> int {
+    while (c->V.size() <= k) {
+      void* v = nullptr;
+      CTS_TRY(cts_alloc(ctx, bytes, &v));
+      c->V.push_back(v);
+    }
+    return CTS_OK;
+  };
+  CTS_TRY(ensure_vec(0));
+  CTS_TRY(cts_div_scalar(ctx, ft, n, c->V[0], r0, rNorm));
+  std::vector<double> z{beta}, cs, ss;
+  std::vector<std::vector<double>> R;
+  bool solved = rNorm <= eps_tol, breakdown = false;
+  size_t k = 0;
+  while (!(solved || k >= itmax || breakdown)) {
+    ++k;
+    c->stats.krylov_iters++;
+    CTS_TRY(matvec(w, c->V[k - 1]));
+    if (precond)
+      CTS_TRY((*precond)(q, w));
+    else
+      CTS_TRY(cts_memcpy_d2d(ctx, q, w, bytes));
+    std::vector<double> col(k);
+    if (c->cfg.batch_gram_schmidt) {  // classical GS: one fused sweep of k dots, then one k-term update
+      std::vector<const void*> Vp(c->V.begin(), c->V.begin() + k);
+      CTS_TRY(cts_multi_dot(ctx, ft, n, (int)k, Vp.data(), q, col.data()));
+      for (size_t i0 = 0; i0 < k; i0 += CTS_MAX_TERMS) {
+        int kk = (int)std::min<size_t>(CTS_MAX_TERMS, k - i0);
+        double coef[CTS_MAX_TERMS];
+        for (int i = 0; i < kk; ++i) coef[i] = -col[i0 + i];
+        CTS_TRY(cts_axpy_n(ctx, ft, n, q, nullptr, 1.0, q, kk, 0, coef, Vp.data() + i0, 0));
+      }
+    } else {  // modified GS (Krylov.jl order): k dependent dots
+      for (size_t i = 0; i < k; ++i) {
+        CTS_TRY(cts_dot(ctx, ft, n, c->V[i], q, &col[i]));
+        CTS_TRY(cts_axpby(ctx, ft, n, -col[i], c->V[i], 1.0, q));
+      }
+    }
+    double Hbis = 0;
+    CTS_TRY(cts_nrm2(ctx, ft, n, q, &Hbis));
+    for (size_t i = 0; i + 1 < k; ++i) {
+      double rtmp = cs[i] * col[i] + ss[i] * col[i + 1];
+      col[i + 1] = ss[i] * col[i] - cs[i] * col[i + 1];
+      col[i] = rtmp;
+    }
+    double cg, sg, rho;
+    sym_givens(col[k - 1], Hbis, cg, sg, rho);
+    col[k - 1] = rho;
+    cs.push_back(cg);
+    ss.push_back(sg);
+    R.push_back(col);
+    double zeta = sg * z[k - 1];
+    z[k - 1] = cg * z[k - 1];
+    rNorm = std::fabs(zeta);
+    solved = rNorm <= eps_tol || rNorm + 1 <= 1;
+    breakdown = Hbis <= btol;
+    if (!(solved || k >= itmax || breakdown)) {
+      CTS_TRY(ensure_vec(k));
+      CTS_TRY(cts_div_scalar(ctx, ft, n, c->V[k], q, Hbis));
+      z.push_back(zeta);
+    }
+  }
+  std::vector<double> y(k, 0.0);
+  for (size_t ii = k; ii-- > 0;) {
+    double acc = z[ii];
+    for (size_t j = ii + 1; j < k; ++j) acc -= R[j][ii] * y[j];
+    y[ii] = (std::fabs(R[ii][ii]) <= btol) ? 0.0 : acc / R[ii][ii];
+  }
+  std::vector<const void*> Vp(c->V.begin(), c->V.begin() + k);
+  CTS_TRY(cts_lincomb(ctx, ft, n, x, (int)k, y.data(), Vp.data(), 0));
+  return CTS_OK;
+}
+
+// solve_krylov! (newtons_method.jl:465-509)
+int solve_krylov(cts_newton_cache* c, void* dx, const void* x, const ResidualFn& f_, const void* f, int n_iter,
+                 const PrepareFn* prepare) {
+  cts_ctx* ctx = c->ctx;
+  const bool jfree = c->cfg.jacobian_free_jvp != 0;
+  std::function<int(void*, const void*)> matvec = [&](void* out, const void* v) -> int {
+    if (!jfree) {
+      if (!c->jac_mul || !c->W) return cts_fail(ctx, CTS_EINVAL, "GMRES without JVP needs mul!(y, W, x)");
+      HOOK(ctx, c->jac_mul(c->ud, out, c->W, v));
+      return CTS_OK;
+    }
+    double e = 0;  // jvp! :173-182
+    CTS_TRY(jvp_step(c, v, x, &e));
+    CTS_TRY(cts_jvp_perturb(ctx, c->ft, c->n, c->x2, x, e, v));
+    if (prepare) CTS_TRY((*prepare)(c->x2));
+    CTS_TRY(f_(c->f2, c->x2));
+    c->stats.f_evals++;
+    c->stats.jvp_evals++;
+    CTS_TRY(cts_jvp_quotient(ctx, c->ft, c->n, out, c->f2, f, e));
+    return CTS_OK;
+  };
+  const bool use_M = !(c->cfg.disable_preconditioner || !c->W || !jfree);
+  std::function<int(void*, const void*)> precond = [&](void* out, const void* w) -> int {
+    HOOK(ctx, c->ldiv(c->ud, out, c->W, w));
+    c->stats.ldiv_calls++;
+    return CTS_OK;
+  };
+  double rtol = 0;
+  CTS_TRY(get_rtol(c, f, n_iter, &rtol));
+  return gmres(c, matvec, use_M ? &precond : nullptr, f, dx, rtol);
+}
+
+// solve_newton! (newtons_method.jl:609-665); no line search, no convergence checker
+int solve_newton(cts_newton_cache* c, void* x, const ResidualFn& f_, const JacFn* j_, const PrepareFn* prepare) {
+  cts_ctx* ctx = c->ctx;
+  const cts_newton_config& cfg = c->cfg;
+  const bool has_j = c->W != nullptr && j_ != nullptr;
+  if (has_j && needs_update(cfg.update_j, CTS_SIG_NEW_NEWTON_SOLVE)) {
+    CTS_TRY((*j_)(c->W, x));
+    c->stats.wfact_evals++;
+  }
+  CTS_TRY(f_(c->f, x));
+  c->stats.f_evals++;
+  for (int n = 1; n <= cfg.max_iters; ++n) {
+    c->stats.newton_iters++;
+    if (has_j && needs_update(cfg.update_j, CTS_SIG_NEW_NEWTON_ITERATION)) {
+      CTS_TRY((*j_)(c->W, x));
+      c->stats.wfact_evals++;
+    }
+    if (!cfg.use_krylov) {
+      if (!c->ldiv || !c->W) return cts_fail(ctx, CTS_EINVAL, "direct Newton needs ldiv! and a Jacobian");
+      HOOK(ctx, c->ldiv(c->ud, c->dx, c->W, c->f));
+      c->stats.ldiv_calls++;
+    } else {
+      CTS_TRY(solve_krylov(c, c->dx, x, f_, c->f, n - 1, prepare));
+    }
+    CTS_TRY(cts_sub_inplace(ctx, c->ft, c->n, x, c->dx));  // K5
+    if (n < cfg.max_iters) {
+      if (prepare) CTS_TRY((*prepare)(x));
+      CTS_TRY(f_(c->f, x));
+      c->stats.f_evals++;
+    }
+  }
+  return CTS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cts_newton_cache_create(cts_ctx* ctx, cts_dtype ft, size_t n, const cts_newton_config* cfg, void* W, cts_ldiv_fn ldiv,
+                            cts_ldiv_fn jac_mul, void* ud, cts_newton_cache** out) {
+  CTS_CHECK_CTX(ctx);
+  if (!cfg || !out || n == 0) return cts_fail(ctx, CTS_EINVAL, "cts_newton_cache_create: bad argument");
+  // newtons_method.jl:585-588: a Jacobian is required unless the Krylov method is Jacobian free
+  if (!W && !(cfg->use_krylov && cfg->jacobian_free_jvp))
+    return cts_fail(ctx, CTS_EINVAL, "NewtonsMethod needs a jac_prototype unless a JacobianFreeJVP is used");
+  auto* c = new cts_newton_cache();
+  c->ctx = ctx;
+  c->ft = ft;
+  c->n = n;
+  c->cfg = *cfg;
+  c->W = W;
+  c->ldiv = ldiv;
+  c->jac_mul = jac_mul;
+  c->ud = ud;
+  int r = newton_alloc(c);
+  if (r) {
+    newton_free(c);
+    delete c;
+    return r;
+  }
+  *out = c;
+  return CTS_OK;
+}
+
+int cts_newton_cache_destroy(cts_newton_cache* c) {
+  if (!c) return CTS_EINVAL;
+  newton_free(c);
+  delete c;
+  return CTS_OK;
+}
+
+int cts_newton_solve(cts_newton_cache* c, void* x, cts_residual_fn f, cts_jac_fn j, cts_prepare_fn prepare, void* ud) {
+  if (!c || !x || !f) return CTS_EINVAL;
+  cts_ctx* ctx = c->ctx;
+  ResidualFn f_ = [&](void* fo, const void* xx) -> int {
+    HOOK(ctx, f(ud, fo, xx));
+    return CTS_OK;
+  };
+  JacFn j_ = [&](void* W, const void* xx) -> int {
+    HOOK(ctx, j(ud, W, xx));
+    return CTS_OK;
+  };
+  PrepareFn p_ = [&](void* xx) -> int {
+    HOOK(ctx, prepare(ud, xx));
+    return CTS_OK;
+  };
+  return solve_newton(c, x, f_, j ? &j_ : nullptr, prepare ? &p_ : nullptr);
+}
+
+int cts_newton_cache_stats(cts_newton_cache* c, cts_solver_stats* out) {
+  if (!c || !out) return CTS_EINVAL;
+  *out = c->stats;
+  return CTS_OK;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// IMEX ARK / SSPRK
+// =============================================================================================
+struct cts_imex_cache {
+  cts_ctx* ctx = nullptr;
+  cts_dtype ft = CTS_F64;
+  size_t n = 0;
+  cts_imex_tableau tab{};
+  int constraint = 0;
+  cts_ode_function f{};
+  cts_newton_config ncfg{};
+  cts_newton_cache* nm = nullptr;
+  bool has_gamma = false;
+  double gamma = 0.0;
+  bool fusion = true;
+  // ARK
+  void* U = nullptr;
+  void* temp = nullptr;
+  void* T_exp[CTS_MAX_STAGES] = {};
+  void* T_lim[CTS_MAX_STAGES] = {};
+  void* T_imp[CTS_MAX_STAGES] = {};
+  // SSPRK
+  void* U_exp = nullptr;
+  void* U_lim = nullptr;
+  void* T_exp1 = nullptr;
+  void* T_lim1 = nullptr;
+  double beta[CTS_MAX_STAGES] = {};
+  int nbuffers = 0;
+  cts_solver_stats stats{};
+};
+
+namespace {
+
+inline double A(const double* a, int s, int i, int j) { return a[i * s + j]; }
+
+bool col_nonzero(const double* a, int s, int j) {
+  for (int i = 0; i < s; ++i)
+    if (A(a, s, i, j) != 0) return true;
+  return false;
+}
+
+bool is_fsal(const cts_imex_tableau& t) {
+  for (int j = 0; j < t.s; ++j)
+    if (t.b_exp[j] != A(t.a_exp, t.s, t.s - 1, j) || t.b_imp[j] != A(t.a_imp, t.s, t.s - 1, j)) return false;
+  return true;
+}
+
+int alloc_state(cts_imex_cache* c, void** p) {
+  CTS_TRY(cts_alloc(c->ctx, c->n * cts_sizeof(c->ft), p));
+  c->nbuffers++;
+  return CTS_OK;
+}
+
+// coefficient fl(dt * a) in the tableau eltype (fused_increment.jl:58,115-116)
+double coef_of(const cts_imex_cache* c, double dt, double a) {
+  if (c->tab.cast_to_state_eltype && c->ft == CTS_F32) return (double)((float)dt * (float)a);
+  return dt * a;
+}
+int native_flag(const cts_imex_cache* c) { return (c->tab.cast_to_state_eltype && c->ft == CTS_F32) ? 1 : 0; }
+
+struct Increment {  // a fused_raw_increment: the non-zero (coef, tendency) pairs, NullBroadcasted when n == 0
+  int n = 0;
+  double coef[CTS_MAX_STAGES];
+  const void* term[CTS_MAX_STAGES];
+};
+
+Increment raw_increment(const cts_imex_cache* c, double dt, const double* coefs, int count, void* const* tend) {
+  Increment inc;
+  for (int j = 0; j < count; ++j) {
+    if (coefs[j] == 0) continue;
+    inc.coef[inc.n] = coef_of(c, dt, coefs[j]);
+    inc.term[inc.n] = tend[j];
+    inc.n++;
+  }
+  return inc;
+}
+
+// assign_with_increments!(out, base, inc_exp, inc_imp)  (fused_increment.jl:220-236)
+int assign_with_increments(cts_imex_cache* c, void* out, void* out2, double c0, const void* base, const Increment& g1,
+                           const Increment& g2) {
+  double coef[CTS_MAX_TERMS];
+  const void* terms[CTS_MAX_TERMS];
+  int k = 0;
+  for (int j = 0; j < g1.n; ++j, ++k) {
+    coef[k] = g1.coef[j];
+    terms[k] = g1.term[j];
+  }
+  for (int j = 0; j < g2.n; ++j, ++k) {
+    coef[k] = g2.coef[j];
+    terms[k] = g2.term[j];
+  }
+  if (k == 0 && out == base && c0 == 1.0 && !out2) return CTS_OK;  // `@. u = u`
+  return cts_axpy_n(c->ctx, c->ft, c->n, out, out2, c0, base, g1.n, g2.n, coef, terms, native_flag(c));
+}
+
+int maybe_update_jacobian(cts_imex_cache* c, const void* u, double t, double dt) {  // async_utils.jl:11-31
+  if (!c->f.T_imp || !c->ncfg.present || !c->nm || !c->nm->W) return CTS_OK;
+  if (!needs_update(c->ncfg.update_j, CTS_SIG_NEW_TIMESTEP, t)) return CTS_OK;
+  HOOK(c->ctx, c->f.Wfact(c->f.ud, c->nm->W, u, dt * c->gamma, t));
+  c->stats.wfact_evals++;
+  return CTS_OK;
+}
+
+int call_dss(cts_imex_cache* c, void* u, double t) {
+  if (c->f.dss) {
+    HOOK(c->ctx, c->f.dss(c->f.ud, u, t));
+    c->stats.dss_calls++;
+  }
+  return CTS_OK;
+}
+int call_state(cts_imex_cache* c, cts_state_fn fn, void* u, double t) {
+  if (fn) HOOK(c->ctx, fn(c->f.ud, u, t));
+  return CTS_OK;
+}
+
+// solve_implicit_equation! (imex_ark.jl:283-308)
+int solve_implicit_equation(cts_imex_cache* c, void* U, const void* U0, double t_imp, double dtg) {
+  cts_ctx* ctx = c->ctx;
+  ResidualFn f_ = [&](void* res, const void* Up) -> int {
+    HOOK(ctx, c->f.T_imp(c->f.ud, res, Up, t_imp));
+    return cts_newton_residual(ctx, c->ft, c->n, res, U0, dtg, Up);  // K3
+  };
+  JacFn j_ = [&](void* W, const void* Up) -> int {
+    HOOK(ctx, c->f.Wfact(c->f.ud, W, Up, dtg, t_imp));
+    return CTS_OK;
+  };
+  PrepareFn p_ = [&](void* Up) -> int { return call_state(c, c->f.cache_imp, Up, t_imp); };
+  return solve_newton(c->nm, U, f_, c->f.Wfact ? &j_ : nullptr, &p_);
+}
+
+// Is the implicit stage eligible for the fused column kernel?
+cts_op_column* fusable_column_op(const cts_imex_cache* c) {
+  const cts_ode_function& f = c->f;
+  if (!c->fusion || !c->ncfg.present || c->ncfg.max_iters != 1 || c->ncfg.use_krylov) return nullptr;
+  if (f.T_imp != cts_op_column_T_imp || f.Wfact != cts_op_column_Wfact || f.ldiv != cts_op_column_ldiv) return nullptr;
+  if (f.has_lim) return nullptr;
+  if (f.dss && f.dss != cts_op_column_dss) return nullptr;  // the library dss! only rewrites ghost rows
+  if (f.constrain_state || f.cache || f.cache_imp || f.initialize_imp) return nullptr;
+  auto* op = static_cast<cts_op_column*>(f.ud);
+  if (!op || !cts_column_fusable(op) || cts_op_column_ctx(op) != c->ctx || cts_op_column_dtype(op) != c->ft) return nullptr;
+  if (cts_op_column_ndof(op) != c->n) return nullptr;
+  return op;
+}
+
+int fused_implicit_stage(cts_imex_cache* c, cts_op_column* op, void* U, double c0, const void* base, const Increment& g1,
+                         const Increment& g2, double dtg, double t_imp, void* T_imp_out) {
+  // Jacobian refresh exactly when the reference would do it inside solve_newton! (the linear operator's W
+  // does not depend on the state, so the stage value is not needed to build it).
+  const bool mf = cts_op_column_matrix_free(op);
+  if (needs_update(c->ncfg.update_j, CTS_SIG_NEW_NEWTON_SOLVE) || needs_update(c->ncfg.update_j, CTS_SIG_NEW_NEWTON_ITERATION)) {
+    if (!mf) HOOK(c->ctx, c->f.Wfact(c->f.ud, c->nm->W, base, dtg, t_imp));
+    c->stats.wfact_evals++;
+  }
+  cts_fused_stage_args a{};
+  a.base = base;
+  a.c0 = c0;
+  a.n_grp1 = g1.n;
+  a.n_grp2 = g2.n;
+  int k = 0;
+  for (int j = 0; j < g1.n; ++j, ++k) {
+    a.coef[k] = g1.coef[j];
+    a.terms[k] = g1.term[j];
+  }
+  for (int j = 0; j < g2.n; ++j, ++k) {
+    a.coef[k] = g2.coef[j];
+    a.terms[k] = g2.term[j];
+  }
+  a.compute_native = native_flag(c);
+  a.dtgamma = dtg;
+  a.W = static_cast<const cts_tridiag*>(c->nm->W);
+  a.U = U;
+  a.T_imp = T_imp_out;
+  a.temp = nullptr;
+  CTS_TRY(cts_column_fused_stage(op, &a));
+  c->stats.fused_stage_launches++;
+  c->stats.newton_iters++;
+  return CTS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// step_u!(integrator, cache::IMEXARKCache)   imex_ark.jl:69-272
+// ---------------------------------------------------------------------------------------------
+int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
+  const cts_imex_tableau& tab = c->tab;
+  const cts_ode_function& f = c->f;
+  const int s = tab.s;
+  const bool has_T_exp = f.T_exp_T_lim != nullptr;
+  const bool has_T_imp = f.T_imp != nullptr;
+  cts_op_column* fuse_op = fusable_column_op(c);
+  // (a matrix-free fused stage regenerates W in the kernel: the stored copy is never read)
+  if (!(fuse_op && cts_op_column_matrix_free(fuse_op))) CTS_TRY(maybe_update_jacobian(c, u, t, dt));
+
+  for (int i = 0; i < s; ++i) {
+    const double t_exp = t + dt * tab.c_exp[i];
+    const double t_imp = t + dt * tab.c_imp[i];
+    const double dtg = dt * A(tab.a_imp, s, i, i);
+    const bool no_imp = !has_T_imp || dtg == 0;
+    const bool has_exp_terms = col_nonzero(tab.a_exp, s, i) || tab.b_exp[i] != 0;
+    const bool has_imp_terms = col_nonzero(tab.a_imp, s, i) || tab.b_imp[i] != 0;
+    void* U = c->U;
+
+    // compute_stage_value!  :140-165
+    Increment inc_exp = has_T_exp ? raw_increment(c, dt, &tab.a_exp[i * s], i, c->T_exp) : Increment{};
+    Increment inc_imp = has_T_imp ? raw_increment(c, dt, &tab.a_imp[i * s], i, c->T_imp) : Increment{};
+
+    bool stage_done = false;
+    if (fuse_op && !no_imp) {
+      // K1 + Newton + K6 in one kernel; the pre-Newton dss! calls only rewrite ghost rows that the column
+      // solve never reads, so one post-Newton dss! leaves every owned DOF bit-identical.
+      CTS_TRY(fused_implicit_stage(c, fuse_op, U, 1.0, u, inc_exp, inc_imp, dtg, t_imp, has_imp_terms ? c->T_imp[i] : nullptr));
+      CTS_TRY(call_dss(c, U, t_imp));
+      stage_done = true;
+    } else if (fuse_op && no_imp && i == 0 && inc_exp.n == 0 && inc_imp.n == 0) {
+      U = u;  // `@. U = u` followed only by tendency evaluations: alias instead of copying
+    } else if (f.has_lim) {
+      Increment inc_lim = raw_increment(c, dt, &tab.a_exp[i * s], i, c->T_lim);
+      CTS_TRY(assign_with_increments(c, U, nullptr, 1.0, u, inc_lim, Increment{}));  // assign_fused_increment! :159
+      if (i != 0 && f.lim) HOOK(c->ctx, f.lim(f.ud, U, t_exp, u));
+      CTS_TRY(assign_with_increments(c, U, nullptr, 1.0, U, inc_exp, inc_imp));
+    } else {
+      CTS_TRY(assign_with_increments(c, U, nullptr, 1.0, u, inc_exp, inc_imp));
+    }
+
+    // solve_stage_implicit!  :174-242
+    if (!stage_done) {
+      const int top_sig = no_imp ? CTS_SIG_END_OF_STAGE : CTS_SIG_WITH_DSS;
+      if (i != 0) {
+        CTS_TRY(call_dss(c, U, t_exp));
+        if (needs_update(f.update_constrain_state, top_sig)) CTS_TRY(call_state(c, f.constrain_state, U, t_exp));
+        if (no_imp && needs_update(f.update_cache, CTS_SIG_END_OF_STAGE)) CTS_TRY(call_state(c, f.cache, U, t_exp));
+      }
+      if (!no_imp) {
+        if (!c->ncfg.present || !c->nm) return cts_fail(c->ctx, CTS_EINVAL, "implicit stage without a NewtonsMethod");
+        CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->temp, nullptr, 1.0, U, 0, 0, nullptr, nullptr, 0));  // K2 :209
+        if (!f.initialize_imp_is_nothing) {
+          if (f.initialize_imp) HOOK(c->ctx, f.initialize_imp(f.ud, U, dtg));
+          CTS_TRY(call_dss(c, U, t_exp));
+          if (needs_update(f.update_constrain_state, CTS_SIG_WITH_DSS)) CTS_TRY(call_state(c, f.constrain_state, U, t_exp));
+          CTS_TRY(call_state(c, f.cache_imp, U, t_imp));
+        } else if (i != 0) {
+          CTS_TRY(call_state(c, f.cache_imp, U, t_imp));
+        }
+        CTS_TRY(solve_implicit_equation(c, U, c->temp, t_imp, dtg));
+        CTS_TRY(call_dss(c, U, t_imp));
+        if (!(i == s - 1 && is_fsal(tab))) {
+          if (needs_update(f.update_constrain_state, CTS_SIG_END_OF_STAGE)) CTS_TRY(call_state(c, f.constrain_state, U, t_imp));
+          if (needs_update(f.update_cache, CTS_SIG_END_OF_STAGE)) CTS_TRY(call_state(c, f.cache, U, t_imp));
+        }
+      }
+    }
+
+    // evaluate_stage_tendencies!  :252-272
+    if (has_exp_terms && f.T_exp_T_lim) HOOK(c->ctx, f.T_exp_T_lim(f.ud, c->T_exp[i], c->T_lim[i], U, t_exp));
+    if (has_imp_terms && has_T_imp && !stage_done) {
+      if (dtg == 0)
+        HOOK(c->ctx, f.T_imp(f.ud, c->T_imp[i], U, t_imp));
+      else
+        CTS_TRY(cts_timp_from_stage(c->ctx, c->ft, c->n, c->T_imp[i], U, c->temp, dtg));  // K6 :269
+    }
+  }
+
+  // final update :79-101
+  const double t_final = t + dt;
+  Increment inc_exp = has_T_exp ? raw_increment(c, dt, tab.b_exp, s, c->T_exp) : Increment{};
+  Increment inc_imp = has_T_imp ? raw_increment(c, dt, tab.b_imp, s, c->T_imp) : Increment{};
+  if (f.has_lim) {
+    Increment inc_lim = raw_increment(c, dt, tab.b_exp, s, c->T_lim);
+    CTS_TRY(assign_with_increments(c, c->temp, nullptr, 1.0, u, inc_lim, Increment{}));
+    if (f.lim) HOOK(c->ctx, f.lim(f.ud, c->temp, t_final, u));
+    CTS_TRY(assign_with_increments(c, u, nullptr, 1.0, c->temp, inc_exp, inc_imp));
+  } else {
+    CTS_TRY(assign_with_increments(c, u, nullptr, 1.0, u, inc_exp, inc_imp));
+  }
+  CTS_TRY(call_dss(c, u, t_final));
+  if (needs_update(f.update_constrain_state, CTS_SIG_END_OF_STEP)) CTS_TRY(call_state(c, f.constrain_state, u, t_final));
+  if (needs_update(f.update_cache, CTS_SIG_END_OF_STEP)) CTS_TRY(call_state(c, f.cache, u, t_final));
+  return CTS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// step_u!(integrator, cache::IMEXSSPRKCache)   imex_ssprk.jl:95-220
+// ---------------------------------------------------------------------------------------------
+// `@. x = x + dt * T` in promote(typeof(dt), FT)   (imex_ssprk.jl:112,117,158,163)
+int axpy_dt(cts_imex_cache* c, void* out, const void* x, double dt, const void* T, int dt_is_f32) {
+  double coef[1] = {dt};
+  const void* terms[1] = {T};
+  int native = (dt_is_f32 && c->ft == CTS_F32) ? 1 : 0;
+  return cts_axpy_n(c->ctx, c->ft, c->n, out, nullptr, 1.0, x, 1, 0, coef, terms, native);
+}
+
+int ssprk_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
+  const cts_imex_tableau& tab = c->tab;
+  const cts_ode_function& f = c->f;
+  const int s = tab.s;
+  const bool has_T_exp = f.T_exp_T_lim != nullptr;
+  const bool has_T_imp = f.T_imp != nullptr;
+  const int native = native_flag(c);
+  cts_op_column* fuse_op = fusable_column_op(c);
+  auto beta_c = [&](double b) { return native ? (double)(float)b : b; };
+  if (!(fuse_op && cts_op_column_matrix_free(fuse_op))) CTS_TRY(maybe_update_jacobian(c, u, t, dt));
+
+  for (int i = 0; i < s; ++i) {
+    const double t_exp = t + dt * tab.c_exp[i];
+    const double t_imp = t + dt * tab.c_imp[i];
+    const double aii = A(tab.a_imp, s, i, i);
+    const double dtg = dt * aii;
+    if (i == 0) {
+      CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->U_exp, nullptr, 1.0, u, 0, 0, nullptr, nullptr, 0));  // :155
+    } else if (c->beta[i - 1] != 0) {
+      if (f.has_lim) {
+        CTS_TRY(axpy_dt(c, c->U_lim, c->U_exp, dt, c->T_lim1, dt_is_f32));
+        if (f.lim) HOOK(c->ctx, f.lim(f.ud, c->U_lim, t_exp, c->U_exp));
+        CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->U_exp, nullptr, 1.0, c->U_lim, 0, 0, nullptr, nullptr, 0));
+      }
+      if (has_T_exp) CTS_TRY(axpy_dt(c, c->U_exp, c->U_exp, dt, c->T_exp1, dt_is_f32));
+      // `@. U_exp = (1 - β) * u + β * U_exp`  :165
+      const double b = beta_c(c->beta[i - 1]);
+      const double omb = native ? (double)(1.0f - (float)b) : 1.0 - b;
+      double coef[1] = {b};
+      const void* terms[1] = {c->U_exp};
+      CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->U_exp, nullptr, omb, u, 1, 0, coef, terms, native));
+      // NB: c0 == 1 would skip the multiply; (1-β) == 1 only when β == 0, which this branch excludes.
+    }
+    Increment inc_imp = has_T_imp ? raw_increment(c, dt, &tab.a_imp[i * s], i, c->T_imp) : Increment{};
+    const bool no_imp = !has_T_imp || aii == 0;
+    const bool has_imp_terms = col_nonzero(tab.a_imp, s, i) || tab.b_imp[i] != 0;
+    bool stage_done = false;
+    if (fuse_op && !no_imp) {
+      CTS_TRY(fused_implicit_stage(c, fuse_op, c->U, 1.0, c->U_exp, inc_imp, Increment{}, dtg, t_imp,
+                                   has_imp_terms ? c->T_imp[i] : nullptr));
+      CTS_TRY(call_dss(c, c->U, t_imp));
+      stage_done = true;
+    } else {
+      CTS_TRY(assign_with_increments(c, c->U, nullptr, 1.0, c->U_exp, inc_imp, Increment{}));  // :169
+    }
+    if (!stage_done) {
+      const int top_sig = no_imp ? CTS_SIG_END_OF_STAGE : CTS_SIG_WITH_DSS;
+      if (i != 0) {
+        CTS_TRY(call_dss(c, c->U, t_exp));
+        if (needs_update(f.update_constrain_state, top_sig)) CTS_TRY(call_state(c, f.constrain_state, c->U, t_exp));
+        if (no_imp && needs_update(f.update_cache, CTS_SIG_END_OF_STAGE)) CTS_TRY(call_state(c, f.cache, c->U, t_exp));
+      }
+      if (!no_imp) {
+        if (!c->ncfg.present || !c->nm) return cts_fail(c->ctx, CTS_EINVAL, "implicit stage without a NewtonsMethod");
+        if (i != 0) CTS_TRY(call_state(c, f.cache_imp, c->U, t_imp));
+        CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->temp, nullptr, 1.0, c->U, 0, 0, nullptr, nullptr, 0));  // :190
+        CTS_TRY(solve_implicit_equation(c, c->U, c->temp, t_imp, dtg));
+        CTS_TRY(call_dss(c, c->U, t_imp));
+        if (needs_update(f.update_constrain_state, CTS_SIG_END_OF_STAGE)) CTS_TRY(call_state(c, f.constrain_state, c->U, t_imp));
+        if (needs_update(f.update_cache, CTS_SIG_END_OF_STAGE)) CTS_TRY(call_state(c, f.cache, c->U, t_imp));
+      }
+    }
+    if (c->beta[i] != 0 && f.T_exp_T_lim) HOOK(c->ctx, f.T_exp_T_lim(f.ud, c->T_exp1, c->T_lim1, c->U, t_exp));
+    if (has_imp_terms && has_T_imp && !stage_done) {
+      if (aii == 0)
+        HOOK(c->ctx, f.T_imp(f.ud, c->T_imp[i], c->U, t_imp));
+      else
+        CTS_TRY(cts_timp_from_stage(c->ctx, c->ft, c->n, c->T_imp[i], c->U, c->temp, dtg));
+    }
+  }
+
+  const double t_final = t + dt;
+  Increment inc_imp = has_T_imp ? raw_increment(c, dt, tab.b_imp, s, c->T_imp) : Increment{};
+  if (c->beta[s - 1] != 0) {
+    if (f.has_lim) {
+      CTS_TRY(axpy_dt(c, c->U_lim, c->U_exp, dt, c->T_lim1, dt_is_f32));
+      if (f.lim) HOOK(c->ctx, f.lim(f.ud, c->U_lim, t_final, c->U_exp));
+      CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->U_exp, nullptr, 1.0, c->U_lim, 0, 0, nullptr, nullptr, 0));
+    }
+    if (has_T_exp) CTS_TRY(axpy_dt(c, c->U_exp, c->U_exp, dt, c->T_exp1, dt_is_f32));
+    // `@. u = (1 - β) * u + β * U_exp + inc_imp`  :120-122
+    const double b = beta_c(c->beta[s - 1]);
+    const double omb = native ? (double)(1.0f - (float)b) : 1.0 - b;
+    Increment g1;
+    g1.n = 1;
+    g1.coef[0] = b;
+    g1.term[0] = c->U_exp;
+    CTS_TRY(assign_with_increments(c, u, nullptr, omb, u, g1, inc_imp));
+  } else if (inc_imp.n > 0) {
+    CTS_TRY(assign_with_increments(c, u, nullptr, 1.0, u, inc_imp, Increment{}));
+  }
+  CTS_TRY(call_dss(c, u, t_final));
+  if (needs_update(f.update_constrain_state, CTS_SIG_END_OF_STEP)) CTS_TRY(call_state(c, f.constrain_state, u, t_final));
+  if (needs_update(f.update_cache, CTS_SIG_END_OF_STEP)) CTS_TRY(call_state(c, f.cache, u, t_final));
+  return CTS_OK;
+}
+
+void imex_free(cts_imex_cache* c) {
+  auto fr = [&](void* p) {
+    if (p) cts_free(c->ctx, p);
+  };
+  fr(c->U);
+  fr(c->temp);
+  fr(c->U_exp);
+  fr(c->U_lim);
+  fr(c->T_exp1);
+  fr(c->T_lim1);
+  for (int i = 0; i < CTS_MAX_STAGES; ++i) {
+    fr(c->T_exp[i]);
+    fr(c->T_lim[i]);
+    fr(c->T_imp[i]);
+  }
+  if (c->nm) cts_newton_cache_destroy(c->nm);
+}
+
+}  // namespace
+
+extern "C" {
+
+int cts_imex_cache_create(cts_ctx* ctx, cts_dtype ft, size_t n, const cts_imex_tableau* tab, int constraint,
+                          const cts_ode_function* f, const cts_newton_config* newton, cts_imex_cache** out) {
+  CTS_CHECK_CTX(ctx);
+  if (!tab || !f || !out || n == 0 || tab->s < 1 || tab->s > CTS_MAX_STAGES)
+    return cts_fail(ctx, CTS_EINVAL, "cts_imex_cache_create: bad argument");
+  const int s = tab->s;
+  // IMEXTableau asserts (imex_tableaus.jl:71-72): a_exp strictly lower, a_imp lower triangular
+  for (int i = 0; i < s; ++i)
+    for (int j = i; j < s; ++j)
+      if (A(tab->a_exp, s, i, j) != 0 || (j > i && A(tab->a_imp, s, i, j) != 0))
+        return cts_fail(ctx, CTS_EINVAL, "IMEXTableau: a_exp must be strictly lower and a_imp lower triangular");
+  auto* c = new cts_imex_cache();
+  c->ctx = ctx;
+  c->ft = ft;
+  c->n = n;
+  c->tab = *tab;
+  c->constraint = constraint;
+  c->f = *f;
+  if (newton) c->ncfg = *newton;
+  auto fail = [&](int code, const char* msg) {
+    imex_free(c);
+    delete c;
+    return cts_fail(ctx, code, msg);
+  };
+  // γ detection (imex_ark.jl:49-51) + check_sdirk_compat (async_utils.jl:93-98)
+  {
+    double uniq[CTS_MAX_STAGES];
+    int nu = 0;
+    for (int i = 0; i < s; ++i) {
+      double g = A(tab->a_imp, s, i, i);
+      if (g == 0) continue;
+      bool seen = false;
+      for (int k = 0; k < nu; ++k) seen = seen || uniq[k] == g;
+      if (!seen) uniq[nu++] = g;
+    }
+    c->has_gamma = nu == 1;
+    c->gamma = nu == 1 ? uniq[0] : 0.0;
+    if (!c->has_gamma && c->ncfg.present && fires_on_new_timestep(c->ncfg.update_j))
+      return fail(CTS_EINVAL, "the tableau has implicit stages with distinct coefficients (it is not SDIRK): do not update on the NewTimeStep signal");
+  }
+  int r = CTS_OK;
+  auto need = [&](void** p) {
+    if (r == CTS_OK) r = alloc_state(c, p);
+  };
+  if (constraint == 0) {
+    need(&c->U);
+    need(&c->temp);
+    for (int i = 0; i < s; ++i) {
+      if (col_nonzero(tab->a_exp, s, i) || tab->b_exp[i] != 0) {
+        need(&c->T_exp[i]);
+        if (f->has_lim) need(&c->T_lim[i]);  // (the reference allocates these even without a limiter, imex_ark.jl:45)
+      }
+      if (col_nonzero(tab->a_imp, s, i) || tab->b_imp[i] != 0) need(&c->T_imp[i]);
+    }
+  } else {
+    // Shu-Osher β and the low-storage check (imex_ssprk.jl:48-65)
+    double ahat[(CTS_MAX_STAGES + 1) * CTS_MAX_STAGES];
+    for (int i = 0; i < s; ++i)
+      for (int j = 0; j < s; ++j) ahat[i * s + j] = A(tab->a_exp, s, i, j);
+    for (int j = 0; j < s; ++j) ahat[s * s + j] = tab->b_exp[j];
+    for (int i = 0; i < s; ++i) c->beta[i] = ahat[(i + 1) * s + i];
+    for (int i = 0; i < s; ++i) {
+      double prod = 1.0;
+      for (int k = i; k < s; ++k) {
+        prod = (k == i) ? c->beta[k] : prod * c->beta[k];
+        if (ahat[(k + 1) * s + i] != prod)
+          return fail(CTS_EINVAL, "The SSP IMEXAlgorithm only supports a low-storage IMEX SSPRK tableau (imex_ssprk.jl:51-64)");
+      }
+    }
+    need(&c->U);
+    need(&c->U_exp);
+    need(&c->T_exp1);
+    need(&c->temp);
+    if (f->has_lim) {
+      need(&c->U_lim);
+      need(&c->T_lim1);
+    }
+    for (int i = 0; i < s; ++i)
+      if (col_nonzero(tab->a_imp, s, i) || tab->b_imp[i] != 0) need(&c->T_imp[i]);
+  }
+  if (r != CTS_OK) {
+    imex_free(c);
+    delete c;
+    return r;
+  }
+  if (f->T_imp && c->ncfg.present) {
+    const bool has_jac = f->Wfact != nullptr && f->W != nullptr;
+    r = cts_newton_cache_create(ctx, ft, n, &c->ncfg, has_jac ? f->W : nullptr, f->ldiv, f->jac_mul, f->ud, &c->nm);
+    if (r != CTS_OK) {
+      std::string msg = ctx->err;
+      imex_free(c);
+      delete c;
+      return cts_fail(ctx, r, msg);
+    }
+    c->nbuffers += 2;  // Δx, f
+  }
+  *out = c;
+  return CTS_OK;
+}
+
+int cts_imex_cache_destroy(cts_imex_cache* c) {
+  if (!c) return CTS_EINVAL;
+  imex_free(c);
+  delete c;
+  return CTS_OK;
+}
+
+int cts_imex_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
+  if (!c || !u) return CTS_EINVAL;
+  return c->constraint == 0 ? ark_step(c, u, t, dt) : ssprk_step(c, u, t, dt, dt_is_f32);
+}
+
+int cts_imex_cache_buffer(cts_imex_cache* c, const char* name, void** dptr) {
+  if (!c || !name || !dptr) return CTS_EINVAL;
+  *dptr = nullptr;
+  std::string s(name);
+  auto idx = [&](const std::string& prefix) -> int {
+    if (s.size() <= prefix.size() || s.compare(0, prefix.size(), prefix) != 0) return -1;
+    int i = atoi(s.c_str() + prefix.size());
+    return (i >= 1 && i <= CTS_MAX_STAGES) ? i - 1 : -1;
+  };
+  if (s == "U") *dptr = c->U;
+  else if (s == "temp") *dptr = c->temp;
+  else if (s == "U_exp") *dptr = c->U_exp;
+  else if (s == "U_lim") *dptr = c->U_lim;
+  else if (s == "T_exp") *dptr = c->T_exp1;
+  else if (s == "T_lim") *dptr = c->T_lim1;
+  else if (s == "dx") *dptr = c->nm ? c->nm->dx : nullptr;
+  else if (s == "f") *dptr = c->nm ? c->nm->f : nullptr;
+  else if (idx("T_exp") >= 0) *dptr = c->T_exp[idx("T_exp")];
+  else if (idx("T_lim") >= 0) *dptr = c->T_lim[idx("T_lim")];
+  else if (idx("T_imp") >= 0) *dptr = c->T_imp[idx("T_imp")];
+  else return cts_fail(c->ctx, CTS_EINVAL, "unknown buffer name");
+  return CTS_OK;
+}
+
+int cts_imex_cache_nbuffers(cts_imex_cache* c, int* n) {
+  if (!c || !n) return CTS_EINVAL;
+  *n = c->nbuffers;
+  return CTS_OK;
+}
+
+int cts_imex_cache_stats(cts_imex_cache* c, cts_solver_stats* out) {
+  if (!c || !out) return CTS_EINVAL;
+  *out = c->stats;
+  if (c->nm) {
+    const cts_solver_stats& n = c->nm->stats;
+    out->newton_iters += n.newton_iters;
+    out->krylov_iters += n.krylov_iters;
+    out->f_evals += n.f_evals;
+    out->jvp_evals += n.jvp_evals;
+    out->wfact_evals += n.wfact_evals;
+    out->ldiv_calls += n.ldiv_calls;
+  }
+  return CTS_OK;
+}
+
+int cts_imex_cache_set_fusion(cts_imex_cache* c, int enabled) {
+  if (!c) return CTS_EINVAL;
+  c->fusion = enabled != 0;
+  return CTS_OK;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// LSRK 2N   (lsrk.jl:49-67)
+// =============================================================================================
+struct cts_lsrk_cache {
+  cts_ctx* ctx = nullptr;
+  cts_dtype ft = CTS_F64;
+  size_t n = 0;
+  int nstages = 0;
+  std::vector<double> A, B, C;
+  cts_incr_fn f = nullptr;
+  void* ud = nullptr;
+  void* du = nullptr;
+  void* scratch = nullptr;  // ping-pong partner of u for the fused out-of-place stage (lazy)
+  bool fusion = true;
+  cts_solver_stats stats{};
+};
+
+extern "C" {
+
+int cts_lsrk_cache_create(cts_ctx* ctx, cts_dtype ft, size_t n, int nstages, const double* A, const double* B, const double* C,
+                          cts_incr_fn f, void* ud, cts_lsrk_cache** out) {
+  CTS_CHECK_CTX(ctx);
+  if (!out || !A || !B || !C || !f || nstages < 1 || n == 0) return cts_fail(ctx, CTS_EINVAL, "cts_lsrk_cache_create: bad argument");
+  auto* c = new cts_lsrk_cache();
+  c->ctx = ctx;
+  c->ft = ft;
+  c->n = n;
+  c->nstages = nstages;
+  c->A.assign(A, A + nstages);
+  c->B.assign(B, B + nstages);
+  c->C.assign(C, C + nstages);
+  c->f = f;
+  c->ud = ud;
+  int r = cts_alloc(ctx, n * cts_sizeof(ft), &c->du);  // `du = zero(prob.u0)` lsrk.jl:50
+  if (r) {
+    delete c;
+    return r;
+  }
+  *out = c;
+  return CTS_OK;
+}
+
+int cts_lsrk_cache_destroy(cts_lsrk_cache* c) {
+  if (!c) return CTS_EINVAL;
+  cts_free(c->ctx, c->du);
+  if (c->scratch) cts_free(c->ctx, c->scratch);
+  delete c;
+  return CTS_OK;
+}
+
+int cts_lsrk_step(cts_lsrk_cache* c, void* u, double t, double dt, int dt_is_f32) {
+  if (!c || !u) return CTS_EINVAL;
+  cts_ctx* ctx = c->ctx;
+  const bool f32 = c->ft == CTS_F32;
+  const int native = (f32 && dt_is_f32) ? 1 : 0;
+  auto dtB_of = [&](int s) { return native ? (double)((float)dt * (float)c->B[s]) : dt * c->B[s]; };
+  auto time_of = [&](int s) { return native ? (double)((float)t + (float)c->C[s] * (float)dt) : t + c->C[s] * dt; };
+
+  cts_op_advection* adv = nullptr;
+  if (c->fusion && c->f == cts_op_advection_incr) {
+    auto* op = static_cast<cts_op_advection*>(c->ud);
+    if (op && cts_op_advection_ctx(op) == ctx && cts_op_advection_dtype(op) == c->ft && cts_op_advection_n(op) == c->n) adv = op;
+  }
+  int s0 = 0;
+  if (adv) {
+    if (!c->scratch) CTS_TRY(cts_alloc(ctx, c->n * cts_sizeof(c->ft), &c->scratch));
+    // Out-of-place fused stages ping-pong between u and scratch and must end in u (the caller's array,
+    // integrators.jl:236): an even number of fused stages, preceded by one un-fused stage if nstages is odd.
+    s0 = c->nstages % 2;
+  }
+  for (int s = 0; s < c->nstages; ++s) {
+    if (adv && s >= s0) {
+      const bool from_u = ((s - s0) % 2) == 0;
+      void* src = from_u ? u : c->scratch;
+      void* dst = from_u ? c->scratch : u;
+      CTS_TRY(cts_advection_fused_stage(adv, dst, src, c->du, c->A[s], dtB_of(s), native));
+      c->stats.fused_stage_launches++;
+    } else {
+      HOOK(ctx, c->f(c->ud, c->du, u, time_of(s), 1.0, c->A[s]));   // lsrk.jl:64
+      c->stats.f_evals++;
+      CTS_TRY(cts_lsrk_update(ctx, c->ft, c->n, u, dtB_of(s), c->du, native));  // lsrk.jl:65
+    }
+  }
+  return CTS_OK;
+}
+
+int cts_lsrk_cache_buffer(cts_lsrk_cache* c, const char* name, void** dptr) {
+  if (!c || !name || !dptr) return CTS_EINVAL;
+  if (strcmp(name, "du") == 0) {
+    *dptr = c->du;
+    return CTS_OK;
+  }
+  return CTS_EINVAL;
+}
+
+int cts_lsrk_cache_set_fusion(cts_lsrk_cache* c, int enabled) {
+  if (!c) return CTS_EINVAL;
+  c->fusion = enabled != 0;
+  return CTS_OK;
+}
+
+int cts_lsrk_cache_stats(cts_lsrk_cache* c, cts_solver_stats* out) {
+  if (!c || !out) return CTS_EINVAL;
+  *out = c->stats;
+  return CTS_OK;
+}
+
+}  // extern "C"
