@@ -34,9 +34,12 @@ class Context:
         self.device = torch.cuda.current_device() if device is None else int(device)
         torch.cuda.set_device(self.device)
         if stream is None:
-            stream = torch.cuda.current_stream(self.device).cuda_stream
+            # torch reports its default stream as handle 0; the library must then enqueue on that SAME stream
+            # (cudaStreamLegacy = 0x1), not on a private one, or torch fills/copies would race with our kernels.
+            stream = torch.cuda.current_stream(self.device).cuda_stream or 0x1
+        self.stream = stream
         h = C.c_void_p()
-        L.check(None, self.lib.cts_ctx_create(C.byref(h), self.device, C.c_void_p(stream or None)), "cts_ctx_create")
+        L.check(None, self.lib.cts_ctx_create(C.byref(h), self.device, C.c_void_p(stream)), "cts_ctx_create")
         self.handle = h
         self.nranks, self.rank = 1, 0
 

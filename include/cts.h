@@ -50,7 +50,8 @@ typedef enum {
 /* ------------------------------------------------------------------ context / memory --------- */
 const char* cts_version(void);
 int cts_abi_version(void);
-/* `cuda_stream`: a cudaStream_t to enqueue on, or NULL to create a private non-blocking stream. */
+/* `cuda_stream`: a cudaStream_t to enqueue on (0x1 = cudaStreamLegacy, the default stream), or NULL to create a
+ * private non-blocking stream. */
 int cts_ctx_create(cts_ctx** out, int device, void* cuda_stream);
 int cts_ctx_destroy(cts_ctx* ctx);
 int cts_ctx_sync(cts_ctx* ctx);

@@ -330,20 +330,68 @@ def assign_fused_increment(U, u, dt, coeffs, tends, cdtype=np.float64):
 # --------------------------------------------------------------------------------------
 # Newton / Krylov  (src/nl_solvers/newtons_method.jl)
 # --------------------------------------------------------------------------------------
-def tree_sum(x: np.ndarray) -> float:
-    """Deterministic pairwise reduction used by BOTH the oracle and the CUDA library for every
-    norm/dot (LinearAlgebra.norm's order is implementation defined, so only tolerance
-    parity is meaningful downstream of a reduction; we pick numpy's pairwise float64 sum)."""
-    return float(np.sum(x.astype(np.float64, copy=False)))
+_RED_BLOCKS, _RED_THREADS = 1184, 256  # csrc/cts_internal.h: kReduceBlocks x kReduceThreads
+
+
+def _warp_tree(a):
+    """xor-butterfly over the last axis (32 lanes): every level adds lane l and lane l^o (commutative, so all
+    lanes agree); equivalent to repeated halving."""
+    for o in (16, 8, 4, 2, 1):
+        a = a[..., :o] + a[..., o:2 * o]
+    return a[..., 0]
+
+
+def _block_tree(acc):
+    """[..., 256] per-thread values -> one value per block: warp shuffles, then warp 0 folds the 8 warp sums."""
+    w = _warp_tree(acc.reshape(acc.shape[:-1] + (_RED_THREADS // 32, 32)))  # [..., 8]
+    w = w[..., :4] + w[..., 4:8]
+    w = w[..., :2] + w[..., 2:4]
+    return w[..., 0] + w[..., 1]
+
+
+def tree_sum(terms: np.ndarray, vn: int = 2) -> float:
+    """The library's deterministic reduction order (csrc/reduce.cu), restated so that norms and dots --
+    and everything downstream of them (JVP step sizes, GMRES) -- are bit-identical on both sides.
+    LinearAlgebra.norm's own order is implementation defined, so this fixed tree IS the
+    specification: thread t of a fixed 1184x256 grid accumulates the 16-byte vectors t, t+T, t+2T, ...
+    (elements of a vector in order), then a scalar tail, then warp/block trees, then the last block folds
+    the per-block partials (thread t takes partials t, t+256, ...) with the same tree.
+    `terms` are the Float64 summands; `vn` = elements per 16-byte vector (2 for Float64, 4 for Float32)."""
+    v = np.ascontiguousarray(terms, dtype=np.float64).ravel()
+    T = _RED_BLOCKS * _RED_THREADS
+    n = v.size
+    acc = np.zeros(T)
+    nvec = n // vn
+    for r in range(0, nvec, T):
+        chunk = v[r * vn:min(r + T, nvec) * vn].reshape(-1, vn)
+        for e in range(vn):
+            acc[:chunk.shape[0]] = acc[:chunk.shape[0]] + chunk[:, e]
+    for r in range(nvec * vn, n, T):
+        chunk = v[r:min(r + T, n)]
+        acc[:chunk.size] = acc[:chunk.size] + chunk
+    partials = _block_tree(acc.reshape(_RED_BLOCKS, _RED_THREADS))  # [1184]
+    fin = np.zeros(_RED_THREADS)
+    for b0 in range(0, _RED_BLOCKS, _RED_THREADS):
+        chunk = partials[b0:b0 + _RED_THREADS]
+        fin[:chunk.size] = fin[:chunk.size] + chunk
+    return float(_block_tree(fin))
+
+
+def _vn(x):
+    return 16 // x.dtype.itemsize
 
 
 def norm2(x):
     xd = _wide(x).ravel()
-    return math.sqrt(tree_sum(xd * xd))
+    return math.sqrt(tree_sum(xd * xd, _vn(x)))
 
 
 def dot(x, y):
-    return tree_sum(_wide(x).ravel() * _wide(y).ravel())
+    return tree_sum(_wide(x).ravel() * _wide(y).ravel(), _vn(x))
+
+
+def sum1pabs(x):
+    return tree_sum(1.0 + np.abs(_wide(x).ravel()), _vn(x))
 
 
 @dataclass
@@ -361,7 +409,7 @@ class ForwardDiffJVP:
         elif self.default_step == 2:
             e = math.sqrt(eps * (1 + norm2(x))) / norm2(dx)
         else:
-            e = math.sqrt(eps) * tree_sum(1 + np.abs(_wide(x))) / (x.size * norm2(dx))
+            e = math.sqrt(eps) * sum1pabs(x) / (x.size * norm2(dx))
         return FT(FT(self.step_adjustment) * FT(e))
 
 
