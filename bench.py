@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- IMEX step DOF-stage updates/s of the B200-native ClimaTimeSteppers state-update path.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched by torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+Workload (BASELINE.json configs[2], the configuration the metric/target is quoted on): ARS343 IMEX on the
+column-stacked vertical-diffusion problem, 2^21 columns x 64 levels = 2^27 DOF per GPU in Float64,
+NewtonsMethod(max_iters = 1, update_j = UpdateEvery(NewTimeStep)), batched tridiagonal Wfact/ldiv!, explicit
+source + 5-point horizontal coupling, dss! = ghost-row halo exchange (NCCL over NVLink when N > 1).
+A "step" is one `step!` of the integrator; the metric is N_dof * s / t_step with s = 4 stages.
+Multi-GPU: weak scaling, each rank owns a 2^10 x 2^11 slab of columns (the global grid grows with N).
+Prints ONE JSON line on rank 0 (contract in the task statement; extra keys: roofline, cpu_baseline, kernels).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NLEV, NX, NY = 64, 2 ** 11, 2 ** 10          # per-GPU slab: 2^21 columns x 64 levels
+DT, NU = 0.02, 1.0
+STAGES = 4                                   # ARS343
+METRIC, UNIT = "imex_step_dof_stage_updates_per_s", "DOF-stage/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, device=0):
+        self.rows, self.stop_evt, self.proc, self.device = [], threading.Event(), None, device
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                if self.stop_evt.is_set():
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        self.t = threading.Thread(target=pump, daemon=True)
+        self.t.start()
+
+    def stop(self):
+        self.stop_evt.set()
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(steps, warmup, sample_cols_log2=18):
+    """The reference's pass structure (oracle/cts_oracle.c, OpenMP over all host cores) on a bounded sample
+    of the same workload: 2^sample_cols_log2 columns x 64 levels."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import cts_oracle as CO
+    import cts_ref as R
+    lib = CO.load()
+    nx = NX
+    ny = max(1, (1 << sample_cols_log2) // nx)
+    cores = lib.oracle_num_threads()
+    ncol = (ny + 2) * nx
+    K = CO.fill_hash(ncol, 2, 0, 0.25, 2.0)
+    z = (np.arange(NLEV) + 1) / (NLEV + 1)
+    S = 5.0 * np.exp(-((z - 0.3) ** 2) / 0.01)
+    co = CO.ColumnARK(NLEV, nx, ny, K, S, NU, 1, tab=R.tableau("ARS343"), max_iters=1, update_j="NewTimeStep")
+    u = CO.fill_hash(ncol * NLEV, 3)
+    co.dss(u)
+    t = 0.0
+    for _ in range(warmup):
+        co.step(u, t, DT)
+        t += DT
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        co.step(u, t, DT)
+        t += DT
+    el = time.perf_counter() - t0
+    n_owned = ny * nx * NLEV
+    assert np.isfinite(u).all()
+    return {"value": n_owned * STAGES * steps / el, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{ny * nx} columns x {NLEV} levels ({n_owned} DOF), {steps} steps after {warmup} warm-up, "
+                      f"oracle/cts_oracle.c (reference pass structure, OpenMP, -O3 -march=native -ffp-contract=off)",
+            "ms_per_step": 1e3 * el / steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 4))
+    warm = max(1, min(args.warmup, 1))
+    cb = cpu_reference(steps, warm)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus, stored_w=True),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus, stored_w):
+    return {"workload": "ARS343 IMEX + NewtonsMethod(max_iters=1, update_j=NewTimeStep), column vertical diffusion "
+                        f"2^21 columns x 64 levels (2^27 DOF) per GPU, Float64, batched tridiagonal W "
+                        f"({'stored dl/d/du' if stored_w else 'matrix-free'}), explicit source + 5-point horizontal coupling, "
+                        "dss! = ghost-row halo exchange",
+            "baseline_config": "BASELINE.json configs[2] (single GPU) / configs[4] (sharded)",
+            "columns_per_gpu": NX * NY, "levels": NLEV, "dof_per_gpu": NX * NY * NLEV, "stages_per_step": STAGES, "dt": DT,
+            "global_dof": NX * NY * NLEV * n_gpus, "parallelism": f"column slabs x{n_gpus}",
+            "cache_policy": "every operand array is 1 GiB >> 126 MB L2, so no L2 flush is needed between steps"}
+
+
+# ------------------------------------------------------------------------------------------------
+def build_problem(cts, ctx, part, matrix_free):
+    import numpy as np
+    nyl = part.ny_local
+    ncol = (nyl + 2) * NX
+    # hashed inputs keyed by GLOBAL indices so every sharding sees the same field
+    K = cts.B200Vector.zeros(ncol, np.float64, ctx)
+    u = cts.B200Vector.zeros(ncol * NLEV, np.float64, ctx)
+    rows = part.local_rows(1)
+    import torch
+    # contiguous runs of global rows (ghost rows wrap around): fill per run
+    r = 0
+    while r < len(rows):
+        e = r
+        while e + 1 < len(rows) and rows[e + 1] == rows[e] + 1:
+            e += 1
+        g0, cnt = int(rows[r]), e - r + 1
+        kv = cts.B200Vector(K.tensor[r * NX:(r + cnt) * NX], ctx)
+        kv.fill_hash(2, g0 * NX, 0.25, 2.0)
+        uv = cts.B200Vector(u.tensor[r * NX * NLEV:(r + cnt) * NX * NLEV], ctx)
+        uv.fill_hash(3, g0 * NX * NLEV)
+        r = e + 1
+    z = (np.arange(NLEV) + 1) / (NLEV + 1)
+    S = cts.B200Vector.from_host(5.0 * np.exp(-((z - 0.3) ** 2) / 0.01), ctx)
+    op = cts.ColumnOperator(NLEV, NX, nyl, K, S_lev=S, nu=NU, halo=1, ctx=ctx).set_matrix_free(matrix_free)
+    alg = cts.IMEXAlgorithm(cts.ARS343(), cts.NewtonsMethod(max_iters=1, update_j=cts.UpdateEvery(cts.NewTimeStep)))
+    prob = cts.ODEProblem(op.ode_function(), u, (0.0, 1.0e9), None)
+    integ = cts.init(prob, alg, dt=DT, save=False)
+    return op, integ, u
+
+
+def stage_bytes(stored_w):
+    """Algorithmic bytes per DOF of the fused column stage launches of one ARS343 step:
+    stage i reads base + nnz(a_exp[i,:]) + nnz(a_imp[i,:]) arrays (+ dl,d,du when W is stored) and writes U and T_imp[i]."""
+    w = 8
+    reads = [1 + 1 + 0, 1 + 2 + 1, 1 + 3 + 2]   # stages 2,3,4
+    return [(r + 2 + (3 if stored_w else 0)) * w for r in reads]
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import cts_b200 as cts
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        ctx = cts.Context(local)           # enqueues on `stream`
+        if world > 1:
+            cts.attach_communicator(ctx, dist)
+        part = cts.SlabPartition(NY * world, world, rank)
+        stored_w = not args.matrix_free
+        op, integ, u = build_problem(cts, ctx, part, args.matrix_free)
+        op.dss(u, None, 0.0)
+        n_owned = op.ndof_owned
+
+        def barrier():
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        for _ in range(args.warmup):
+            cts.step_(integ)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ctx.prof_read()
+        ctx.prof_enable(True)
+        l0 = ctx.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            cts.step_(integ)
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        launches = ctx.launch_count() - l0
+        prof = ctx.prof_read()
+        ctx.prof_enable(False)
+        clocks = sampler.stop() if rank == 0 else None
+        stats = integ.cache.stats()
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        finite = bool(torch.isfinite(u.tensor).all())
+
+        # ---- end-to-end through the public API with HOST buffers: H2D of the state, step!, D2H of the result ----
+        e2e_steps = max(1, min(args.steps, 5))
+        host = torch.empty(u.tensor.numel(), dtype=torch.float64).pin_memory()
+        host.copy_(u.tensor)
+        barrier()
+        ev0.record(stream)
+        for _ in range(e2e_steps):
+            u.tensor.copy_(host, non_blocking=True)
+            cts.step_(integ)
+            host.copy_(u.tensor, non_blocking=True)
+            stream.synchronize()
+        ev1.record(stream)
+        barrier()
+        ms_e2e = ev0.elapsed_time(ev1)
+        if dist is not None:
+            t = torch.tensor([ms_e2e], dtype=torch.float64, device=f"cuda:{local}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t.item())
+
+        # ---- extras (rank 0, N = 1): the other single-GPU workloads and stand-alone kernels --------------
+        extras = {}
+        if world == 1 and not args.no_extras:
+            del integ
+            extras = run_extras(cts, ctx, stream, op, u)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    value = n_owned * world * STAGES * args.steps / (ms * 1e-3)
+    # roofline of the dominant kernel (fused column stage): algorithmic bytes / measured launch time
+    fs_ms, fs_n = prof.get("fused_stage", (0.0, 0))
+    ndof_local = op.ndof
+    per_step = sum(stage_bytes(stored_w)) * ndof_local
+    roof = None
+    if fs_n:
+        achieved = per_step * (fs_n / 3.0) / (fs_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "column_fused_stage_kernel (K1+K2+T_imp+K3+K4+K5+K6 of one implicit stage)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": None, "launches": fs_n, "avg_launch_ms": fs_ms / fs_n,
+                "algorithmic_bytes_per_dof_per_launch": stage_bytes(stored_w),
+                "share_of_step": fs_ms / ms}
+    kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items()}
+    step_bytes = step_bytes_per_dof(stored_w) * ndof_local
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(world, stored_w),
+            "roofline": roof,
+            "step_hbm": {"algorithmic_bytes_per_dof_step": step_bytes_per_dof(stored_w),
+                         "achieved_GBs_per_gpu": step_bytes / (ms / args.steps * 1e-3) / 1e9,
+                         "frac_of_peak": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
+            "kernels": kernels,
+            "e2e": {"value": n_owned * world * STAGES * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(u.tensor.numel() * 8), "d2h_bytes_per_step": int(u.tensor.numel() * 8),
+                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                    "api": "cts_b200.step_(integrator) with the state uploaded from / downloaded to pinned host memory every step"},
+            "gpu_launches": launches, "clocks": clocks, "solver_stats": stats, "finite": finite}
+    if not args.no_cpu_baseline and world == 1:
+        cb = cpu_reference(2, 1)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    else:
+        line["cpu_baseline"] = None
+    if extras:
+        line["extras"] = extras
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def step_bytes_per_dof(stored_w):
+    """Whole fused ARS343 step (SURVEY §8d 'fused minimum'): 3 fused stages + final update (7 reads, 1 write)
+    + 4 T_exp! (1 read, 1 write) [+ Wfact 3 writes when W is stored]."""
+    return sum(stage_bytes(stored_w)) + 8 * 8 + 4 * 2 * 8 + (3 * 8 if stored_w else 0)
+
+
+def timed(stream, fn, reps, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream.synchronize()
+    a.record(stream)
+    for _ in range(reps):
+        fn()
+    b.record(stream)
+    stream.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def run_extras(cts, ctx, stream, op, u):
+    """Other single-GPU configs / kernels, each as achieved algorithmic GB/s vs the measured HBM peak."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from cts_b200 import _lib as L
+    peak, _ = peaks()
+    out = {}
+    n = 1 << 27
+    # --- K1 stand-alone: ARS343 final update shape (7 reads + 1 write) and stage-2 shape (2 reads + 1 write)
+    vs = [cts.B200Vector.zeros(n, np.float64, ctx).fill_hash(10 + k) for k in range(7)]
+    dst = cts.B200Vector.zeros(n, np.float64, ctx)
+    for nt in (1, 3, 6):
+        g1 = [(0.01 * (k + 1), vs[1 + k]) for k in range(nt)]
+        ms = timed(stream, lambda: cts.axpy_n(dst, vs[0], g1[:nt // 2 + nt % 2], g1[nt // 2 + nt % 2:]), 10)
+        gb = (2 + nt) * 8 * n / (ms * 1e-3) / 1e9
+        out[f"K1_axpy_n_{nt}terms"] = {"ms": ms, "GBs": gb, "frac": gb / peak, "bytes_per_dof": (2 + nt) * 8}
+    # --- K4 stand-alone: batched tridiagonal solve (5w)
+    W = L.Tridiag(NLEV, n // NLEV, vs[1].ptr, vs[2].ptr, vs[3].ptr)
+    vs[2].tensor.add_(-4.0)  # diagonally dominant
+    ms = timed(stream, lambda: ctx.check(ctx.lib.cts_tridiag_solve_batched(ctx.handle, 1, C.byref(W), vs[4].ptr, dst.ptr)), 10)
+    gb = 5 * 8 * n / (ms * 1e-3) / 1e9
+    out["K4_tridiag_solve_batched"] = {"ms": ms, "GBs": gb, "frac": gb / peak, "bytes_per_dof": 40}
+    # --- reductions
+    ms = timed(stream, lambda: vs[0].norm(), 10)
+    out["R1_nrm2"] = {"ms": ms, "GBs": 8 * n / (ms * 1e-3) / 1e9, "frac": 8 * n / (ms * 1e-3) / 1e9 / peak}
+    ms = timed(stream, lambda: vs[0].dot(vs[1]), 10)
+    out["R3_dot"] = {"ms": ms, "GBs": 16 * n / (ms * 1e-3) / 1e9, "frac": 16 * n / (ms * 1e-3) / 1e9 / peak}
+    # --- config C2: LSRK54CarpenterKennedy on 2^27-element upwind advection, fused and un-fused
+    del vs[3:]
+    adv = cts.AdvectionOperator(n, ctx=ctx)
+    ua = cts.B200Vector.zeros(n, np.float64, ctx).fill_hash(1)
+    integ = cts.init(cts.ODEProblem(adv.ode_function(), ua, (0.0, 1e9), None), cts.LSRK54CarpenterKennedy(), dt=0.5 / n, save=False)
+    for fused in (True, False):
+        integ.cache.set_fusion(fused)
+        ms = timed(stream, lambda: cts.step_(integ), 5)
+        model = (4 * 4 + 6) * 8 if fused else 30 * 8   # bytes/DOF/step: 4 fused stages (4w) + 1 two-pass stage (6w) | 5 x 6w
+        out[f"C2_lsrk54_advection_{'fused' if fused else 'unfused'}"] = {
+            "ms_per_step": ms, "dof_stage_per_s": n * 5 / (ms * 1e-3), "GBs": model * n / (ms * 1e-3) / 1e9,
+            "frac": model * n / (ms * 1e-3) / 1e9 / peak, "bytes_per_dof_step": model}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--matrix-free", action="store_true", help="regenerate W = dtγJ - I inside the fused stage kernel")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -19,6 +19,7 @@ from .integrators import (CallbackSet, DiscreteCallback, EveryXSimulationSteps, 
                           EveryXWallTimeSeconds, add_saveat_, add_tstop_, get_dt, init, reinit_, set_dt_, solve,
                           solve_, step_)
 from .operators import AdvectionOperator, ColumnOperator, ColumnTridiag
+from .parallel import SlabPartition, attach_communicator
 from .solvers import IMEXCache, LSRKCache, init_cache, step_u
 from .tableaus import *  # noqa: F401,F403  (named tableaux: ARS343, SSP333, ...)
 from .tableaus import IMEX_NAMES, EXPLICIT_NAMES, IMEXTableau, is_fsal

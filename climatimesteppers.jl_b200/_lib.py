@@ -19,6 +19,8 @@ CTS_MAX_STAGES, CTS_MAX_TERMS = 8, 16
 STATUS = {0: "CTS_OK", -1: "CTS_EINVAL", -2: "CTS_ECUDA", -3: "CTS_ENCCL", -4: "CTS_ENODEVICE",
           -5: "CTS_ECALLBACK", -6: "CTS_EUNSUPPORTED"}
 
+PROF_CATEGORIES = ["stage_assembly", "final_update", "fused_stage", "T_exp", "T_imp", "Wfact", "ldiv", "newton_ew", "dss",
+                   "krylov", "lsrk_fused", "lsrk_rhs", "lsrk_update", "other_hooks"]
 c_void_pp = C.POINTER(C.c_void_p)
 c_double_p = C.POINTER(C.c_double)
 
@@ -92,6 +94,8 @@ SIGNATURES = [
     ("cts_last_error", C.c_char_p, [_P]),
     ("cts_ctx_stream", _P, [_P]),
     ("cts_launch_count", _I, [_P, C.POINTER(_U64)]),
+    ("cts_prof_enable", _I, [_P, _I]),
+    ("cts_prof_read", _I, [_P, c_double_p, C.POINTER(_U64)]),
     ("cts_alloc", _I, [_P, _SZ, c_void_pp]),
     ("cts_free", _I, [_P, _P]),
     ("cts_memset_zero", _I, [_P, _P, _SZ]),

@@ -29,6 +29,40 @@ struct cts_ctx {
   // communicator (comm.cpp)
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
+  // per-kernel timing (cts_prof_*)
+  bool prof_on = false;
+  struct ProfRec {
+    int cat;
+    cudaEvent_t a, b;
+  };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+};
+
+// RAII bracket: records a start/stop event pair on the context's stream around a kernel family.
+struct cts_prof_scope {
+  cts_ctx* ctx;
+  int idx = -1;
+  cts_prof_scope(cts_ctx* c, int cat) : ctx(c) {
+    if (!c || !c->prof_on) return;
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!c->prof_pool.empty()) {
+        e = c->prof_pool.back();
+        c->prof_pool.pop_back();
+      } else {
+        cudaEventCreate(&e);
+      }
+      return e;
+    };
+    cts_ctx::ProfRec r{cat, get(), get()};
+    cudaEventRecord(r.a, c->stream);
+    c->prof_recs.push_back(r);
+    idx = (int)c->prof_recs.size() - 1;
+  }
+  ~cts_prof_scope() {
+    if (idx >= 0) cudaEventRecord(ctx->prof_recs[idx].b, ctx->stream);
+  }
 };
 
 constexpr int kReduceBlocks = 1184;  // 148 SMs x 8: fixed so that reductions are deterministic

@@ -52,6 +52,11 @@ int cts_ctx_destroy(cts_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->nccl_comm) cts_comm_destroy(ctx);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (auto& r : ctx->prof_recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  for (auto e : ctx->prof_pool) cudaEventDestroy(e);
   if (ctx->d_partials) cudaFree(ctx->d_partials);
   if (ctx->d_result) cudaFree(ctx->d_result);
   if (ctx->d_counter) cudaFree(ctx->d_counter);
@@ -74,6 +79,33 @@ int cts_launch_count(cts_ctx* ctx, uint64_t* out) {
   CTS_CHECK_CTX(ctx);
   if (!out) return CTS_EINVAL;
   *out = ctx->launches;
+  return CTS_OK;
+}
+
+int cts_prof_enable(cts_ctx* ctx, int enabled) {
+  CTS_CHECK_CTX(ctx);
+  ctx->prof_on = enabled != 0;
+  return CTS_OK;
+}
+
+int cts_prof_read(cts_ctx* ctx, double* ms, uint64_t* launches) {
+  CTS_CHECK_CTX(ctx);
+  if (!ms || !launches) return CTS_EINVAL;
+  for (int k = 0; k < CTS_PROF_NCAT; ++k) {
+    ms[k] = 0.0;
+    launches[k] = 0;
+  }
+  CTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& r : ctx->prof_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.cat >= 0 && r.cat < CTS_PROF_NCAT) {
+      ms[r.cat] += t;
+      launches[r.cat] += 1;
+    }
+    ctx->prof_pool.push_back(r.a);
+    ctx->prof_pool.push_back(r.b);
+  }
+  ctx->prof_recs.clear();
   return CTS_OK;
 }
 

@@ -218,24 +218,46 @@ __global__ void __launch_bounds__(256) column_wfact_kernel(T* __restrict__ dl, T
   }
 }
 
-// T_exp = S[lev]*g(t) + nu * (((uw + ue) + us) + un - 4 uc), owned rows only.
-template <typename T>
+// T_exp = S[lev]*g(t) + nu * (((uw + ue) + us) + un - 4 uc), owned rows only.  One thread per VN consecutive
+// levels (VN = 16 bytes when the level count allows it): the four horizontal neighbours of a level vector are
+// whole columns away, so every access is a full-width coalesced 16-byte load.
+template <typename T, int VN>
 __global__ void __launch_bounds__(256) column_texp_kernel(T* __restrict__ out, const T* __restrict__ u,
                                                           const T* __restrict__ S, T g, T nu, int nlev, size_t nx,
                                                           size_t ny_local, int halo, int has_src) {
   const size_t row_elems = nx * (size_t)nlev;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // index within the owned rows
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VN;  // first element, within the owned rows
   if (i >= ny_local * row_elems) return;
-  size_t jr = i / row_elems;          // owned row
-  size_t r = i - jr * row_elems;      // offset in the row
-  size_t ix = r / (size_t)nlev;
-  int lev = (int)(r - ix * (size_t)nlev);
-  size_t rows = ny_local + 2 * (size_t)halo;
-  size_t j = jr + (size_t)halo;       // row in the local array
-  size_t idx = j * row_elems + r;
-  T val = has_src ? rmul(S[lev], g) : T(0);
+  const size_t jr = i / row_elems;      // owned row
+  const size_t r = i - jr * row_elems;  // offset in the row
+  const size_t ix = r / (size_t)nlev;
+  const int lev = (int)(r - ix * (size_t)nlev);
+  const size_t rows = ny_local + 2 * (size_t)halo;
+  const size_t j = jr + (size_t)halo;   // row in the local array
+  const size_t idx = j * row_elems + r;
+  T val[VN];
+  auto ld = [&](const T* p, T (&e)[VN]) {
+    if (VN == 1) {
+      e[0] = p[0];
+    } else {
+      typename Vec<T>::type v = *reinterpret_cast<const typename Vec<T>::type*>(p);
+      T t[Vec<T>::N];
+      vec_unpack<T>(v, t);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) e[k] = t[k];
+    }
+  };
+  if (has_src) {
+    T s[VN];
+    ld(S + lev, s);
+#pragma unroll
+    for (int k = 0; k < VN; ++k) val[k] = rmul(s[k], g);
+  } else {
+#pragma unroll
+    for (int k = 0; k < VN; ++k) val[k] = T(0);
+  }
   if (nu != T(0)) {
-    size_t ixw = ix == 0 ? nx - 1 : ix - 1, ixe = ix == nx - 1 ? 0 : ix + 1;
+    const size_t ixw = ix == 0 ? nx - 1 : ix - 1, ixe = ix == nx - 1 ? 0 : ix + 1;
     size_t js, jn;
     if (halo) {
       js = j - 1;
@@ -244,13 +266,26 @@ __global__ void __launch_bounds__(256) column_texp_kernel(T* __restrict__ out, c
       js = j == 0 ? rows - 1 : j - 1;
       jn = j == rows - 1 ? 0 : j + 1;
     }
-    T uc = u[idx];
-    T uw = u[j * row_elems + ixw * (size_t)nlev + lev], ue = u[j * row_elems + ixe * (size_t)nlev + lev];
-    T us = u[js * row_elems + r], un = u[jn * row_elems + r];
-    T lap = rsub(radd(radd(radd(uw, ue), us), un), rmul(T(4), uc));
-    val = radd(val, rmul(nu, lap));
+    T uc[VN], uw[VN], ue[VN], us[VN], un[VN];
+    ld(u + idx, uc);
+    ld(u + j * row_elems + ixw * (size_t)nlev + lev, uw);
+    ld(u + j * row_elems + ixe * (size_t)nlev + lev, ue);
+    ld(u + js * row_elems + r, us);
+    ld(u + jn * row_elems + r, un);
+#pragma unroll
+    for (int k = 0; k < VN; ++k) {
+      const T lap = rsub(radd(radd(radd(uw[k], ue[k]), us[k]), un[k]), rmul(T(4), uc[k]));
+      val[k] = radd(val[k], rmul(nu, lap));
+    }
   }
-  out[idx] = val;
+  if (VN == 1) {
+    out[idx] = val[0];
+  } else {
+    T t[Vec<T>::N];
+#pragma unroll
+    for (int k = 0; k < VN; ++k) t[k] = val[k];
+    *reinterpret_cast<typename Vec<T>::type*>(out + idx) = vec_pack<T>(t);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -281,8 +316,10 @@ struct FusedArgs {
   int pitch;
 };
 
+constexpr int kFusedThreads = 256;  // 2 solver warps (a lane pair per column) + 6 more warps that only move data
+
 template <typename T, typename C, int NT, bool MATRIX_FREE>
-__global__ void __launch_bounds__(kTileThreads) column_fused_stage_kernel(const FusedArgs<NT> a) {
+__global__ void __launch_bounds__(kFusedThreads) column_fused_stage_kernel(const FusedArgs<NT> a) {
   using V = typename Vec<T>::type;
   constexpr int VN = Vec<T>::N;
   constexpr int NTS = NT > 0 ? NT : 1;
@@ -291,7 +328,7 @@ __global__ void __launch_bounds__(kTileThreads) column_fused_stage_kernel(const 
   const int tile_bytes = kTileCols * pitch;
   char* sU0 = smem;
   char* sr = smem + tile_bytes;
-  char* sfac = smem + 2 * tile_bytes;  // matrix-free: cp/lp scratch; stored: dl tile (du and d follow)
+  char* sfac = smem + 2 * tile_bytes;  // matrix-free: cp/lp scratch; stored: dl tile (d and du follow)
   char* sdl = sfac;
   char* sd = smem + 3 * tile_bytes;
   char* sdu = smem + 4 * tile_bytes;
@@ -319,69 +356,89 @@ __global__ void __launch_bounds__(kTileThreads) column_fused_stage_kernel(const 
     }
   }
 
-  // ---- phase A: U0 tile = K1(base, terms), coalesced 128-bit loads ------------------------------
+  // ---- phase A: U0 tile = K1(base, terms).  Two 16-byte vectors per thread and round, every operand's load
+  // issued before the first use: (1+NT)*2 independent requests per thread, 256 threads per CTA. ---------------
   const int cpc = col_bytes / 16;
   const int total = nvalid * cpc;
-  for (int q = threadIdx.x; q < total; q += kTileThreads) {
-    const int col = q / cpc, k = q - col * cpc;
-    const size_t gi = (goff * sizeof(T) + (size_t)col * col_bytes + (size_t)k * 16) / 16;  // 16-byte vector index
-    V vb = reinterpret_cast<const V*>(a.ax.base)[gi];
-    V vt[NTS];
+  constexpr int UN = 2;
+  for (int q0 = threadIdx.x; q0 < total; q0 += UN * kFusedThreads) {
+    V vb[UN], vt[NTS][UN];
+    size_t gi[UN];
+    int so[UN];
+    bool ok[UN];
 #pragma unroll
-    for (int t = 0; t < NT; ++t) vt[t] = reinterpret_cast<const V*>(a.ax.terms[t])[gi];
-    T eb[VN], eo[VN], et[NTS][VN];
-    vec_unpack<T>(vb, eb);
+    for (int u = 0; u < UN; ++u) {
+      const int q = q0 + u * kFusedThreads;
+      ok[u] = q < total;
+      const int col = q / cpc, k = q - col * cpc;
+      so[u] = col * pitch + k * 16;
+      gi[u] = (goff * sizeof(T) + (size_t)col * col_bytes + (size_t)k * 16) / 16;  // 16-byte vector index
+      if (ok[u]) {
+        vb[u] = reinterpret_cast<const V*>(a.ax.base)[gi[u]];
 #pragma unroll
-    for (int t = 0; t < NT; ++t) vec_unpack<T>(vt[t], et[t]);
-#pragma unroll
-    for (int e = 0; e < VN; ++e) {
-      T x[NTS];
-#pragma unroll
-      for (int t = 0; t < NT; ++t) x[t] = et[t][e];
-      eo[e] = axpy_combine<T, C, NT>(eb[e], x, a.ax);
+        for (int t = 0; t < NT; ++t) vt[t][u] = reinterpret_cast<const V*>(a.ax.terms[t])[gi[u]];
+      }
     }
-    V vo = vec_pack<T>(eo);
-    *reinterpret_cast<V*>(sU0 + col * pitch + k * 16) = vo;
-    if (a.temp) reinterpret_cast<V*>(a.temp)[gi] = vo;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      if (!ok[u]) continue;
+      T eb[VN], eo[VN], et[NTS][VN];
+      vec_unpack<T>(vb[u], eb);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) vec_unpack<T>(vt[t][u], et[t]);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) {
+        T x[NTS];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) x[t] = et[t][e];
+        eo[e] = axpy_combine<T, C, NT>(eb[e], x, a.ax);
+      }
+      V vo = vec_pack<T>(eo);
+      *reinterpret_cast<V*>(sU0 + so[u]) = vo;
+      if (a.temp) reinterpret_cast<V*>(a.temp)[gi[u]] = vo;
+    }
   }
   __syncthreads();
 
-  // ---- phase B: residual + two-sided Thomas, a lane pair per column -----------------------------
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int col = warp * 16 + (lane & 15);
-  const bool is_up = lane >= 16;
-  const bool valid = col < nvalid;
-  const int col_off = col * pitch;
-  T acol = T(0);
-  if (valid) {
-    acol = col_a<T>(((const T*)a.Kcol)[col0 + col], (T)a.dz);
-    const T* U0 = reinterpret_cast<const T*>(sU0 + col_off);
-    T* r = reinterpret_cast<T*>(sr + col_off);
-    const int m = nlev / 2;
-    const int lo = is_up ? m : 0, hi = is_up ? nlev : m;
-    T um = lo > 0 ? U0[lo - 1] : T(0);
-    T uc = U0[lo];
-    for (int l = lo; l < hi; ++l) {
-      T up = l < nlev - 1 ? U0[l + 1] : T(0);
-      T ti = timp_linear<T>(acol, um, uc, up);
-      r[l] = (T)__dsub_rn(__dadd_rn((double)uc, __dmul_rn(a.dtg, (double)ti)), (double)uc);
-      um = uc;
-      uc = up;
+  // ---- phase B (warps 0-1): residual + two-sided Thomas, a lane pair per column ------------------------
+  if (threadIdx.x < kTileThreads) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = warp * 16 + (lane & 15);
+    const bool is_up = lane >= 16;
+    const bool valid = col < nvalid;
+    const int col_off = col * pitch;
+    T acol = T(0);
+    if (valid) {
+      acol = col_a<T>(((const T*)a.Kcol)[col0 + col], (T)a.dz);
+      const T* U0 = reinterpret_cast<const T*>(sU0 + col_off);
+      T* r = reinterpret_cast<T*>(sr + col_off);
+      const int m = nlev / 2;
+      const int lo = is_up ? m : 0, hi = is_up ? nlev : m;
+      T um = lo > 0 ? U0[lo - 1] : T(0);
+      T uc = U0[lo];
+#pragma unroll 4
+      for (int l = lo; l < hi; ++l) {
+        const T up = l < nlev - 1 ? U0[l + 1] : T(0);
+        const T ti = timp_linear<T>(acol, um, uc, up);
+        r[l] = (T)__dsub_rn(__dadd_rn((double)uc, __dmul_rn(a.dtg, (double)ti)), (double)uc);
+        um = uc;
+        uc = up;
+      }
     }
-  }
-  if (MATRIX_FREE) {
-    double o = __dmul_rn(a.dtg, (double)acol);
-    ConstRows<T> rows{(T)o, (T)__dsub_rn(__dmul_rn(-2.0, o), 1.0)};
-    babe_solve_lanepair<T>(rows, sfac, sr, col_off, nlev, is_up, valid);
-  } else {
-    mbar_wait(bar, 0);
-    StoredRows<T> rows{sdl, sd, sdu};
-    babe_solve_lanepair<T>(rows, is_up ? sdl : sdu, sr, col_off, nlev, is_up, valid);
+    if (MATRIX_FREE) {
+      const double o = __dmul_rn(a.dtg, (double)acol);
+      ConstRows<T> rows{(T)o, (T)__dsub_rn(__dmul_rn(-2.0, o), 1.0), sfac};
+      babe_solve_lanepair<T>(rows, sr, col_off, nlev, is_up, valid);
+    } else {
+      mbar_wait(bar, 0);
+      StoredRows<T> rows{sdl, sd, sdu};
+      babe_solve_lanepair<T>(rows, sr, col_off, nlev, is_up, valid);
+    }
   }
   __syncthreads();
 
   // ---- phase C: U = U0 - dx ; Timp = (U - U0)/dtγ ; coalesced 128-bit stores -----------------------
-  for (int q = threadIdx.x; q < total; q += kTileThreads) {
+  for (int q = threadIdx.x; q < total; q += kFusedThreads) {
     const int c = q / cpc, k = q - c * cpc;
     const size_t gi = (goff * sizeof(T) + (size_t)c * col_bytes + (size_t)k * 16) / 16;
     T e0[VN], ex[VN], eU[VN], eT[VN];
@@ -434,11 +491,11 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
   if (mf) {
     auto k = column_fused_stage_kernel<T, C, NT, true>;
     CTS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)tiles, kTileThreads, smem, ctx->stream>>>(a);
+    k<<<(unsigned)tiles, kFusedThreads, smem, ctx->stream>>>(a);
   } else {
     auto k = column_fused_stage_kernel<T, C, NT, false>;
     CTS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)tiles, kTileThreads, smem, ctx->stream>>>(a);
+    k<<<(unsigned)tiles, kFusedThreads, smem, ctx->stream>>>(a);
   }
   CTS_LAUNCH_CHECK(ctx);
   return CTS_OK;
@@ -461,10 +518,10 @@ int dispatch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
 }  // namespace
 
 bool cts_column_fusable(const cts_op_column* op) {
-  const int vn = op->ft == CTS_F64 ? 2 : 4;
   const int es = op->ft == CTS_F64 ? 8 : 4;
   size_t smem = (size_t)5 * kTileCols * pitch_bytes(op->d.nlev, es) + 16;
-  return !op->d.nonlinear && op->d.nlev >= 2 * vn && (op->d.nlev % (2 * vn)) == 0 && smem <= 200 * 1024;
+  return !op->d.nonlinear && op->d.nlev >= 2 && (op->d.nlev % 2) == 0 && ((op->d.nlev * es) % 16) == 0 &&
+         smem <= 200 * 1024;
 }
 
 int cts_column_fused_stage(cts_op_column* op, const cts_fused_stage_args* s) {
@@ -613,10 +670,20 @@ int cts_op_column_T_exp(void* vop, void* du_exp, void* du_lim, const void* u, do
   // time factor of the source, evaluated once on the host in Float64 (docs/src/tutorials/imex_diffusion.md:65-69)
   double g = 1.0 + 0.5 * sin(2.0 * M_PI * t);
   int has_src = d.S_lev != nullptr;
-  if (op->ft == CTS_F64)
-    column_texp_kernel<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)du_exp, (const double*)u, (const double*)d.S_lev, g, d.nu, d.nlev, d.nx, d.ny_local, d.halo, has_src);
-  else
-    column_texp_kernel<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)du_exp, (const float*)u, (const float*)d.S_lev, (float)g, (float)d.nu, d.nlev, d.nx, d.ny_local, d.halo, has_src);
+  const int vn = op->ft == CTS_F64 ? 2 : 4;
+  const bool vec = (d.nlev % vn) == 0 && cts_aligned16(du_exp) && cts_aligned16(u) && (!has_src || cts_aligned16(d.S_lev));
+  if (vec) {
+    size_t blocks = (n_owned / vn + 255) / 256;
+    if (op->ft == CTS_F64)
+      column_texp_kernel<double, 2><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)du_exp, (const double*)u, (const double*)d.S_lev, g, d.nu, d.nlev, d.nx, d.ny_local, d.halo, has_src);
+    else
+      column_texp_kernel<float, 4><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)du_exp, (const float*)u, (const float*)d.S_lev, (float)g, (float)d.nu, d.nlev, d.nx, d.ny_local, d.halo, has_src);
+  } else {
+    if (op->ft == CTS_F64)
+      column_texp_kernel<double, 1><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)du_exp, (const double*)u, (const double*)d.S_lev, g, d.nu, d.nlev, d.nx, d.ny_local, d.halo, has_src);
+    else
+      column_texp_kernel<float, 1><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)du_exp, (const float*)u, (const float*)d.S_lev, (float)g, (float)d.nu, d.nlev, d.nx, d.ny_local, d.halo, has_src);
+  }
   CTS_LAUNCH_CHECK(ctx);
   return CTS_OK;
 }

@@ -290,16 +290,21 @@ int solve_krylov(cts_newton_cache* c, void* dx, const void* x, const ResidualFn&
     }
     double e = 0;  // jvp! :173-182
     CTS_TRY(jvp_step(c, v, x, &e));
-    CTS_TRY(cts_jvp_perturb(ctx, c->ft, c->n, c->x2, x, e, v));
+    {
+      cts_prof_scope ps(ctx, CTS_PROF_NEWTON_EW);
+      CTS_TRY(cts_jvp_perturb(ctx, c->ft, c->n, c->x2, x, e, v));
+    }
     if (prepare) CTS_TRY((*prepare)(c->x2));
     CTS_TRY(f_(c->f2, c->x2));
     c->stats.f_evals++;
     c->stats.jvp_evals++;
+    cts_prof_scope ps(ctx, CTS_PROF_NEWTON_EW);
     CTS_TRY(cts_jvp_quotient(ctx, c->ft, c->n, out, c->f2, f, e));
     return CTS_OK;
   };
   const bool use_M = !(c->cfg.disable_preconditioner || !c->W || !jfree);
   std::function<int(void*, const void*)> precond = [&](void* out, const void* w) -> int {
+    cts_prof_scope ps(ctx, CTS_PROF_LDIV);
     HOOK(ctx, c->ldiv(c->ud, out, c->W, w));
     c->stats.ldiv_calls++;
     return CTS_OK;
@@ -328,12 +333,18 @@ int solve_newton(cts_newton_cache* c, void* x, const ResidualFn& f_, const JacFn
     }
     if (!cfg.use_krylov) {
       if (!c->ldiv || !c->W) return cts_fail(ctx, CTS_EINVAL, "direct Newton needs ldiv! and a Jacobian");
-      HOOK(ctx, c->ldiv(c->ud, c->dx, c->W, c->f));
+      {
+        cts_prof_scope ps(ctx, CTS_PROF_LDIV);
+        HOOK(ctx, c->ldiv(c->ud, c->dx, c->W, c->f));
+      }
       c->stats.ldiv_calls++;
     } else {
       CTS_TRY(solve_krylov(c, c->dx, x, f_, c->f, n - 1, prepare));
     }
-    CTS_TRY(cts_sub_inplace(ctx, c->ft, c->n, x, c->dx));  // K5
+    {
+      cts_prof_scope ps(ctx, CTS_PROF_NEWTON_EW);
+      CTS_TRY(cts_sub_inplace(ctx, c->ft, c->n, x, c->dx));  // K5
+    }
     if (n < cfg.max_iters) {
       if (prepare) CTS_TRY((*prepare)(x));
       CTS_TRY(f_(c->f, x));
@@ -485,7 +496,8 @@ Increment raw_increment(const cts_imex_cache* c, double dt, const double* coefs,
 
 // assign_with_increments!(out, base, inc_exp, inc_imp)  (fused_increment.jl:220-236)
 int assign_with_increments(cts_imex_cache* c, void* out, void* out2, double c0, const void* base, const Increment& g1,
-                           const Increment& g2) {
+                           const Increment& g2, int cat = CTS_PROF_STAGE_ASSEMBLY) {
+  cts_prof_scope ps(c->ctx, cat);
   double coef[CTS_MAX_TERMS];
   const void* terms[CTS_MAX_TERMS];
   int k = 0;
@@ -504,6 +516,7 @@ int assign_with_increments(cts_imex_cache* c, void* out, void* out2, double c0, 
 int maybe_update_jacobian(cts_imex_cache* c, const void* u, double t, double dt) {  // async_utils.jl:11-31
   if (!c->f.T_imp || !c->ncfg.present || !c->nm || !c->nm->W) return CTS_OK;
   if (!needs_update(c->ncfg.update_j, CTS_SIG_NEW_TIMESTEP, t)) return CTS_OK;
+  cts_prof_scope ps(c->ctx, CTS_PROF_WFACT);
   HOOK(c->ctx, c->f.Wfact(c->f.ud, c->nm->W, u, dt * c->gamma, t));
   c->stats.wfact_evals++;
   return CTS_OK;
@@ -511,13 +524,17 @@ int maybe_update_jacobian(cts_imex_cache* c, const void* u, double t, double dt)
 
 int call_dss(cts_imex_cache* c, void* u, double t) {
   if (c->f.dss) {
+    cts_prof_scope ps(c->ctx, CTS_PROF_DSS);
     HOOK(c->ctx, c->f.dss(c->f.ud, u, t));
     c->stats.dss_calls++;
   }
   return CTS_OK;
 }
 int call_state(cts_imex_cache* c, cts_state_fn fn, void* u, double t) {
-  if (fn) HOOK(c->ctx, fn(c->f.ud, u, t));
+  if (fn) {
+    cts_prof_scope ps(c->ctx, CTS_PROF_OTHER_HOOKS);
+    HOOK(c->ctx, fn(c->f.ud, u, t));
+  }
   return CTS_OK;
 }
 
@@ -525,10 +542,15 @@ int call_state(cts_imex_cache* c, cts_state_fn fn, void* u, double t) {
 int solve_implicit_equation(cts_imex_cache* c, void* U, const void* U0, double t_imp, double dtg) {
   cts_ctx* ctx = c->ctx;
   ResidualFn f_ = [&](void* res, const void* Up) -> int {
-    HOOK(ctx, c->f.T_imp(c->f.ud, res, Up, t_imp));
+    {
+      cts_prof_scope ps(ctx, CTS_PROF_T_IMP);
+      HOOK(ctx, c->f.T_imp(c->f.ud, res, Up, t_imp));
+    }
+    cts_prof_scope ps(ctx, CTS_PROF_NEWTON_EW);
     return cts_newton_residual(ctx, c->ft, c->n, res, U0, dtg, Up);  // K3
   };
   JacFn j_ = [&](void* W, const void* Up) -> int {
+    cts_prof_scope ps(ctx, CTS_PROF_WFACT);
     HOOK(ctx, c->f.Wfact(c->f.ud, W, Up, dtg, t_imp));
     return CTS_OK;
   };
@@ -556,7 +578,10 @@ int fused_implicit_stage(cts_imex_cache* c, cts_op_column* op, void* U, double c
   // does not depend on the state, so the stage value is not needed to build it).
   const bool mf = cts_op_column_matrix_free(op);
   if (needs_update(c->ncfg.update_j, CTS_SIG_NEW_NEWTON_SOLVE) || needs_update(c->ncfg.update_j, CTS_SIG_NEW_NEWTON_ITERATION)) {
-    if (!mf) HOOK(c->ctx, c->f.Wfact(c->f.ud, c->nm->W, base, dtg, t_imp));
+    if (!mf) {
+      cts_prof_scope ps(c->ctx, CTS_PROF_WFACT);
+      HOOK(c->ctx, c->f.Wfact(c->f.ud, c->nm->W, base, dtg, t_imp));
+    }
     c->stats.wfact_evals++;
   }
   cts_fused_stage_args a{};
@@ -579,7 +604,10 @@ int fused_implicit_stage(cts_imex_cache* c, cts_op_column* op, void* U, double c
   a.U = U;
   a.T_imp = T_imp_out;
   a.temp = nullptr;
-  CTS_TRY(cts_column_fused_stage(op, &a));
+  {
+    cts_prof_scope ps(c->ctx, CTS_PROF_FUSED_STAGE);
+    CTS_TRY(cts_column_fused_stage(op, &a));
+  }
   c->stats.fused_stage_launches++;
   c->stats.newton_iters++;
   return CTS_OK;
@@ -639,7 +667,10 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
       }
       if (!no_imp) {
         if (!c->ncfg.present || !c->nm) return cts_fail(c->ctx, CTS_EINVAL, "implicit stage without a NewtonsMethod");
-        CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->temp, nullptr, 1.0, U, 0, 0, nullptr, nullptr, 0));  // K2 :209
+        {
+          cts_prof_scope ps(c->ctx, CTS_PROF_NEWTON_EW);
+          CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->temp, nullptr, 1.0, U, 0, 0, nullptr, nullptr, 0));  // K2 :209
+        }
         if (!f.initialize_imp_is_nothing) {
           if (f.initialize_imp) HOOK(c->ctx, f.initialize_imp(f.ud, U, dtg));
           CTS_TRY(call_dss(c, U, t_exp));
@@ -658,12 +689,18 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
     }
 
     // evaluate_stage_tendencies!  :252-272
-    if (has_exp_terms && f.T_exp_T_lim) HOOK(c->ctx, f.T_exp_T_lim(f.ud, c->T_exp[i], c->T_lim[i], U, t_exp));
+    if (has_exp_terms && f.T_exp_T_lim) {
+      cts_prof_scope ps(c->ctx, CTS_PROF_T_EXP);
+      HOOK(c->ctx, f.T_exp_T_lim(f.ud, c->T_exp[i], c->T_lim[i], U, t_exp));
+    }
     if (has_imp_terms && has_T_imp && !stage_done) {
-      if (dtg == 0)
+      if (dtg == 0) {
+        cts_prof_scope ps(c->ctx, CTS_PROF_T_IMP);
         HOOK(c->ctx, f.T_imp(f.ud, c->T_imp[i], U, t_imp));
-      else
+      } else {
+        cts_prof_scope ps(c->ctx, CTS_PROF_NEWTON_EW);
         CTS_TRY(cts_timp_from_stage(c->ctx, c->ft, c->n, c->T_imp[i], U, c->temp, dtg));  // K6 :269
+      }
     }
   }
 
@@ -675,9 +712,9 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
     Increment inc_lim = raw_increment(c, dt, tab.b_exp, s, c->T_lim);
     CTS_TRY(assign_with_increments(c, c->temp, nullptr, 1.0, u, inc_lim, Increment{}));
     if (f.lim) HOOK(c->ctx, f.lim(f.ud, c->temp, t_final, u));
-    CTS_TRY(assign_with_increments(c, u, nullptr, 1.0, c->temp, inc_exp, inc_imp));
+    CTS_TRY(assign_with_increments(c, u, nullptr, 1.0, c->temp, inc_exp, inc_imp, CTS_PROF_FINAL_UPDATE));
   } else {
-    CTS_TRY(assign_with_increments(c, u, nullptr, 1.0, u, inc_exp, inc_imp));
+    CTS_TRY(assign_with_increments(c, u, nullptr, 1.0, u, inc_exp, inc_imp, CTS_PROF_FINAL_UPDATE));
   }
   CTS_TRY(call_dss(c, u, t_final));
   if (needs_update(f.update_constrain_state, CTS_SIG_END_OF_STEP)) CTS_TRY(call_state(c, f.constrain_state, u, t_final));
@@ -690,6 +727,7 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
 // ---------------------------------------------------------------------------------------------
 // `@. x = x + dt * T` in promote(typeof(dt), FT)   (imex_ssprk.jl:112,117,158,163)
 int axpy_dt(cts_imex_cache* c, void* out, const void* x, double dt, const void* T, int dt_is_f32) {
+  cts_prof_scope ps(c->ctx, CTS_PROF_STAGE_ASSEMBLY);
   double coef[1] = {dt};
   const void* terms[1] = {T};
   int native = (dt_is_f32 && c->ft == CTS_F32) ? 1 : 0;
@@ -713,6 +751,7 @@ int ssprk_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
     const double aii = A(tab.a_imp, s, i, i);
     const double dtg = dt * aii;
     if (i == 0) {
+      cts_prof_scope ps(c->ctx, CTS_PROF_STAGE_ASSEMBLY);
       CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->U_exp, nullptr, 1.0, u, 0, 0, nullptr, nullptr, 0));  // :155
     } else if (c->beta[i - 1] != 0) {
       if (f.has_lim) {
@@ -726,7 +765,10 @@ int ssprk_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
       const double omb = native ? (double)(1.0f - (float)b) : 1.0 - b;
       double coef[1] = {b};
       const void* terms[1] = {c->U_exp};
-      CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->U_exp, nullptr, omb, u, 1, 0, coef, terms, native));
+      {
+        cts_prof_scope ps(c->ctx, CTS_PROF_STAGE_ASSEMBLY);
+        CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->U_exp, nullptr, omb, u, 1, 0, coef, terms, native));
+      }
       // NB: c0 == 1 would skip the multiply; (1-β) == 1 only when β == 0, which this branch excludes.
     }
     Increment inc_imp = has_T_imp ? raw_increment(c, dt, &tab.a_imp[i * s], i, c->T_imp) : Increment{};
@@ -751,19 +793,28 @@ int ssprk_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
       if (!no_imp) {
         if (!c->ncfg.present || !c->nm) return cts_fail(c->ctx, CTS_EINVAL, "implicit stage without a NewtonsMethod");
         if (i != 0) CTS_TRY(call_state(c, f.cache_imp, c->U, t_imp));
-        CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->temp, nullptr, 1.0, c->U, 0, 0, nullptr, nullptr, 0));  // :190
+        {
+          cts_prof_scope ps(c->ctx, CTS_PROF_NEWTON_EW);
+          CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->temp, nullptr, 1.0, c->U, 0, 0, nullptr, nullptr, 0));  // :190
+        }
         CTS_TRY(solve_implicit_equation(c, c->U, c->temp, t_imp, dtg));
         CTS_TRY(call_dss(c, c->U, t_imp));
         if (needs_update(f.update_constrain_state, CTS_SIG_END_OF_STAGE)) CTS_TRY(call_state(c, f.constrain_state, c->U, t_imp));
         if (needs_update(f.update_cache, CTS_SIG_END_OF_STAGE)) CTS_TRY(call_state(c, f.cache, c->U, t_imp));
       }
     }
-    if (c->beta[i] != 0 && f.T_exp_T_lim) HOOK(c->ctx, f.T_exp_T_lim(f.ud, c->T_exp1, c->T_lim1, c->U, t_exp));
+    if (c->beta[i] != 0 && f.T_exp_T_lim) {
+      cts_prof_scope ps(c->ctx, CTS_PROF_T_EXP);
+      HOOK(c->ctx, f.T_exp_T_lim(f.ud, c->T_exp1, c->T_lim1, c->U, t_exp));
+    }
     if (has_imp_terms && has_T_imp && !stage_done) {
-      if (aii == 0)
+      if (aii == 0) {
+        cts_prof_scope ps(c->ctx, CTS_PROF_T_IMP);
         HOOK(c->ctx, f.T_imp(f.ud, c->T_imp[i], c->U, t_imp));
-      else
+      } else {
+        cts_prof_scope ps(c->ctx, CTS_PROF_NEWTON_EW);
         CTS_TRY(cts_timp_from_stage(c->ctx, c->ft, c->n, c->T_imp[i], c->U, c->temp, dtg));
+      }
     }
   }
 
@@ -783,9 +834,9 @@ int ssprk_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
     g1.n = 1;
     g1.coef[0] = b;
     g1.term[0] = c->U_exp;
-    CTS_TRY(assign_with_increments(c, u, nullptr, omb, u, g1, inc_imp));
+    CTS_TRY(assign_with_increments(c, u, nullptr, omb, u, g1, inc_imp, CTS_PROF_FINAL_UPDATE));
   } else if (inc_imp.n > 0) {
-    CTS_TRY(assign_with_increments(c, u, nullptr, 1.0, u, inc_imp, Increment{}));
+    CTS_TRY(assign_with_increments(c, u, nullptr, 1.0, u, inc_imp, Increment{}, CTS_PROF_FINAL_UPDATE));
   }
   CTS_TRY(call_dss(c, u, t_final));
   if (needs_update(f.update_constrain_state, CTS_SIG_END_OF_STEP)) CTS_TRY(call_state(c, f.constrain_state, u, t_final));
@@ -1055,11 +1106,16 @@ int cts_lsrk_step(cts_lsrk_cache* c, void* u, double t, double dt, int dt_is_f32
       const bool from_u = ((s - s0) % 2) == 0;
       void* src = from_u ? u : c->scratch;
       void* dst = from_u ? c->scratch : u;
+      cts_prof_scope ps(ctx, CTS_PROF_LSRK_FUSED);
       CTS_TRY(cts_advection_fused_stage(adv, dst, src, c->du, c->A[s], dtB_of(s), native));
       c->stats.fused_stage_launches++;
     } else {
-      HOOK(ctx, c->f(c->ud, c->du, u, time_of(s), 1.0, c->A[s]));   // lsrk.jl:64
+      {
+        cts_prof_scope ps(ctx, CTS_PROF_LSRK_RHS);
+        HOOK(ctx, c->f(c->ud, c->du, u, time_of(s), 1.0, c->A[s]));  // lsrk.jl:64
+      }
       c->stats.f_evals++;
+      cts_prof_scope ps(ctx, CTS_PROF_LSRK_UPDATE);
       CTS_TRY(cts_lsrk_update(ctx, c->ft, c->n, u, dtB_of(s), c->du, native));  // lsrk.jl:65
     }
   }

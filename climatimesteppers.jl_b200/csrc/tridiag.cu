@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kTileThreads) tridiag_tile_kernel(const T* __r
   const int col = warp * 16 + (lane & 15);
   const bool is_up = lane >= 16;
   StoredRows<T> rows{sdl, sd, sdu};
-  babe_solve_lanepair<T>(rows, is_up ? sdl : sdu, sr, col * pitch, nlev, is_up, col < nvalid);
+  babe_solve_lanepair<T>(rows, sr, col * pitch, nlev, is_up, col < nvalid);
 
   if (USE_TMA) {
     fence_proxy_async_smem();  // generic-proxy writes of x -> visible to the async proxy
@@ -153,11 +153,10 @@ template <typename T>
 int solve_t(cts_ctx* ctx, const cts_tridiag* W, const void* rhs, void* x) {
   const int nlev = W->nlev;
   const size_t ncols = W->ncols;
-  const int VN = LV<T>::N;
   const int col_bytes = nlev * (int)sizeof(T);
   const int pitch = pitch_bytes(nlev, sizeof(T));
   const size_t smem = (size_t)4 * kTileCols * pitch + 16;
-  bool tile_ok = nlev >= 2 * VN && (nlev % (2 * VN)) == 0 && (col_bytes % 16) == 0 && smem <= 200 * 1024 &&
+  bool tile_ok = nlev >= 2 && (nlev % 2) == 0 && (col_bytes % 16) == 0 && smem <= 200 * 1024 &&
                  cts_aligned16(W->dl) && cts_aligned16(W->d) && cts_aligned16(W->du) && cts_aligned16(rhs) &&
                  cts_aligned16(x);
   if (tile_ok) {

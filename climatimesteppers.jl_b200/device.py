@@ -60,6 +60,16 @@ class Context:
         self.check(self.lib.cts_launch_count(self.handle, C.byref(out)))
         return int(out.value)
 
+    def prof_enable(self, enabled: bool = True):
+        self.check(self.lib.cts_prof_enable(self.handle, int(enabled)))
+
+    def prof_read(self) -> dict:
+        """{category: (device ms, launches)} since the last read (the per-hook table of `benchmark_step`)."""
+        n = len(L.PROF_CATEGORIES)
+        ms, cnt = (C.c_double * n)(), (C.c_uint64 * n)()
+        self.check(self.lib.cts_prof_read(self.handle, ms, cnt))
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(L.PROF_CATEGORIES) if cnt[i]}
+
     def set_reduction_window(self, offset: int, count: int):
         self.check(self.lib.cts_set_reduction_window(self.handle, offset, count))
 

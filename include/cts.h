@@ -67,6 +67,31 @@ int cts_memcpy_h2d(cts_ctx* ctx, void* dst_dev, const void* src_host, size_t byt
 int cts_memcpy_d2h_sync(cts_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 int cts_memcpy_d2d(cts_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);
 
+/* ------------------------------------------------------------------ per-kernel timing ---------- */
+/* The counterpart of the reference's `benchmark_step` table (ext/ClimaTimeSteppersBenchmarkToolsExt.jl:42-146):
+ * when enabled, the step engine brackets every kernel family it launches with CUDA events on the context's
+ * stream; cts_prof_read synchronises, returns the accumulated device time (ms) and launch count per
+ * category since the last read, and resets the accumulators. */
+typedef enum {
+  CTS_PROF_STAGE_ASSEMBLY = 0, /* K1 stage value (compute_stage_value!)            */
+  CTS_PROF_FINAL_UPDATE = 1,   /* K1 final update of u                             */
+  CTS_PROF_FUSED_STAGE = 2,    /* fused K1+Newton+K6 column stage                  */
+  CTS_PROF_T_EXP = 3,          /* T_exp_T_lim! hook                                */
+  CTS_PROF_T_IMP = 4,          /* T_imp! hook                                      */
+  CTS_PROF_WFACT = 5,          /* Wfact hook                                       */
+  CTS_PROF_LDIV = 6,           /* ldiv! hook (K4)                                  */
+  CTS_PROF_NEWTON_EW = 7,      /* K2, K3, K5, K6, K7, K8 element-wise passes       */
+  CTS_PROF_DSS = 8,            /* dss! hook (halo exchange)                        */
+  CTS_PROF_KRYLOV = 9,         /* GMRES vector work (dots, norms, axpys)           */
+  CTS_PROF_LSRK_FUSED = 10,    /* fused LSRK stage (K10f + K10)                    */
+  CTS_PROF_LSRK_RHS = 11,      /* user f(du,u,p,t,1,A) (K10f)                      */
+  CTS_PROF_LSRK_UPDATE = 12,   /* u += dtB*du (K10)                                */
+  CTS_PROF_OTHER_HOOKS = 13,   /* cache!/constrain_state!/lim!/initialize_imp!     */
+  CTS_PROF_NCAT = 14
+} cts_prof_category;
+int cts_prof_enable(cts_ctx* ctx, int enabled);
+int cts_prof_read(cts_ctx* ctx, double* ms_per_category /*[CTS_PROF_NCAT]*/, uint64_t* launches_per_category /*[CTS_PROF_NCAT]*/);
+
 /* ------------------------------------------------------------------ element-wise kernels ----- */
 /* K1/K2/K11  fused multi-operand increment -- replaces `assign_with_increments!`,
  * `assign_fused_increment!`, `fused_increment!` (src/utilities/fused_increment.jl:183-236) and the
