@@ -403,8 +403,8 @@ __global__ void __launch_bounds__(kFusedThreads) column_fused_stage_kernel(const
   // ---- phase B (warps 0-1): residual + two-sided Thomas, a lane pair per column ------------------------
   if (threadIdx.x < kTileThreads) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int col = warp * 16 + (lane & 15);
-    const bool is_up = lane >= 16;
+    const int col = warp * 16 + lane_column(lane);
+    const bool is_up = lane_is_up(lane);
     const bool valid = col < nvalid;
     const int col_off = col * pitch;
     T acol = T(0);

@@ -19,7 +19,8 @@ using namespace cts_tile;
 
 namespace {
 
-template <typename T, bool USE_TMA>
+// LOADER: 0 = cooperative LDG/STS, 1 = 1-D bulk TMA (one 512-byte copy per column), 2 = cp.async (LDGSTS)
+template <typename T, int LOADER>
 __global__ void __launch_bounds__(kTileThreads) tridiag_tile_kernel(const T* __restrict__ dl, const T* __restrict__ d,
                                                                     const T* __restrict__ du, const T* rhs, T* x,
                                                                     int nlev, size_t ncols, int pitch) {
@@ -36,7 +37,7 @@ __global__ void __launch_bounds__(kTileThreads) tridiag_tile_kernel(const T* __r
   const int col_bytes = nlev * (int)sizeof(T);
   const size_t goff = col0 * (size_t)nlev;
 
-  if (USE_TMA) {
+  if (LOADER == 1) {
     if (threadIdx.x == 0) {
       mbar_init(bar, 1);
       fence_mbar_init();
@@ -52,6 +53,14 @@ __global__ void __launch_bounds__(kTileThreads) tridiag_tile_kernel(const T* __r
       bulk_g2s(sr + c * pitch, rhs + g, col_bytes, bar);
     }
     mbar_wait(bar, 0);
+  } else if (LOADER == 2) {
+    cpasync_load_tile(sdl, reinterpret_cast<const char*>(dl + goff), nvalid, col_bytes, pitch);
+    cpasync_load_tile(sd, reinterpret_cast<const char*>(d + goff), nvalid, col_bytes, pitch);
+    cpasync_load_tile(sdu, reinterpret_cast<const char*>(du + goff), nvalid, col_bytes, pitch);
+    cpasync_load_tile(sr, reinterpret_cast<const char*>(rhs + goff), nvalid, col_bytes, pitch);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
   } else {
     coop_load_tile(sdl, reinterpret_cast<const char*>(dl + goff), nvalid, col_bytes, pitch);
     coop_load_tile(sd, reinterpret_cast<const char*>(d + goff), nvalid, col_bytes, pitch);
@@ -62,12 +71,12 @@ __global__ void __launch_bounds__(kTileThreads) tridiag_tile_kernel(const T* __r
 
   // lane pair (l, l+16) of warp w owns column 16*w + (l & 15)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int col = warp * 16 + (lane & 15);
-  const bool is_up = lane >= 16;
+  const int col = warp * 16 + lane_column(lane);
+  const bool is_up = lane_is_up(lane);
   StoredRows<T> rows{sdl, sd, sdu};
   babe_solve_lanepair<T>(rows, sr, col * pitch, nlev, is_up, col < nvalid);
 
-  if (USE_TMA) {
+  if (LOADER == 1) {
     fence_proxy_async_smem();  // generic-proxy writes of x -> visible to the async proxy
     __syncthreads();
     if ((int)threadIdx.x < nvalid) {
@@ -97,25 +106,23 @@ __global__ void tridiag_generic_kernel(const T* dl, const T* d, const T* du, con
   }
   const int m = n / 2;
   T fp = T(0), rp = T(0);
-  for (int i = 0; i < m; ++i) {
-    T l = (i == 0) ? T(0) : dl[i];
-    T piv = rsub(d[i], rmul(l, fp));
-    T inv = rdiv(T(1), piv);
-    fp = rmul(du[i], inv);
-    rp = rmul(rsub(rhs[i], rmul(l, rp)), inv);
-    fac[i] = fp;
-    x[i] = rp;
+  {
+    ProductSweep<T> sw;
+    for (int i = 0; i < m; ++i) {
+      sw.row(i == 0 ? T(0) : dl[i], d[i], du[i], rhs[i], i, fp, rp);
+      fac[i] = fp;
+      x[i] = rp;
+    }
   }
   T cpm = fp, rpm = rp;
   fp = T(0); rp = T(0);
-  for (int j = n - 1; j >= m; --j) {
-    T u = (j == n - 1) ? T(0) : du[j];
-    T piv = rsub(d[j], rmul(u, fp));
-    T inv = rdiv(T(1), piv);
-    fp = rmul(dl[j], inv);
-    rp = rmul(rsub(rhs[j], rmul(u, rp)), inv);
-    fac[j] = fp;
-    x[j] = rp;
+  {
+    ProductSweep<T> sw;
+    for (int j = n - 1, s = 0; j >= m; --j, ++s) {
+      sw.row(j == n - 1 ? T(0) : du[j], d[j], dl[j], rhs[j], s, fp, rp);
+      fac[j] = fp;
+      x[j] = rp;
+    }
   }
   T lpm = fp, spm = rp;
   T det = rsub(T(1), rmul(cpm, lpm));
@@ -140,13 +147,16 @@ __global__ void __launch_bounds__(256) tridiag_matvec_kernel(const T* __restrict
   y[i] = acc;
 }
 
-bool tma_enabled() {
+int tile_loader() {  // CTS_TILE_LOADER = 0 | 1 | 2 (default 1: bulk TMA, the fastest measured); CTS_DISABLE_TMA=1 forces 0
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("CTS_DISABLE_TMA");
-    v = (e && e[0] == '1') ? 0 : 1;
+    v = 1;
+    const char* e = getenv("CTS_TILE_LOADER");
+    if (e && e[0] >= '0' && e[0] <= '2') v = e[0] - '0';
+    const char* d = getenv("CTS_DISABLE_TMA");
+    if (d && d[0] == '1' && v == 1) v = 0;
   }
-  return v == 1;
+  return v;
 }
 
 template <typename T>
@@ -161,17 +171,19 @@ int solve_t(cts_ctx* ctx, const cts_tridiag* W, const void* rhs, void* x) {
                  cts_aligned16(x);
   if (tile_ok) {
     size_t tiles = (ncols + kTileCols - 1) / kTileCols;
-    if (tma_enabled()) {
-      auto k = tridiag_tile_kernel<T, true>;
+    const int loader = tile_loader();
+    auto launch = [&](auto k) -> int {
       CTS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k<<<(unsigned)tiles, kTileThreads, smem, ctx->stream>>>((const T*)W->dl, (const T*)W->d, (const T*)W->du,
                                                               (const T*)rhs, (T*)x, nlev, ncols, pitch);
-    } else {
-      auto k = tridiag_tile_kernel<T, false>;
-      CTS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k<<<(unsigned)tiles, kTileThreads, smem, ctx->stream>>>((const T*)W->dl, (const T*)W->d, (const T*)W->du,
-                                                              (const T*)rhs, (T*)x, nlev, ncols, pitch);
-    }
+      return CTS_OK;
+    };
+    if (loader == 1)
+      CTS_TRY(launch(tridiag_tile_kernel<T, 1>));
+    else if (loader == 2)
+      CTS_TRY(launch(tridiag_tile_kernel<T, 2>));
+    else
+      CTS_TRY(launch(tridiag_tile_kernel<T, 0>));
     CTS_LAUNCH_CHECK(ctx);
     return CTS_OK;
   }

@@ -1,6 +1,6 @@
 """numpy restatement of the synthetic benchmark models of SURVEY §8d (configs C2-C5): hashed inputs,
 upwind advection, the column diffusion model (T_imp, Wfact, T_exp, ghost-row dss!) and the batched
-two-sided Thomas solve that plays ``ldiv!`` for the column-stacked tridiagonal ``W``.
+two-sided product-form Thomas solve that plays ``ldiv!`` for the column-stacked tridiagonal ``W``.
 
 *** TEST INFRASTRUCTURE ONLY *** (see oracle/cts_ref.py).  These models are OURS, not the reference's
 (the reference ships no model at this scale); they are defined once here, operation by operation, and
@@ -48,12 +48,63 @@ class Advection:
 
 
 # ------------------------------------------------------------------------------ tridiagonal ldiv! ---
+def _pow2_rescale(P):
+    """Exact power of two 2^-e, e = unbiased exponent of P (1 for zero/subnormal/huge/non-finite P): the bit
+    logic of csrc/tile_device.cuh::pow2_rescale."""
+    if P.dtype == np.float64:
+        be = ((P.view(np.uint64) >> np.uint64(52)) & np.uint64(0x7FF)).astype(np.int64)
+        ok = (be != 0) & (be < 2046)
+        sc = np.ldexp(np.float64(1.0), np.where(ok, 1023 - be, 0).astype(np.int32))
+    else:
+        be = ((P.view(np.uint32) >> np.uint32(23)) & np.uint32(0xFF)).astype(np.int64)
+        ok = (be != 0) & (be < 254)
+        sc = np.ldexp(np.float32(1.0), np.where(ok, 127 - be, 0).astype(np.int32)).astype(np.float32)
+    return sc
+
+
+def _rcp_checked(P):
+    """csrc/tile_device.cuh::rcp_checked: correctly rounded 1/P for pivot products inside the safe exponent
+    range, NaN otherwise (zero / subnormal / overflowing / non-finite product = singular or badly scaled W)."""
+    if P.dtype == np.float64:
+        be = ((np.ascontiguousarray(P).view(np.uint64) >> np.uint64(52)) & np.uint64(0x7FF)).astype(np.int64)
+        bad = (be < 25) | (be > 2021)
+    else:
+        be = ((np.ascontiguousarray(P).view(np.uint32) >> np.uint32(23)) & np.uint32(0xFF)).astype(np.int64)
+        bad = (be == 0) | (be == 255)
+    return np.where(bad, P.dtype.type(np.nan), P.dtype.type(1) / P)
+
+
+class _ProductSweep:
+    """Product-form elimination (csrc/tile_device.cuh::ProductSweep): P_i = d_i P_{i-1} - (l_i u_{i-1}) P_{i-2},
+    S_i = r_i P_{i-1} - l_i S_{i-1}, cp_i = (u_i P_{i-1})/P_i, rp_i = S_i/P_i, power-of-two rescale every 8 rows (4 in Float32)."""
+
+    def __init__(self, nc, FT):
+        self.P1, self.P2 = np.ones(nc, FT), np.zeros(nc, FT)
+        self.S1, self.aprev = np.zeros(nc, FT), np.zeros(nc, FT)
+        self.one = FT(1)
+        self.every = 8 if np.dtype(FT).itemsize == 8 else 4  # RescaleEvery<T>
+
+    def row(self, toward, dd, away, rr, s):
+        lu = toward * self.aprev
+        P = dd * self.P1 - lu * self.P2
+        S = rr * self.P1 - toward * self.S1
+        inv = _rcp_checked(P)
+        fac = (away * self.P1) * inv
+        rhs = S * inv
+        self.P2, self.P1, self.S1, self.aprev = self.P1, P, S, away
+        if (s + 1) % self.every == 0:
+            sc = _pow2_rescale(np.ascontiguousarray(self.P1))
+            self.P1, self.P2, self.S1 = self.P1 * sc, self.P2 * sc, self.S1 * sc
+        return fac, rhs
+
+
 def babe_solve(dl, d, du, rhs, nlev):
-    """Two-sided Thomas elimination, identical operation sequence to csrc/tile_device.cuh (one reciprocal per row):
-    arrays are column-stacked (level fastest); returns x.  dl[0] / du[nlev-1] of each column are ignored."""
+    """Two-sided, product-form Thomas elimination: identical operation sequence to csrc/tile_device.cuh
+    (babe_solve_lanepair) and csrc/tridiag.cu (generic kernel).  Arrays are column-stacked (level fastest);
+    returns x.  dl[0] / du[nlev-1] of each column are ignored."""
     FT = rhs.dtype.type
     sh = (-1, nlev)
-    dl, d, du, r = (a.reshape(sh) for a in (dl, d, du, rhs))
+    dl, d, du, r = (np.ascontiguousarray(a.reshape(sh)) for a in (dl, d, du, rhs))
     nc = r.shape[0]
     x = np.empty_like(r)
     one = FT(1)
@@ -61,34 +112,45 @@ def babe_solve(dl, d, du, rhs, nlev):
         return (r[:, 0] * (one / d[:, 0])).reshape(rhs.shape)
     m = nlev // 2
     fac = np.empty_like(r)
-    fp = np.zeros(nc, FT)
-    rp = np.zeros(nc, FT)
-    for i in range(m):  # down sweep
-        l = np.zeros(nc, FT) if i == 0 else dl[:, i]
+    zero = np.zeros(nc, FT)
+    with np.errstate(all="ignore"):
+        sw = _ProductSweep(nc, FT)
+        for i in range(m):  # down sweep
+            fp, rp = sw.row(zero if i == 0 else dl[:, i], d[:, i], du[:, i], r[:, i], i)
+            fac[:, i], x[:, i] = fp, rp
+        cpm, rpm = fp, rp
+        sw = _ProductSweep(nc, FT)
+        for s, j in enumerate(range(nlev - 1, m - 1, -1)):  # up sweep
+            fp, rp = sw.row(zero if j == nlev - 1 else du[:, j], d[:, j], dl[:, j], r[:, j], s)
+            fac[:, j], x[:, j] = fp, rp
+        lpm, spm = fp, rp
+        det = one - cpm * lpm
+        xm1 = (rpm - cpm * spm) / det
+        xm = spm - lpm * xm1
+        x[:, m - 1], x[:, m] = xm1, xm
+        for i in range(m - 2, -1, -1):
+            x[:, i] = x[:, i] - fac[:, i] * x[:, i + 1]
+        for j in range(m + 1, nlev):
+            x[:, j] = x[:, j] - fac[:, j] * x[:, j - 1]
+    return x.reshape(rhs.shape)
+
+
+def thomas_reference(dl, d, du, rhs, nlev):
+    """Textbook Thomas in extended precision (accuracy yardstick for the product form; not used for parity)."""
+    L = lambda a: a.reshape(-1, nlev).astype(np.longdouble)
+    dl, d, du, r = L(dl), L(d), L(du), L(rhs)
+    cp, rp = np.zeros_like(d), np.zeros_like(d)
+    fp, q = np.zeros(d.shape[0], np.longdouble), np.zeros(d.shape[0], np.longdouble)
+    for i in range(nlev):
+        l = dl[:, i] if i > 0 else 0 * dl[:, i]
         piv = d[:, i] - l * fp
-        inv = one / piv
-        fp = du[:, i] * inv
-        rp = (r[:, i] - l * rp) * inv
-        fac[:, i], x[:, i] = fp, rp
-    cpm, rpm = fp, rp
-    fp = np.zeros(nc, FT)
-    rp = np.zeros(nc, FT)
-    for j in range(nlev - 1, m - 1, -1):  # up sweep
-        uu = np.zeros(nc, FT) if j == nlev - 1 else du[:, j]
-        piv = d[:, j] - uu * fp
-        inv = one / piv
-        fp = dl[:, j] * inv
-        rp = (r[:, j] - uu * rp) * inv
-        fac[:, j], x[:, j] = fp, rp
-    lpm, spm = fp, rp
-    det = one - cpm * lpm
-    xm1 = (rpm - cpm * spm) / det
-    xm = spm - lpm * xm1
-    x[:, m - 1], x[:, m] = xm1, xm
-    for i in range(m - 2, -1, -1):
-        x[:, i] = x[:, i] - fac[:, i] * x[:, i + 1]
-    for j in range(m + 1, nlev):
-        x[:, j] = x[:, j] - fac[:, j] * x[:, j - 1]
+        fp = du[:, i] / piv
+        q = (r[:, i] - l * q) / piv
+        cp[:, i], rp[:, i] = fp, q
+    x = np.zeros_like(d)
+    x[:, -1] = rp[:, -1]
+    for i in range(nlev - 2, -1, -1):
+        x[:, i] = rp[:, i] - cp[:, i] * x[:, i + 1]
     return x.reshape(rhs.shape)
 
 

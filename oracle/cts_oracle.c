@@ -181,7 +181,46 @@ void oracle_col_dss(const col_model* m, double* u) { /* single rank: periodic gh
   memcpy(u + (ny + 1) * re, u + re, re * sizeof(double));
 }
 
-/* two-sided Thomas elimination: the operation sequence of csrc/tile_device.cuh / cts_models.babe_solve */
+/* two-sided, product-form Thomas elimination: the operation sequence of csrc/tile_device.cuh / cts_models.babe_solve */
+static inline double pow2_rescale(double p) {
+  uint64_t bits;
+  memcpy(&bits, &p, 8);
+  int be = (int)((bits >> 52) & 0x7ff);
+  if (be == 0 || be >= 2046) return 1.0;
+  uint64_t out = (uint64_t)(2046 - be) << 52;
+  double sc;
+  memcpy(&sc, &out, 8);
+  return sc;
+}
+static inline double rcp_checked(double p) { /* csrc/tile_device.cuh::rcp_checked */
+  uint64_t bits;
+  memcpy(&bits, &p, 8);
+  int be = (int)((bits >> 52) & 0x7ff);
+  if (be < 25 || be > 2021) return NAN;
+  return 1.0 / p;
+}
+typedef struct {
+  double P1, P2, S1, aprev;
+} sweep_t;
+static inline void sweep_row(sweep_t* w, double toward, double dd, double away, double rr, int s, double* fac,
+                             double* rhs) {
+  const double lu = toward * w->aprev;
+  const double P = dd * w->P1 - lu * w->P2;
+  const double S = rr * w->P1 - toward * w->S1;
+  const double inv = rcp_checked(P);
+  *fac = (away * w->P1) * inv;
+  *rhs = S * inv;
+  w->P2 = w->P1;
+  w->P1 = P;
+  w->S1 = S;
+  w->aprev = away;
+  if (((s + 1) & 7) == 0) { /* RescaleEvery<double> = 8 */
+    const double sc = pow2_rescale(w->P1);
+    w->P1 = w->P1 * sc;
+    w->P2 = w->P2 * sc;
+    w->S1 = w->S1 * sc;
+  }
+}
 static void babe_column(const double* dl, const double* d, const double* du, const double* rhs, double* x, double* fac,
                         int n) {
   if (n == 1) {
@@ -190,24 +229,16 @@ static void babe_column(const double* dl, const double* d, const double* du, con
   }
   const int m = n / 2;
   double fp = 0.0, rp = 0.0;
+  sweep_t w = {1.0, 0.0, 0.0, 0.0};
   for (int i = 0; i < m; ++i) {
-    double l = i == 0 ? 0.0 : dl[i];
-    double piv = d[i] - l * fp;
-    double inv = 1.0 / piv;
-    fp = du[i] * inv;
-    rp = (rhs[i] - l * rp) * inv;
+    sweep_row(&w, i == 0 ? 0.0 : dl[i], d[i], du[i], rhs[i], i, &fp, &rp);
     fac[i] = fp;
     x[i] = rp;
   }
   const double cpm = fp, rpm = rp;
-  fp = 0.0;
-  rp = 0.0;
-  for (int j = n - 1; j >= m; --j) {
-    double u = j == n - 1 ? 0.0 : du[j];
-    double piv = d[j] - u * fp;
-    double inv = 1.0 / piv;
-    fp = dl[j] * inv;
-    rp = (rhs[j] - u * rp) * inv;
+  sweep_t w2 = {1.0, 0.0, 0.0, 0.0};
+  for (int j = n - 1, s = 0; j >= m; --j, ++s) {
+    sweep_row(&w2, j == n - 1 ? 0.0 : du[j], d[j], dl[j], rhs[j], s, &fp, &rp);
     fac[j] = fp;
     x[j] = rp;
   }

@@ -15,4 +15,4 @@ torch.cuda.synchronize(); a.record()
 for _ in range(10): run()
 b.record(); torch.cuda.synchronize()
 ms = a.elapsed_time(b) / 10
-print(f"TMA_disabled={os.environ.get('CTS_DISABLE_TMA','0')} tridiag 2^21 cols: {ms:.3f} ms  {5*8*n/ms/1e6:.0f} GB/s")
+print(f"loader={os.environ.get('CTS_TILE_LOADER','default')} tridiag 2^21 cols: {ms:.3f} ms  {5*8*n/ms/1e6:.0f} GB/s")

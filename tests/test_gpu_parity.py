@@ -165,7 +165,7 @@ def test_tridiag_solve_bit_exact(cts, ctx, dtype, ncols, nlev):
 
 
 def test_tridiag_solve_without_tma_is_identical():
-    # the cooperative-load variant of the tile kernel (CTS_DISABLE_TMA=1) must give the same bits
+    # the cooperative-load variant of the tile kernel (CTS_TILE_LOADER selects cooperative / bulk-TMA / cp.async loaders) must give the same bits
     code = r"""
 import sys, numpy as np, ctypes as C
 sys.path[:0] = [%r, %r, %r]
@@ -182,7 +182,7 @@ assert np.array_equal(x.to_host(), M.babe_solve(dl,d,du,rhs,nl))
 print("OK")
 """ % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
        os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
-    env = dict(os.environ, CTS_DISABLE_TMA="1")
+    env = dict(os.environ, CTS_TILE_LOADER="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]
 

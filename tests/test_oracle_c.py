@@ -78,3 +78,34 @@ def test_lsrk_advection_matches():
         CO.lsrk_advection_step(u2, du2, 1.0, 1.0 / n, 0.5 / n, A, B)
     np.testing.assert_array_equal(u2, u1)
     np.testing.assert_array_equal(du2, du1)
+
+
+@pytest.mark.parametrize("dtype,scale", [(np.float64, 0.1), (np.float64, 22.0), (np.float64, 1e4), (np.float32, 22.0)])
+def test_product_form_accuracy(dtype, scale):
+    """The product-form elimination (reciprocal off the dependent chain) is as accurate as textbook Thomas on
+    diagonally dominant W = dtγJ - I, and never leaves the exponent range thanks to the power-of-two rescaling."""
+    rng = np.random.default_rng(0)
+    nc, n = 500, 64
+    dl = (scale * rng.uniform(.5, 1, nc * n)).astype(dtype)
+    du = (scale * rng.uniform(.5, 1, nc * n)).astype(dtype)
+    d = (-(dl + du) - 1).astype(dtype)
+    r = rng.standard_normal(nc * n).astype(dtype)
+    x = M.babe_solve(dl, d, du, r, n)
+    xe = M.thomas_reference(dl, d, du, r, n)
+    err = np.abs(x.astype(np.longdouble) - xe).reshape(nc, n).max(axis=1) / np.abs(xe).reshape(nc, n).max(axis=1)
+    eps = np.finfo(dtype).eps
+    assert np.isfinite(x).all()
+    assert float(err.max()) < 40 * eps * max(1.0, scale ** 0.5)
+
+
+def test_product_form_large_pivots_do_not_overflow():
+    # pivots ~ 1e30 per row over 128 rows would overflow any un-scaled running product
+    n, nc = 128, 4
+    dl = np.full(nc * n, 1e29)
+    du = np.full(nc * n, 1e29)
+    d = np.full(nc * n, -1e30)
+    r = np.linspace(1, 2, nc * n)
+    x = M.babe_solve(dl, d, du, r, n)
+    xe = M.thomas_reference(dl, d, du, r, n)
+    assert np.isfinite(x).all()
+    assert float(np.max(np.abs(x - xe)) / np.max(np.abs(xe))) < 1e-14
