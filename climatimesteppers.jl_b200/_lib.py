@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcts_sm100a.so")
+LIB_PATH = os.environ.get("CTS_LIB_PATH") or os.path.join(_HERE, "libcts_sm100a.so")  # override for A/B builds
 
 CTS_F32, CTS_F64 = 0, 1
 CTS_MAX_STAGES, CTS_MAX_TERMS = 8, 16

@@ -316,7 +316,10 @@ struct FusedArgs {
   int pitch;
 };
 
-constexpr int kFusedThreads = 256;  // 2 solver warps (a lane pair per column) + 6 more warps that only move data
+#ifndef CTS_FUSED_THREADS
+#define CTS_FUSED_THREADS 128
+#endif
+constexpr int kFusedThreads = CTS_FUSED_THREADS;  // the solver warps (a lane pair per column) + warps that only move data
 
 template <typename T, typename C, int NT, bool MATRIX_FREE>
 __global__ void __launch_bounds__(kFusedThreads) column_fused_stage_kernel(const FusedArgs<NT> a) {
