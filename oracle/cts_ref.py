@@ -377,21 +377,32 @@ def tree_sum(terms: np.ndarray, vn: int = 2) -> float:
     return float(_block_tree(fin))
 
 
+REDUCTION_WINDOW = None  # (offset, count): restrict norms/dots to owned elements (cts_set_reduction_window)
+
+
 def _vn(x):
     return 16 // x.dtype.itemsize
 
 
+def _win(x):
+    x = x.ravel()
+    if REDUCTION_WINDOW is None:
+        return x
+    off, cnt = REDUCTION_WINDOW
+    return x[off:off + cnt]
+
+
 def norm2(x):
-    xd = _wide(x).ravel()
+    xd = _wide(_win(x))
     return math.sqrt(tree_sum(xd * xd, _vn(x)))
 
 
 def dot(x, y):
-    return tree_sum(_wide(x).ravel() * _wide(y).ravel(), _vn(x))
+    return tree_sum(_wide(_win(x)) * _wide(_win(y)), _vn(x))
 
 
 def sum1pabs(x):
-    return tree_sum(1.0 + np.abs(_wide(x).ravel()), _vn(x))
+    return tree_sum(1.0 + np.abs(_wide(_win(x))), _vn(x))
 
 
 @dataclass
@@ -409,7 +420,7 @@ class ForwardDiffJVP:
         elif self.default_step == 2:
             e = math.sqrt(eps * (1 + norm2(x))) / norm2(dx)
         else:
-            e = math.sqrt(eps) * sum1pabs(x) / (x.size * norm2(dx))
+            e = math.sqrt(eps) * sum1pabs(x) / (_win(x).size * norm2(dx))
         return FT(FT(self.step_adjustment) * FT(e))
 
 

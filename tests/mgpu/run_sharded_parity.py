@@ -1,0 +1,97 @@
+"""Launched by torchrun (one rank per GPU): config C5 in miniature.  Every rank steps its slab of the column
+problem on its GPU (library dss! = NCCL halo exchange); rank 0 gathers the owned rows and compares them with the
+single-process numpy oracle of the GLOBAL problem.  Also checks the all-reduced reductions and a sharded JFNK step."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+import cts_b200 as cts  # noqa: E402
+import cts_models as M  # noqa: E402
+import cts_ref as R  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)  # a non-default stream shared by torch and the library (as in bench.py)
+    ctx = cts.Context(local)
+    cts.attach_communicator(ctx, dist)
+    log = lambda *a: print(f"[rank {rank}]", *a, flush=True) if os.environ.get("CTS_MGPU_VERBOSE") else None
+    nx, ny_g, nsteps, dt = 16, 8 * world, 3, 0.01
+    part = cts.SlabPartition(ny_g, world, rank)
+    ok = True
+    for name, newton, nonlinear, krylov in (("ARS343", dict(max_iters=1), False, False),
+                                            ("SSP333", dict(max_iters=2), True, True)):
+        nlev = 16 if krylov else 64  # the frozen-coefficient preconditioner is only effective in the mildly stiff regime
+        K, T0, S = M.column_inputs(nlev, nx, ny_g, part.row0, part.ny_local, 1)
+        dev = lambda a: cts.B200Vector.from_host(a, ctx)
+        op = cts.ColumnOperator(nlev, nx, part.ny_local, dev(K), S_lev=dev(S), nu=1.0, halo=1, nonlinear=nonlinear, ctx=ctx)
+        u = dev(T0)
+        op.dss(u, None, 0.0)
+        off, cnt = part.owned_window(nx, nlev)
+        ctx.set_reduction_window(off, cnt)
+        nm_kw = dict(newton)
+        if krylov:
+            nm_kw["krylov_method"] = cts.KrylovMethod(jacobian_free_jvp=cts.ForwardDiffJVP(), forcing_term=cts.ConstantForcing(1e-3), itmax=30)
+        integ = cts.init(cts.ODEProblem(op.ode_function(), u, (0.0, 1e9), None),
+                         cts.IMEXAlgorithm(getattr(cts, name)(), cts.NewtonsMethod(**nm_kw)), dt=dt, save=False)
+        for k in range(nsteps):
+            cts.step_(integ)
+            log(name, 'step', k, 'done')
+        nrm = u.norm()  # all-reduced over owned rows
+        log(name, 'norm', nrm)
+        own = u.tensor[off:off + cnt].contiguous()
+        parts = [torch.empty_like(own) for _ in range(world)] if rank == 0 else None
+        torch.cuda.synchronize()
+        dist.gather(own, parts, dst=0)
+        torch.cuda.synchronize()
+        log(name, 'gathered')
+        ctx.set_reduction_window(0, 0)
+        if rank == 0:
+            got = torch.cat(parts).cpu().numpy()
+            # oracle: the global problem in one process (periodic ghost rows, halo = 1)
+            Kg, Tg, Sg = M.column_inputs(nlev, nx, ny_g, 0, ny_g, 1)
+            model = M.ColumnModel(nlev, nx, ny_g, Kg, S_lev=Sg, nu=1.0, halo=1, nonlinear=nonlinear)
+            uo = Tg.copy()
+            model.dss(uo, None, 0.0)
+            R.REDUCTION_WINDOW = (nx * nlev, ny_g * nx * nlev)  # norms/dots over owned rows only, like the shards
+            o_kw = dict(newton)
+            if krylov:
+                o_kw["krylov_method"] = R.KrylovMethod(jacobian_free_jvp=R.ForwardDiffJVP(), forcing_term=R.ConstantForcing(1e-3), itmax=30)
+            _, step = R.make_stepper(model.ode_function(), R.imex_algorithm(name, R.NewtonsMethod(**o_kw)), uo)
+            t = 0.0
+            for _ in range(nsteps):
+                step(uo, None, t, dt)
+                t += dt
+            R.REDUCTION_WINDOW = None
+            want = uo[nx * nlev:-nx * nlev]
+            err = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
+            exact = bool(np.array_equal(got, want))
+            nerr = abs(nrm - float(np.linalg.norm(want))) / float(np.linalg.norm(want))
+            # the all-reduce changes the summation order of every dot/norm by a few ulp and the finite-difference JVP
+            # amplifies that (its own noise is ~1e-6 of ||Jv|| at this size): Newton-Krylov parity is a tolerance
+            tol = 0.0 if not krylov else 1e-6
+            good = (exact if not krylov else err <= tol) and nerr < (1e-13 if not krylov else tol)
+            ok = ok and good
+            st = integ.cache.stats()
+            good = good and np.isfinite(got).all() and (not krylov or st["krylov_iters"] < 30 * st["newton_iters"])
+            ok = ok and good
+            print(f"[{world} ranks] {name} nonlinear={nonlinear} krylov={krylov}: rel err {err:.3e} bit-exact={exact} krylov_iters={st['krylov_iters']} "
+                  f"norm rel err {nerr:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
+        dist.barrier()
+    flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
