@@ -322,7 +322,10 @@ struct FusedArgs {
 constexpr int kFusedThreads = CTS_FUSED_THREADS;  // the solver warps (a lane pair per column) + warps that only move data
 
 template <typename T, typename C, int NT, bool MATRIX_FREE>
-__global__ void __launch_bounds__(kFusedThreads) column_fused_stage_kernel(const FusedArgs<NT> a) {
+#ifndef CTS_FUSED_MIN_BLOCKS
+#define CTS_FUSED_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_MIN_BLOCKS) column_fused_stage_kernel(const FusedArgs<NT> a) {
   using V = typename Vec<T>::type;
   constexpr int VN = Vec<T>::N;
   constexpr int NTS = NT > 0 ? NT : 1;
