@@ -6,6 +6,7 @@
 //                                 in one pass over the column tile, (2+nnz)w [+3w for stored W] B/DOF
 // Both produce results bit-identical to the un-fused hook sequence (tests/test_gpu_parity.py).
 #include <cmath>
+#include <cstdlib>
 
 #include "cts_internal.h"
 #include "ew_device.cuh"
@@ -149,6 +150,7 @@ struct cts_op_column {
   size_t rows;   // ny_local + 2*halo
   size_t ncols;  // rows*nx
   bool matrix_free;
+  void* a_col;   // K_col / dz^2 per local column (state precision), computed once at creation
 };
 
 namespace {
@@ -177,14 +179,20 @@ __device__ __forceinline__ T timp_nonlinear(T a, T um, T uc, T up) {
 }
 
 // T_imp: one thread per DOF vector; neighbours along the (contiguous) level axis.
+template <typename T>
+__global__ void column_acol_kernel(T* __restrict__ a, const T* __restrict__ Kcol, T dz, size_t ncols) {
+  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncols) a[c] = col_a<T>(Kcol[c], dz);
+}
+
 template <typename T, bool NONLINEAR>
 __global__ void __launch_bounds__(256) column_timp_kernel(T* __restrict__ out, const T* __restrict__ u,
-                                                          const T* __restrict__ Kcol, T dz, int nlev, size_t n) {
+                                                          const T* __restrict__ acol, int nlev, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   size_t col = i / (size_t)nlev;
   int lev = (int)(i - col * (size_t)nlev);
-  T a = col_a<T>(Kcol[col], dz);
+  T a = acol[col];
   T uc = u[i];
   T um = lev > 0 ? u[i - 1] : T(0);
   T up = lev < nlev - 1 ? u[i + 1] : T(0);
@@ -194,13 +202,13 @@ __global__ void __launch_bounds__(256) column_timp_kernel(T* __restrict__ out, c
 // Wfact: W = dtγ J - I   (tridiagonal; frozen coefficients at u for the nonlinear operator)
 template <typename T, bool NONLINEAR>
 __global__ void __launch_bounds__(256) column_wfact_kernel(T* __restrict__ dl, T* __restrict__ d, T* __restrict__ du,
-                                                           const T* __restrict__ u, const T* __restrict__ Kcol, T dz,
+                                                           const T* __restrict__ u, const T* __restrict__ acol,
                                                            double dtg, int nlev, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   size_t col = i / (size_t)nlev;
   int lev = (int)(i - col * (size_t)nlev);
-  T a = col_a<T>(Kcol[col], dz);
+  T a = acol[col];
   if (!NONLINEAR) {
     double o = __dmul_rn(dtg, (double)a);
     dl[i] = (T)o;
@@ -314,6 +322,7 @@ struct FusedArgs {
   int nlev;
   size_t ncols;
   int pitch;
+  long long* dbg;  // optional phase timeline (CTS_FUSED_TIMELINE=1): 5 clock64 stamps per CTA
 };
 
 #ifndef CTS_FUSED_THREADS
@@ -323,7 +332,7 @@ constexpr int kFusedThreads = CTS_FUSED_THREADS;  // the solver warps (a lane pa
 
 template <typename T, typename C, int NT, bool MATRIX_FREE>
 #ifndef CTS_FUSED_MIN_BLOCKS
-#define CTS_FUSED_MIN_BLOCKS 1
+#define CTS_FUSED_MIN_BLOCKS 5
 #endif
 __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_MIN_BLOCKS) column_fused_stage_kernel(const FusedArgs<NT> a) {
   using V = typename Vec<T>::type;
@@ -339,12 +348,16 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_MIN_BLOCKS) column_fu
   char* sd = smem + 3 * tile_bytes;
   char* sdu = smem + 4 * tile_bytes;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (MATRIX_FREE ? 3 : 5) * tile_bytes);
+  T* sAcol = reinterpret_cast<T*>(smem + (MATRIX_FREE ? 3 : 5) * tile_bytes + 16);  // K/dz^2 of the tile's columns
 
   const int nlev = a.nlev;
   const size_t col0 = (size_t)blockIdx.x * kTileCols;
   const int nvalid = (int)((a.ncols - col0) < (size_t)kTileCols ? (a.ncols - col0) : (size_t)kTileCols);
   const int col_bytes = nlev * (int)sizeof(T);
   const size_t goff = col0 * (size_t)nlev;
+  long long tstamp[5];
+  tstamp[0] = clock64();
+  if ((int)threadIdx.x < nvalid) sAcol[threadIdx.x] = ((const T*)a.Kcol)[col0 + threadIdx.x];  // visible after phase A's barrier
 
   if (!MATRIX_FREE) {  // W tiles arrive by bulk TMA while U0 is being assembled
     if (threadIdx.x == 0) {
@@ -405,45 +418,54 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_MIN_BLOCKS) column_fu
     }
   }
   __syncthreads();
+  tstamp[1] = clock64();
 
-  // ---- phase B (warps 0-1): residual + two-sided Thomas, a lane pair per column ------------------------
+  // ---- phase A2: Newton residual f = (U0 + dtγ T_imp(U0)) - U0 (K3), element-parallel over the tile: every thread
+  // takes 16-byte level vectors of U0 plus the two neighbouring levels and writes the rhs tile. ------------------
+  for (int q = threadIdx.x; q < total; q += kFusedThreads) {
+    const int c = q / cpc, k = q - c * cpc;
+    const T acol = sAcol[c];
+    const T* U0c = reinterpret_cast<const T*>(sU0 + c * pitch);
+    const int l0 = k * VN;
+    T uu[VN], rr[VN];
+    vec_unpack<T>(*reinterpret_cast<const V*>(sU0 + c * pitch + k * 16), uu);
+    T um = l0 > 0 ? U0c[l0 - 1] : T(0);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      const int l = l0 + e;
+      const T up = (e + 1 < VN) ? uu[e + 1 < VN ? e + 1 : e] : (l < nlev - 1 ? U0c[l + 1] : T(0));
+      const T ti = timp_linear<T>(acol, um, uu[e], up);
+      rr[e] = (T)__dsub_rn(__dadd_rn((double)uu[e], __dmul_rn(a.dtg, (double)ti)), (double)uu[e]);
+      um = uu[e];
+    }
+    *reinterpret_cast<V*>(sr + c * pitch + k * 16) = vec_pack<T>(rr);
+  }
+  __syncthreads();
+  tstamp[2] = clock64();
+
+  // ---- phase B (solver warps): two-sided product-form Thomas, a lane pair per column ---------------------
   if (threadIdx.x < kTileThreads) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int col = warp * 16 + lane_column(lane);
     const bool is_up = lane_is_up(lane);
     const bool valid = col < nvalid;
     const int col_off = col * pitch;
-    T acol = T(0);
-    if (valid) {
-      acol = col_a<T>(((const T*)a.Kcol)[col0 + col], (T)a.dz);
-      const T* U0 = reinterpret_cast<const T*>(sU0 + col_off);
-      T* r = reinterpret_cast<T*>(sr + col_off);
-      const int m = nlev / 2;
-      const int lo = is_up ? m : 0, hi = is_up ? nlev : m;
-      T um = lo > 0 ? U0[lo - 1] : T(0);
-      T uc = U0[lo];
-#pragma unroll 4
-      for (int l = lo; l < hi; ++l) {
-        const T up = l < nlev - 1 ? U0[l + 1] : T(0);
-        const T ti = timp_linear<T>(acol, um, uc, up);
-        r[l] = (T)__dsub_rn(__dadd_rn((double)uc, __dmul_rn(a.dtg, (double)ti)), (double)uc);
-        um = uc;
-        uc = up;
-      }
-    }
     if (MATRIX_FREE) {
+      const T acol = valid ? sAcol[col] : T(0);
       const double o = __dmul_rn(a.dtg, (double)acol);
       ConstRows<T> rows{(T)o, (T)__dsub_rn(__dmul_rn(-2.0, o), 1.0), sfac};
-      babe_solve_lanepair<T>(rows, sr, col_off, nlev, is_up, valid);
+      babe_solve_lanepair<T>(rows, RhsFromTile<T>{}, sr, col_off, nlev, is_up, valid);
     } else {
       mbar_wait(bar, 0);
       StoredRows<T> rows{sdl, sd, sdu};
-      babe_solve_lanepair<T>(rows, sr, col_off, nlev, is_up, valid);
+      babe_solve_lanepair<T>(rows, RhsFromTile<T>{}, sr, col_off, nlev, is_up, valid);
     }
   }
   __syncthreads();
+  tstamp[3] = clock64();
 
   // ---- phase C: U = U0 - dx ; Timp = (U - U0)/dtγ ; coalesced 128-bit stores -----------------------
+  const DivConst dc = div_const_prepare(a.dtg);
   for (int q = threadIdx.x; q < total; q += kFusedThreads) {
     const int c = q / cpc, k = q - c * cpc;
     const size_t gi = (goff * sizeof(T) + (size_t)c * col_bytes + (size_t)k * 16) / 16;
@@ -453,10 +475,15 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_MIN_BLOCKS) column_fu
 #pragma unroll
     for (int e = 0; e < VN; ++e) {
       eU[e] = rsub(e0[e], ex[e]);
-      eT[e] = (T)__ddiv_rn((double)rsub(eU[e], e0[e]), a.dtg);
+      eT[e] = (T)div_const((double)rsub(eU[e], e0[e]), dc);
     }
     reinterpret_cast<V*>(a.U)[gi] = vec_pack<T>(eU);
     if (a.Timp) reinterpret_cast<V*>(a.Timp)[gi] = vec_pack<T>(eT);
+  }
+  if (a.dbg && threadIdx.x == 0) {
+    tstamp[4] = clock64();
+#pragma unroll
+    for (int k = 0; k < 5; ++k) a.dbg[(size_t)blockIdx.x * 5 + k] = tstamp[k];
   }
 }
 
@@ -477,7 +504,7 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
   a.U = s->U;
   a.Timp = s->T_imp;
   a.temp = s->temp;
-  a.Kcol = op->d.K_col;
+  a.Kcol = op->a_col;
   a.dtg = s->dtgamma;
   a.dz = op->d.dz;
   a.nlev = op->d.nlev;
@@ -493,7 +520,10 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
     a.dl = a.d = a.du = nullptr;
   }
   size_t tiles = (op->ncols + kTileCols - 1) / kTileCols;
-  size_t smem = (size_t)(mf ? 3 : 5) * kTileCols * a.pitch + 16;
+  size_t smem = (size_t)(mf ? 3 : 5) * kTileCols * a.pitch + 16 + kTileCols * sizeof(T);
+  static const bool timeline = getenv("CTS_FUSED_TIMELINE") != nullptr;  // developer aid: per-phase clock64 averages
+  a.dbg = nullptr;
+  if (timeline) CTS_CUDA(ctx, cudaMalloc(&a.dbg, tiles * 5 * sizeof(long long)));
   if (mf) {
     auto k = column_fused_stage_kernel<T, C, NT, true>;
     CTS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -504,6 +534,17 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
     k<<<(unsigned)tiles, kFusedThreads, smem, ctx->stream>>>(a);
   }
   CTS_LAUNCH_CHECK(ctx);
+  if (timeline) {
+    std::vector<long long> h(tiles * 5);
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpy(h.data(), a.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(a.dbg);
+    double ph[4] = {0, 0, 0, 0};
+    for (size_t i = 0; i < tiles; ++i)
+      for (int k = 0; k < 4; ++k) ph[k] += (double)(h[i * 5 + k + 1] - h[i * 5 + k]);
+    fprintf(stderr, "[cts fused timeline] NT=%d mf=%d tiles=%zu avg cycles: A(load+K1)=%.0f residual=%.0f solve=%.0f C(store)=%.0f\n", NT,
+            (int)mf, tiles, ph[0] / tiles, ph[1] / tiles, ph[2] / tiles, ph[3] / tiles);
+  }
   return CTS_OK;
 }
 
@@ -565,11 +606,24 @@ int cts_op_column_create(cts_ctx* ctx, cts_dtype ft, const cts_column_desc* desc
   op->rows = desc->ny_local + 2 * (size_t)desc->halo;
   op->ncols = op->rows * desc->nx;
   op->matrix_free = false;
+  op->a_col = nullptr;
+  int r = cts_alloc(ctx, op->ncols * cts_sizeof(ft), &op->a_col);
+  if (r != CTS_OK) {
+    delete op;
+    return r;
+  }
+  unsigned blocks = (unsigned)((op->ncols + 255) / 256);
+  if (ft == CTS_F64)
+    column_acol_kernel<double><<<blocks, 256, 0, ctx->stream>>>((double*)op->a_col, (const double*)desc->K_col, desc->dz, op->ncols);
+  else
+    column_acol_kernel<float><<<blocks, 256, 0, ctx->stream>>>((float*)op->a_col, (const float*)desc->K_col, (float)desc->dz, op->ncols);
+  CTS_LAUNCH_CHECK(ctx);
   *out = op;
   return CTS_OK;
 }
 
 int cts_op_column_destroy(cts_op_column* op) {
+  if (op && op->a_col) cts_free(op->ctx, op->a_col);
   delete op;
   return CTS_OK;
 }
@@ -618,14 +672,14 @@ int cts_op_column_T_imp(void* vop, void* du, const void* u, double t) {
   const int nl = op->d.nlev;
   if (op->ft == CTS_F64) {
     if (op->d.nonlinear)
-      column_timp_kernel<double, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)du, (const double*)u, (const double*)op->d.K_col, op->d.dz, nl, n);
+      column_timp_kernel<double, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)du, (const double*)u, (const double*)op->a_col, nl, n);
     else
-      column_timp_kernel<double, false><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)du, (const double*)u, (const double*)op->d.K_col, op->d.dz, nl, n);
+      column_timp_kernel<double, false><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)du, (const double*)u, (const double*)op->a_col, nl, n);
   } else {
     if (op->d.nonlinear)
-      column_timp_kernel<float, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)du, (const float*)u, (const float*)op->d.K_col, (float)op->d.dz, nl, n);
+      column_timp_kernel<float, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)du, (const float*)u, (const float*)op->a_col, nl, n);
     else
-      column_timp_kernel<float, false><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)du, (const float*)u, (const float*)op->d.K_col, (float)op->d.dz, nl, n);
+      column_timp_kernel<float, false><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)du, (const float*)u, (const float*)op->a_col, nl, n);
   }
   CTS_LAUNCH_CHECK(ctx);
   return CTS_OK;
@@ -641,14 +695,14 @@ int cts_op_column_Wfact(void* vop, void* vW, const void* u, double dtgamma, doub
   const int nl = op->d.nlev;
   if (op->ft == CTS_F64) {
     if (op->d.nonlinear)
-      column_wfact_kernel<double, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)W->dl, (double*)W->d, (double*)W->du, (const double*)u, (const double*)op->d.K_col, op->d.dz, dtgamma, nl, n);
+      column_wfact_kernel<double, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)W->dl, (double*)W->d, (double*)W->du, (const double*)u, (const double*)op->a_col, dtgamma, nl, n);
     else
-      column_wfact_kernel<double, false><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)W->dl, (double*)W->d, (double*)W->du, (const double*)u, (const double*)op->d.K_col, op->d.dz, dtgamma, nl, n);
+      column_wfact_kernel<double, false><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)W->dl, (double*)W->d, (double*)W->du, (const double*)u, (const double*)op->a_col, dtgamma, nl, n);
   } else {
     if (op->d.nonlinear)
-      column_wfact_kernel<float, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)W->dl, (float*)W->d, (float*)W->du, (const float*)u, (const float*)op->d.K_col, (float)op->d.dz, dtgamma, nl, n);
+      column_wfact_kernel<float, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)W->dl, (float*)W->d, (float*)W->du, (const float*)u, (const float*)op->a_col, dtgamma, nl, n);
     else
-      column_wfact_kernel<float, false><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)W->dl, (float*)W->d, (float*)W->du, (const float*)u, (const float*)op->d.K_col, (float)op->d.dz, dtgamma, nl, n);
+      column_wfact_kernel<float, false><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)W->dl, (float*)W->d, (float*)W->du, (const float*)u, (const float*)op->a_col, dtgamma, nl, n);
   }
   CTS_LAUNCH_CHECK(ctx);
   return CTS_OK;

@@ -1,4 +1,4 @@
-for v in mb6 mb8; do
+for v in mb3 mb4; do
   for mf in "" "--matrix-free"; do
     CTS_LIB_PATH=$PWD/scratch/variants/lib_$v.so python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extras $mf > /tmp/b.json 2>/dev/null
     python -c "

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kTileThreads) k(const double* dl, const double
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = warp * 16 + lane_column(lane);
   StoredRows<double> rows{sdl, sd, sdu};
-  babe_solve_lanepair<double>(rows, sr, col * pitch, nlev, lane_is_up(lane), true);
+  babe_solve_lanepair<double>(rows, RhsFromTile<double>{}, sr, col * pitch, nlev, lane_is_up(lane), true);
   __syncthreads();
   long long t2 = clock64();
   coop_store_tile((char*)(x + goff), sr, nvalid, col_bytes, pitch);
