@@ -118,6 +118,7 @@ struct cts_fused_stage_args {
   int compute_native;
   double dtgamma;
   const cts_tridiag* W;  // stored W (ignored when matrix free)
+  int emit_W;            // stored W is stale: regenerate it in the kernel for dtgamma and write it to W (no read)
   void* U;               // out: stage value
   void* T_imp;           // out: (U - U0)/dtγ, may be null
   void* temp;            // out (optional): U0

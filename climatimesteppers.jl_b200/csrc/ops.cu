@@ -5,6 +5,7 @@
 //   * cts_column_fused_stage    : K1 + K2 + T_imp + K3 + K4 + K5 + K6 of one implicit ARK/SSPRK stage
 //                                 in one pass over the column tile, (2+nnz)w [+3w for stored W] B/DOF
 // Both produce results bit-identical to the un-fused hook sequence (tests/test_gpu_parity.py).
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
@@ -296,6 +297,84 @@ __global__ void __launch_bounds__(256) column_texp_kernel(T* __restrict__ out, c
   }
 }
 
+// Marching variant (used whenever the level count is a multiple of the 16-byte vector): a thread owns one 16-byte level vector of a row chunk and walks ROWS rows of the slow horizontal
+// axis with a sliding (south, centre, north) register window, so each element is fetched once per strip instead of
+// three times; west/east come from lines the CTA touched one iteration earlier (L1).  Same arithmetic.
+template <typename T, int VN, int ROWS>
+__global__ void __launch_bounds__(256) column_texp_march_kernel(T* __restrict__ out, const T* __restrict__ u,
+                                                                const T* __restrict__ S, T g, T nu, unsigned nlev,
+                                                                unsigned nx, unsigned row_elems, size_t ny_local,
+                                                                int halo, int has_src) {
+  using V = typename Vec<T>::type;
+  const unsigned r = (blockIdx.x * 256u + threadIdx.x) * VN;
+  if (r >= row_elems) return;
+  const size_t rows = ny_local + 2 * (size_t)halo;
+  const unsigned ix = r / nlev, lev = r - ix * nlev;
+  const unsigned wrap = (nx - 1) * nlev;
+  const unsigned rw = ix == 0 ? r + wrap : r - nlev;
+  const unsigned re = ix == nx - 1 ? r - wrap : r + nlev;
+  T src[VN];
+#pragma unroll
+  for (int e = 0; e < VN; ++e) src[e] = T(0);
+  if (has_src) {
+    T t[VN];
+    vec_unpack<T>(*reinterpret_cast<const V*>(S + lev), t);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) src[e] = rmul(t[e], g);
+  }
+  const size_t jr0 = (size_t)blockIdx.y * ROWS;
+  const size_t jr1 = jr0 + ROWS < ny_local ? jr0 + ROWS : ny_local;
+  // row of the local array that holds owned row jr (jr = -1 and jr = ny_local are the neighbours across the slab
+  // edge: ghost rows with a halo, the periodic wrap without)
+  auto row_of = [&](long long jr) -> const T* {
+    size_t j;
+    if (halo)
+      j = (size_t)(jr + 1);
+    else
+      j = jr < 0 ? rows - 1 : ((size_t)jr == rows ? 0 : (size_t)jr);
+    return u + j * (size_t)row_elems;
+  };
+  V vs = *reinterpret_cast<const V*>(row_of((long long)jr0 - 1) + r);
+  V vc = *reinterpret_cast<const V*>(row_of((long long)jr0) + r);
+  auto emit = [&](size_t jr, const V& vw, const V& ve, const V& vn) {
+    T c[VN], w[VN], e_[VN], s_[VN], n_[VN], val[VN];
+    vec_unpack<T>(vc, c);
+    vec_unpack<T>(vw, w);
+    vec_unpack<T>(ve, e_);
+    vec_unpack<T>(vs, s_);
+    vec_unpack<T>(vn, n_);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      const T lap = rsub(radd(radd(radd(w[e], e_[e]), s_[e]), n_[e]), rmul(T(4), c[e]));
+      val[e] = radd(src[e], rmul(nu, lap));
+    }
+    *reinterpret_cast<V*>(out + (jr + (size_t)halo) * (size_t)row_elems + r) = vec_pack<T>(val);
+    vs = vc;
+    vc = vn;
+  };
+  constexpr int B = 4;  // rows per batch: 3*B independent 16-byte loads in flight per thread
+  size_t jr = jr0;
+  for (; jr + B <= jr1; jr += B) {
+    V vn[B], vw[B], ve[B];
+#pragma unroll
+    for (int k = 0; k < B; ++k) {
+      const T* crow = row_of((long long)(jr + k));
+      vn[k] = *reinterpret_cast<const V*>(row_of((long long)(jr + k) + 1) + r);
+      vw[k] = *reinterpret_cast<const V*>(crow + rw);
+      ve[k] = *reinterpret_cast<const V*>(crow + re);
+    }
+#pragma unroll
+    for (int k = 0; k < B; ++k) emit(jr + k, vw[k], ve[k], vn[k]);
+  }
+  for (; jr < jr1; ++jr) {
+    const T* crow = row_of((long long)jr);
+    const V vn = *reinterpret_cast<const V*>(row_of((long long)jr + 1) + r);
+    const V vw = *reinterpret_cast<const V*>(crow + rw);
+    const V ve = *reinterpret_cast<const V*>(crow + re);
+    emit(jr, vw, ve, vn);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Fused implicit stage for the LINEAR column operator, Newton max_iters = 1, direct solve:
 //   U0   = (c0*base + G1) + G2                        K1  (fused_increment.jl:220-236)
@@ -322,6 +401,7 @@ struct FusedArgs {
   int nlev;
   size_t ncols;
   int pitch;
+  int emit_w;      // matrix-free launch that also writes W = dtγJ - I into dl/d/du (replaces a separate Wfact pass)
   long long* dbg;  // optional phase timeline (CTS_FUSED_TIMELINE=1): 5 clock64 stamps per CTA
 };
 
@@ -479,6 +559,19 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_MIN_BLOCKS) column_fu
     }
     reinterpret_cast<V*>(a.U)[gi] = vec_pack<T>(eU);
     if (a.Timp) reinterpret_cast<V*>(a.Timp)[gi] = vec_pack<T>(eT);
+    if (MATRIX_FREE && a.emit_w) {  // same expressions as column_wfact_kernel
+      const double o = __dmul_rn(a.dtg, (double)sAcol[c]);
+      T eo[VN], ed[VN];
+#pragma unroll
+      for (int e = 0; e < VN; ++e) {
+        eo[e] = (T)o;
+        ed[e] = (T)__dsub_rn(__dmul_rn(-2.0, o), 1.0);
+      }
+      const V vo = vec_pack<T>(eo);
+      reinterpret_cast<V*>(const_cast<void*>(a.dl))[gi] = vo;
+      reinterpret_cast<V*>(const_cast<void*>(a.d))[gi] = vec_pack<T>(ed);
+      reinterpret_cast<V*>(const_cast<void*>(a.du))[gi] = vo;
+    }
   }
   if (a.dbg && threadIdx.x == 0) {
     tstamp[4] = clock64();
@@ -510,14 +603,16 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
   a.nlev = op->d.nlev;
   a.ncols = op->ncols;
   a.pitch = pitch_bytes(op->d.nlev, sizeof(T));
-  const bool mf = op->matrix_free;
-  if (!mf) {
+  const bool mf = op->matrix_free || s->emit_W;
+  a.emit_w = s->emit_W;
+  if (!op->matrix_free) {
     if (!s->W) return cts_fail(ctx, CTS_EINVAL, "fused stage: stored W required");
     a.dl = s->W->dl;
     a.d = s->W->d;
     a.du = s->W->du;
   } else {
     a.dl = a.d = a.du = nullptr;
+    a.emit_w = 0;
   }
   size_t tiles = (op->ncols + kTileCols - 1) / kTileCols;
   size_t smem = (size_t)(mf ? 3 : 5) * kTileCols * a.pitch + 16 + kTileCols * sizeof(T);
@@ -732,7 +827,16 @@ int cts_op_column_T_exp(void* vop, void* du_exp, void* du_lim, const void* u, do
   int has_src = d.S_lev != nullptr;
   const int vn = op->ft == CTS_F64 ? 2 : 4;
   const bool vec = (d.nlev % vn) == 0 && cts_aligned16(du_exp) && cts_aligned16(u) && (!has_src || cts_aligned16(d.S_lev));
-  if (vec) {
+  const size_t row_elems = d.nx * (size_t)d.nlev;
+  if (vec && row_elems < (1ull << 31) && d.nu != 0.0 && (d.ny_local + 7) / 8 <= 65535) {
+    // strips of 8 rows (25 % of the rows are fetched twice, from L2): measured best of 8/16/32/64/128 on B200
+    constexpr int ROWS = 8;
+    dim3 grid((unsigned)((row_elems / vn + 255) / 256), (unsigned)((d.ny_local + ROWS - 1) / ROWS));
+    if (op->ft == CTS_F64)
+      column_texp_march_kernel<double, 2, ROWS><<<grid, 256, 0, ctx->stream>>>((double*)du_exp, (const double*)u, (const double*)d.S_lev, g, d.nu, (unsigned)d.nlev, (unsigned)d.nx, (unsigned)row_elems, d.ny_local, d.halo, has_src);
+    else
+      column_texp_march_kernel<float, 4, ROWS><<<grid, 256, 0, ctx->stream>>>((float*)du_exp, (const float*)u, (const float*)d.S_lev, (float)g, (float)d.nu, (unsigned)d.nlev, (unsigned)d.nx, (unsigned)row_elems, d.ny_local, d.halo, has_src);
+  } else if (vec) {
     size_t blocks = (n_owned / vn + 255) / 256;
     if (op->ft == CTS_F64)
       column_texp_kernel<double, 2><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)du_exp, (const double*)u, (const double*)d.S_lev, g, d.nu, d.nlev, d.nx, d.ny_local, d.halo, has_src);

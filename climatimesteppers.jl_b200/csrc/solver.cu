@@ -432,6 +432,10 @@ struct cts_imex_cache {
   bool has_gamma = false;
   double gamma = 0.0;
   bool fusion = true;
+  bool w_pending = false;   // a due Wfact(dt·γ) folded into the next fused stage launch (which writes W itself)
+  double w_pending_dtg = 0.0;
+  const void* w_pending_u = nullptr;
+  double w_pending_t = 0.0;
   // ARK
   void* U = nullptr;
   void* temp = nullptr;
@@ -513,12 +517,28 @@ int assign_with_increments(cts_imex_cache* c, void* out, void* out2, double c0, 
   return cts_axpy_n(c->ctx, c->ft, c->n, out, out2, c0, base, g1.n, g2.n, coef, terms, native_flag(c));
 }
 
-int maybe_update_jacobian(cts_imex_cache* c, const void* u, double t, double dt) {  // async_utils.jl:11-31
+int maybe_update_jacobian(cts_imex_cache* c, const void* u, double t, double dt, bool defer = false) {  // async_utils.jl:11-31
   if (!c->f.T_imp || !c->ncfg.present || !c->nm || !c->nm->W) return CTS_OK;
   if (!needs_update(c->ncfg.update_j, CTS_SIG_NEW_TIMESTEP, t)) return CTS_OK;
+  if (defer) {  // the first fused stage of this step regenerates W in registers and stores it: no separate pass
+    c->w_pending = true;
+    c->w_pending_dtg = dt * c->gamma;
+    c->w_pending_u = u;
+    c->w_pending_t = t;
+    c->stats.wfact_evals++;
+    return CTS_OK;
+  }
   cts_prof_scope ps(c->ctx, CTS_PROF_WFACT);
   HOOK(c->ctx, c->f.Wfact(c->f.ud, c->nm->W, u, dt * c->gamma, t));
   c->stats.wfact_evals++;
+  return CTS_OK;
+}
+
+int flush_pending_jacobian(cts_imex_cache* c) {  // a deferred Wfact that no fused stage consumed
+  if (!c->w_pending) return CTS_OK;
+  c->w_pending = false;
+  cts_prof_scope ps(c->ctx, CTS_PROF_WFACT);
+  HOOK(c->ctx, c->f.Wfact(c->f.ud, c->nm->W, c->w_pending_u, c->w_pending_dtg, c->w_pending_t));
   return CTS_OK;
 }
 
@@ -577,12 +597,18 @@ int fused_implicit_stage(cts_imex_cache* c, cts_op_column* op, void* U, double c
   // Jacobian refresh exactly when the reference would do it inside solve_newton! (the linear operator's W
   // does not depend on the state, so the stage value is not needed to build it).
   const bool mf = cts_op_column_matrix_free(op);
+  bool emit_W = false;
   if (needs_update(c->ncfg.update_j, CTS_SIG_NEW_NEWTON_SOLVE) || needs_update(c->ncfg.update_j, CTS_SIG_NEW_NEWTON_ITERATION)) {
-    if (!mf) {
-      cts_prof_scope ps(c->ctx, CTS_PROF_WFACT);
-      HOOK(c->ctx, c->f.Wfact(c->f.ud, c->nm->W, base, dtg, t_imp));
-    }
+    emit_W = !mf;  // W(dtγ of this stage) is produced and stored by the stage kernel itself
+    c->w_pending = false;
     c->stats.wfact_evals++;
+  } else if (c->w_pending) {
+    if (dtg == c->w_pending_dtg) {
+      emit_W = true;
+      c->w_pending = false;
+    } else {
+      CTS_TRY(flush_pending_jacobian(c));
+    }
   }
   cts_fused_stage_args a{};
   a.base = base;
@@ -601,6 +627,7 @@ int fused_implicit_stage(cts_imex_cache* c, cts_op_column* op, void* U, double c
   a.compute_native = native_flag(c);
   a.dtgamma = dtg;
   a.W = static_cast<const cts_tridiag*>(c->nm->W);
+  a.emit_W = emit_W ? 1 : 0;
   a.U = U;
   a.T_imp = T_imp_out;
   a.temp = nullptr;
@@ -624,7 +651,7 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
   const bool has_T_imp = f.T_imp != nullptr;
   cts_op_column* fuse_op = fusable_column_op(c);
   // (a matrix-free fused stage regenerates W in the kernel: the stored copy is never read)
-  if (!(fuse_op && cts_op_column_matrix_free(fuse_op))) CTS_TRY(maybe_update_jacobian(c, u, t, dt));
+  if (!(fuse_op && cts_op_column_matrix_free(fuse_op))) CTS_TRY(maybe_update_jacobian(c, u, t, dt, fuse_op != nullptr));
 
   for (int i = 0; i < s; ++i) {
     const double t_exp = t + dt * tab.c_exp[i];
@@ -705,6 +732,7 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
   }
 
   // final update :79-101
+  CTS_TRY(flush_pending_jacobian(c));
   const double t_final = t + dt;
   Increment inc_exp = has_T_exp ? raw_increment(c, dt, tab.b_exp, s, c->T_exp) : Increment{};
   Increment inc_imp = has_T_imp ? raw_increment(c, dt, tab.b_imp, s, c->T_imp) : Increment{};
@@ -743,7 +771,7 @@ int ssprk_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
   const int native = native_flag(c);
   cts_op_column* fuse_op = fusable_column_op(c);
   auto beta_c = [&](double b) { return native ? (double)(float)b : b; };
-  if (!(fuse_op && cts_op_column_matrix_free(fuse_op))) CTS_TRY(maybe_update_jacobian(c, u, t, dt));
+  if (!(fuse_op && cts_op_column_matrix_free(fuse_op))) CTS_TRY(maybe_update_jacobian(c, u, t, dt, fuse_op != nullptr));
 
   for (int i = 0; i < s; ++i) {
     const double t_exp = t + dt * tab.c_exp[i];
@@ -818,6 +846,7 @@ int ssprk_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
     }
   }
 
+  CTS_TRY(flush_pending_jacobian(c));
   const double t_final = t + dt;
   Increment inc_imp = has_T_imp ? raw_increment(c, dt, tab.b_imp, s, c->T_imp) : Increment{};
   if (c->beta[s - 1] != 0) {

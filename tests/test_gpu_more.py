@@ -225,3 +225,44 @@ def test_benchmark_step_table(cts):
         assert all(ms >= 0 for ms, _ in prof.values())
     ctx.prof_enable(False)
     assert ctx.launch_count() > l0
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("policy", ["NewTimeStep", "NewNewtonSolve"])
+def test_fused_stage_emits_the_stored_W(cts, dtype, policy):
+    # The fused path folds Wfact into a stage launch (the kernel writes W instead of reading it): afterwards the
+    # Newton cache's W must hold exactly what Wfact(W, u, p, dtγ, t) writes (newtons_method.jl:596, imex_ark.jl:304).
+    np_dt = np.float64 if dtype == "f64" else np.float32
+    nlev, nx, ny = 32, 24, 5
+    K = (0.25 + 0.5 * M.fill_hash((ny + 2) * nx, 2)).astype(np_dt)
+    op = cts.ColumnOperator(nlev, nx, ny, dev(cts, K), nu=1.0, halo=1)
+    u = dev(cts, M.fill_hash(op.ndof, 3).astype(np_dt))
+    alg = cts.IMEXAlgorithm(cts.ARS343(), cts.NewtonsMethod(max_iters=1, update_j=cts.UpdateEvery(getattr(cts, policy))))
+    integ = cts.init(cts.ODEProblem(op.ode_function(), u, (0.0, 1e9), None), alg, dt=0.02, save=False)
+    for _ in range(2):
+        cts.step_(integ)
+    assert integ.cache.stats()["fused_stage_launches"] == 6
+    got = [v.to_host() for v in integ.cache.jac.diagonals()]
+    ref = op.jac_prototype().zero()
+    gamma = 0.4358665215084590
+    op.Wfact(ref, u, None, 0.02 * gamma, 0.0)
+    for g, r in zip(got, (v.to_host() for v in ref.diagonals())):
+        np.testing.assert_array_equal(g, r)
+
+
+@pytest.mark.parametrize("shape", [(64, 8, 1), (64, 1, 3), (64, 5, 9), (64, 3, 17), (16, 40, 33), (6, 7, 5), (7, 4, 3)])
+@pytest.mark.parametrize("halo", [0, 1])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_T_exp_shapes_bit_exact(cts, shape, halo, dtype):
+    # the marching stencil kernel (strips of 8 rows, batches of 4) against the numpy model: strip tails, a single
+    # row / column (periodic neighbours are the element itself), level counts that force the scalar kernel
+    nlev, nx, ny = shape
+    K, T0, S = M.column_inputs(nlev, nx, ny, 0, ny, halo, dtype)
+    model = M.ColumnModel(nlev, nx, ny, K, S_lev=S, nu=0.7, halo=halo)
+    op = cts.ColumnOperator(nlev, nx, ny, dev(cts, K), S_lev=dev(cts, S), nu=0.7, halo=halo)
+    want = np.zeros(model.n, dtype)
+    model.T_exp(want, T0, None, 0.3)
+    u = dev(cts, T0)
+    got = cts.B200Vector.zeros(model.n, dtype)
+    op.T_exp(got, u, None, 0.3)
+    np.testing.assert_array_equal(got.to_host(), want)
