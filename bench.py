@@ -297,7 +297,12 @@ def run_ours(args):
         achieved = per_step * (fs_n / 3.0) / (fs_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "column_fused_stage_kernel (K1+K2+T_imp+K3+K4+K5+K6 of one implicit stage)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": None, "launches": fs_n, "avg_launch_ms": fs_ms / fs_n,
+                "nominal_peak": 8000.0, "frac_of_nominal": achieved / 8000.0,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch (mean of the step's 3 launches) from the
+                # ncu --set full capture summarised in profiles/r1_step_kernels_ncu.txt; same workload, stored W only
+                "traffic": 9.668e9 if (stored_w and ndof_local == 134348800) else None,
+                "algorithmic_bytes_per_launch": per_step / 3.0,
+                "launches": fs_n, "avg_launch_ms": fs_ms / fs_n,
                 "algorithmic_bytes_per_dof_per_launch": stage_bytes(stored_w),
                 "share_of_step": fs_ms / ms}
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items()}

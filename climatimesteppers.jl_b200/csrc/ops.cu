@@ -580,6 +580,183 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_MIN_BLOCKS) column_fu
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-resident variant of the fused stage (the one the engine normally runs).  When a column is a power-of-two
+// number (<= 32) of 16-byte vectors, consecutive lanes hold consecutive level vectors of one column, so the K3
+// residual's level neighbours come from warp shuffles and U0 never has to live in shared memory: every thread keeps its
+// (at most kKeep) U0 vectors in registers across the solve and reuses them in the epilogue.  Shared memory per tile
+// drops from 5 to 4 column tiles (stored W) or from 3 to 2 (matrix free), and the separate residual phase with its
+// barrier disappears.  Arithmetic is identical to the kernel above.  (Measured on B200: capping registers at 80 to fit
+// 6 CTAs per SM costs the solver more than the extra CTA gives: 6.1 ms vs 5.4 ms per step; 64/96-thread CTAs have too
+// few loads in flight: 6.7 ms.  So: 128 threads, <= 96 registers, 5 CTAs per SM.)
+constexpr int kKeep = (kTileCols * 32 + kFusedThreads - 1) / kFusedThreads;  // U0 vectors per thread at 32 vectors/column
+
+#ifndef CTS_FUSED_REG_MIN_BLOCKS
+#define CTS_FUSED_REG_MIN_BLOCKS 5
+#endif
+template <typename T, typename C, int NT, bool MATRIX_FREE>
+__global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) column_fused_stage_reg_kernel(const FusedArgs<NT> a) {
+  using V = typename Vec<T>::type;
+  constexpr int VN = Vec<T>::N;
+  constexpr int NTS = NT > 0 ? NT : 1;
+  extern __shared__ __align__(128) char smem[];
+  const int pitch = a.pitch;
+  const int tile_bytes = kTileCols * pitch;
+  char* sx = smem;                   // residual -> rp -> dx
+  char* sfac = smem + tile_bytes;    // matrix-free: cp scratch; stored: dl tile (d and du follow)
+  char* sdl = sfac;
+  char* sd = smem + 2 * tile_bytes;
+  char* sdu = smem + 3 * tile_bytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (MATRIX_FREE ? 2 : 4) * tile_bytes);
+  T* sAcol = reinterpret_cast<T*>(smem + (MATRIX_FREE ? 2 : 4) * tile_bytes + 16);
+
+  const int nlev = a.nlev;
+  const size_t col0 = (size_t)blockIdx.x * kTileCols;
+  const int nvalid = (int)((a.ncols - col0) < (size_t)kTileCols ? (a.ncols - col0) : (size_t)kTileCols);
+  const int col_bytes = nlev * (int)sizeof(T);
+  const size_t goff = col0 * (size_t)nlev;
+  if (MATRIX_FREE && (int)threadIdx.x < nvalid) sAcol[threadIdx.x] = ((const T*)a.Kcol)[col0 + threadIdx.x];
+
+  if (!MATRIX_FREE) {  // W tiles arrive by bulk TMA while U0 is being assembled
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+      mbar_arrive_expect_tx(bar, (uint32_t)(3 * nvalid * col_bytes));
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nvalid) {
+      const int c = threadIdx.x;
+      const size_t g = goff + (size_t)c * nlev;
+      bulk_g2s(sdl + c * pitch, (const T*)a.dl + g, col_bytes, bar);
+      bulk_g2s(sd + c * pitch, (const T*)a.d + g, col_bytes, bar);
+      bulk_g2s(sdu + c * pitch, (const T*)a.du + g, col_bytes, bar);
+    }
+  }
+
+  // ---- phase A: U0 = K1(base, terms) in registers, residual f = (U0 + dtγ T_imp(U0)) - U0 (K3) through warp
+  // shuffles, residual tile to shared memory.  cpc = vectors per column (power of two <= 32). ----------------
+  const int cpc = col_bytes / 16;
+  const int cshift = 31 - __clz(cpc);
+  const int total = nvalid * cpc;
+  V keep[kKeep];
+  constexpr int UN = 2;
+  static_assert(kKeep % UN == 0, "rounds are processed in pairs");
+#pragma unroll
+  for (int r0 = 0; r0 < kKeep; r0 += UN) {
+    V vb[UN], vt[NTS][UN];
+    size_t gi[UN];
+    int so[UN], kk[UN];
+    bool ok[UN];
+    T acol[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int q = (int)threadIdx.x + (r0 + u) * kFusedThreads;
+      ok[u] = q < total;
+      const int col = q >> cshift;
+      kk[u] = q & (cpc - 1);
+      so[u] = col * pitch + kk[u] * 16;
+      gi[u] = (goff * sizeof(T) + (size_t)col * col_bytes + (size_t)kk[u] * 16) / 16;  // 16-byte vector index
+      acol[u] = T(0);
+      if (ok[u]) {
+        vb[u] = reinterpret_cast<const V*>(a.ax.base)[gi[u]];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) vt[t][u] = reinterpret_cast<const V*>(a.ax.terms[t])[gi[u]];
+        acol[u] = ((const T*)a.Kcol)[col0 + col];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      T eb[VN], uu[VN], rr[VN], et[NTS][VN];
+      vec_unpack<T>(vb[u], eb);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) vec_unpack<T>(vt[t][u], et[t]);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) {
+        T x[NTS];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) x[t] = et[t][e];
+        uu[e] = axpy_combine<T, C, NT>(eb[e], x, a.ax);
+      }
+      keep[r0 + u] = vec_pack<T>(uu);
+      // level neighbours across the vector boundary: the previous / next lane of the same column segment
+      T below = __shfl_up_sync(0xffffffffu, uu[VN - 1], 1, cpc);
+      T above = __shfl_down_sync(0xffffffffu, uu[0], 1, cpc);
+      if (kk[u] == 0) below = T(0);        // Dirichlet 0 below level 0
+      if (kk[u] == cpc - 1) above = T(0);  // ... and above the top level
+#pragma unroll
+      for (int e = 0; e < VN; ++e) {
+        const T um = e > 0 ? uu[e > 0 ? e - 1 : 0] : below;
+        const T up = e + 1 < VN ? uu[e + 1 < VN ? e + 1 : e] : above;
+        const T ti = timp_linear<T>(acol[u], um, uu[e], up);
+        rr[e] = (T)__dsub_rn(__dadd_rn((double)uu[e], __dmul_rn(a.dtg, (double)ti)), (double)uu[e]);
+      }
+      if (ok[u]) {
+        *reinterpret_cast<V*>(sx + so[u]) = vec_pack<T>(rr);
+        if (a.temp) reinterpret_cast<V*>(a.temp)[gi[u]] = keep[r0 + u];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B (solver warps): two-sided product-form Thomas, a lane pair per column ---------------------
+  if (threadIdx.x < kTileThreads) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = warp * 16 + lane_column(lane);
+    const bool is_up = lane_is_up(lane);
+    const bool valid = col < nvalid;
+    const int col_off = col * pitch;
+    if (MATRIX_FREE) {
+      const T acol = valid ? sAcol[col] : T(0);
+      const double o = __dmul_rn(a.dtg, (double)acol);
+      ConstRows<T> rows{(T)o, (T)__dsub_rn(__dmul_rn(-2.0, o), 1.0), sfac};
+      babe_solve_lanepair<T>(rows, RhsFromTile<T>{}, sx, col_off, nlev, is_up, valid);
+    } else {
+      mbar_wait(bar, 0);
+      StoredRows<T> rows{sdl, sd, sdu};
+      babe_solve_lanepair<T>(rows, RhsFromTile<T>{}, sx, col_off, nlev, is_up, valid);
+    }
+  } else if (MATRIX_FREE && a.emit_w) {
+    // the warps that only move data write W = dtγJ - I (same expressions as column_wfact_kernel) while the solver
+    // warp works: the stores overlap the elimination instead of lengthening the epilogue
+    for (int q = (int)threadIdx.x - kTileThreads; q < total; q += kFusedThreads - kTileThreads) {
+      const int c = q >> cshift, k = q & (cpc - 1);
+      const size_t gi = (goff * sizeof(T) + (size_t)c * col_bytes + (size_t)k * 16) / 16;
+      const double o = __dmul_rn(a.dtg, (double)sAcol[c]);
+      T eo[VN], ed[VN];
+#pragma unroll
+      for (int e = 0; e < VN; ++e) {
+        eo[e] = (T)o;
+        ed[e] = (T)__dsub_rn(__dmul_rn(-2.0, o), 1.0);
+      }
+      const V vo = vec_pack<T>(eo);
+      reinterpret_cast<V*>(const_cast<void*>(a.dl))[gi] = vo;
+      reinterpret_cast<V*>(const_cast<void*>(a.d))[gi] = vec_pack<T>(ed);
+      reinterpret_cast<V*>(const_cast<void*>(a.du))[gi] = vo;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase C: U = U0 - dx ; Timp = (U - U0)/dtγ ; coalesced 128-bit stores; U0 from registers ----------
+  const DivConst dc = div_const_prepare(a.dtg);
+#pragma unroll
+  for (int r = 0; r < kKeep; ++r) {
+    const int q = (int)threadIdx.x + r * kFusedThreads;
+    if (q >= total) continue;
+    const int c = q >> cshift, k = q & (cpc - 1);
+    const size_t gi = (goff * sizeof(T) + (size_t)c * col_bytes + (size_t)k * 16) / 16;
+    T e0[VN], ex[VN], eU[VN], eT[VN];
+    vec_unpack<T>(keep[r], e0);
+    vec_unpack<T>(*reinterpret_cast<const V*>(sx + c * pitch + k * 16), ex);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      eU[e] = rsub(e0[e], ex[e]);
+      eT[e] = (T)div_const((double)rsub(eU[e], e0[e]), dc);
+    }
+    reinterpret_cast<V*>(a.U)[gi] = vec_pack<T>(eU);
+    if (a.Timp) reinterpret_cast<V*>(a.Timp)[gi] = vec_pack<T>(eT);
+  }
+}
+
 template <typename T, typename C, int NT>
 int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
   cts_ctx* ctx = op->ctx;
@@ -615,8 +792,25 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
     a.emit_w = 0;
   }
   size_t tiles = (op->ncols + kTileCols - 1) / kTileCols;
-  size_t smem = (size_t)(mf ? 3 : 5) * kTileCols * a.pitch + 16 + kTileCols * sizeof(T);
   static const bool timeline = getenv("CTS_FUSED_TIMELINE") != nullptr;  // developer aid: per-phase clock64 averages
+  static const bool no_reg = getenv("CTS_FUSED_NO_REG") != nullptr;      // developer aid: force the 5-tile kernel
+  const int cpc = op->d.nlev * (int)sizeof(T) / 16;
+  if (!timeline && !no_reg && cpc >= 1 && cpc <= 32 && (cpc & (cpc - 1)) == 0) {
+    size_t smem_reg = (size_t)(mf ? 2 : 4) * kTileCols * a.pitch + 16 + kTileCols * sizeof(T);
+    a.dbg = nullptr;
+    if (mf) {
+      auto k = column_fused_stage_reg_kernel<T, C, NT, true>;
+      CTS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_reg));
+      k<<<(unsigned)tiles, kFusedThreads, smem_reg, ctx->stream>>>(a);
+    } else {
+      auto k = column_fused_stage_reg_kernel<T, C, NT, false>;
+      CTS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_reg));
+      k<<<(unsigned)tiles, kFusedThreads, smem_reg, ctx->stream>>>(a);
+    }
+    CTS_LAUNCH_CHECK(ctx);
+    return CTS_OK;
+  }
+  size_t smem = (size_t)(mf ? 3 : 5) * kTileCols * a.pitch + 16 + kTileCols * sizeof(T);
   a.dbg = nullptr;
   if (timeline) CTS_CUDA(ctx, cudaMalloc(&a.dbg, tiles * 5 * sizeof(long long)));
   if (mf) {
