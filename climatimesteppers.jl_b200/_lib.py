@@ -103,6 +103,7 @@ SIGNATURES = [
     ("cts_memcpy_d2h_sync", _I, [_P, _P, _P, _SZ]),
     ("cts_memcpy_d2d", _I, [_P, _P, _P, _SZ]),
     ("cts_axpy_n", _I, [_P, _I, _SZ, _P, _P, _D, _P, _I, _I, c_double_p, c_void_pp, _I]),
+    ("cts_ssprk_stage", _I, [_P, _I, _SZ, _P, _P, _P, _P, _P, _P, _D, _I, _D, _D, _I, c_double_p, c_void_pp, _I, _I]),
     ("cts_newton_residual", _I, [_P, _I, _SZ, _P, _P, _D, _P]),
     ("cts_sub_inplace", _I, [_P, _I, _SZ, _P, _P]),
     ("cts_timp_from_stage", _I, [_P, _I, _SZ, _P, _P, _P, _D]),

@@ -121,6 +121,157 @@ int dispatch_axpy(cts_ctx* ctx, size_t n, void* out, void* out2, double c0, cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// K11: one Shu-Osher stage assembly of the IMEX-SSPRK scheme in a single pass (imex_ssprk.jl:112-122,162-169; the
+// reference runs these as 3-4 separate broadcasts):
+//   e1    = U_exp + dt*T_exp                 (rounded to T, as the stand-alone pass stores it)
+//   blend = (1-β)*u + β*e1                   -> U_exp   (rounded to T unless this is the final update)
+//   U     = blend + Σ coef_k*T_imp_k         -> U, temp
+// Every operation is individually rounded in the same order as the chained passes, so results are bit-identical.
+template <int NT>
+struct SspArgs {
+  AxpyArgs<NT> ax;  // coef/terms of the implicit increment; ax.out = U (nullable), ax.out2 = temp (nullable)
+  const void* xexp;
+  const void* texp;  // nullable
+  const void* u;
+  void* out_exp;     // nullable
+  double dt, beta, omb;
+  int dt_native, final_update;
+};
+
+template <typename T, typename C, int NT>
+__device__ __forceinline__ void ssp_combine(T xe, T te, T uu, const T (&x)[NT > 0 ? NT : 1], const SspArgs<NT>& a, T& o_exp, T& o_u) {
+  T e1 = xe;
+  if (a.texp) {
+    if (a.dt_native)
+      e1 = (T)op_add((float)xe, op_mul((float)a.dt, (float)te));
+    else
+      e1 = (T)op_add((double)xe, op_mul(a.dt, (double)te));
+  }
+  C blend = op_add(op_mul((C)a.omb, (C)uu), op_mul((C)a.beta, (C)e1));
+  o_exp = (T)blend;
+  if (!a.final_update) blend = (C)o_exp;
+  if (NT > 0) {
+    C g = 0;
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+      C p = op_mul((C)a.ax.coef[k], (C)x[k]);
+      g = (k == 0) ? p : op_add(g, p);
+    }
+    o_u = (T)op_add(blend, g);
+  } else {
+    o_u = o_exp;
+  }
+}
+
+template <typename T, typename C, int NT, int UNROLL>
+__global__ void __launch_bounds__(256) ssprk_stage_vec_kernel(const SspArgs<NT> a, size_t nvec) {
+  using V = typename Vec<T>::type;
+  constexpr int VN = Vec<T>::N;
+  constexpr int NTS = NT > 0 ? NT : 1;
+  const size_t tile = (size_t)blockIdx.x * (blockDim.x * UNROLL);
+  V vx[UNROLL], vT[UNROLL], vu[UNROLL], vt[NTS][UNROLL];
+  bool ok[UNROLL];
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    size_t i = tile + (size_t)u * blockDim.x + threadIdx.x;
+    ok[u] = i < nvec;
+    if (ok[u]) {
+      vx[u] = reinterpret_cast<const V*>(a.xexp)[i];
+      vT[u] = a.texp ? reinterpret_cast<const V*>(a.texp)[i] : vx[u];
+      vu[u] = reinterpret_cast<const V*>(a.u)[i];
+#pragma unroll
+      for (int k = 0; k < NT; ++k) vt[k][u] = reinterpret_cast<const V*>(a.ax.terms[k])[i];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    if (!ok[u]) continue;
+    size_t i = tile + (size_t)u * blockDim.x + threadIdx.x;
+    T ex[VN], eT[VN], eu[VN], oe[VN], oU[VN], et[NTS][VN];
+    vec_unpack<T>(vx[u], ex);
+    vec_unpack<T>(vT[u], eT);
+    vec_unpack<T>(vu[u], eu);
+#pragma unroll
+    for (int k = 0; k < NT; ++k) vec_unpack<T>(vt[k][u], et[k]);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      T x[NTS];
+#pragma unroll
+      for (int k = 0; k < NT; ++k) x[k] = et[k][e];
+      ssp_combine<T, C, NT>(ex[e], eT[e], eu[e], x, a, oe[e], oU[e]);
+    }
+    if (a.out_exp) reinterpret_cast<V*>(a.out_exp)[i] = vec_pack<T>(oe);
+    V vo = vec_pack<T>(oU);
+    if (a.ax.out) reinterpret_cast<V*>(a.ax.out)[i] = vo;
+    if (a.ax.out2) reinterpret_cast<V*>(a.ax.out2)[i] = vo;
+  }
+}
+
+template <typename T, typename C, int NT>
+__global__ void __launch_bounds__(256) ssprk_stage_scalar_kernel(const SspArgs<NT> a, size_t begin, size_t n) {
+  constexpr int NTS = NT > 0 ? NT : 1;
+  size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T xe = reinterpret_cast<const T*>(a.xexp)[i];
+  T te = a.texp ? reinterpret_cast<const T*>(a.texp)[i] : xe;
+  T uu = reinterpret_cast<const T*>(a.u)[i];
+  T x[NTS];
+#pragma unroll
+  for (int k = 0; k < NT; ++k) x[k] = reinterpret_cast<const T*>(a.ax.terms[k])[i];
+  T oe, oU;
+  ssp_combine<T, C, NT>(xe, te, uu, x, a, oe, oU);
+  if (a.out_exp) reinterpret_cast<T*>(a.out_exp)[i] = oe;
+  if (a.ax.out) reinterpret_cast<T*>(a.ax.out)[i] = oU;
+  if (a.ax.out2) reinterpret_cast<T*>(a.ax.out2)[i] = oU;
+}
+
+template <typename T, typename C, int NT>
+int launch_ssprk(cts_ctx* ctx, size_t n, SspArgs<NT> a, const double* coef, const void* const* terms) {
+  bool aligned = cts_aligned16(a.xexp) && cts_aligned16(a.u) && (!a.texp || cts_aligned16(a.texp)) &&
+                 (!a.out_exp || cts_aligned16(a.out_exp)) && (!a.ax.out || cts_aligned16(a.ax.out)) &&
+                 (!a.ax.out2 || cts_aligned16(a.ax.out2));
+  for (int k = 0; k < NT; ++k) {
+    a.ax.terms[k] = terms[k];
+    a.ax.coef[k] = coef[k];
+    aligned = aligned && cts_aligned16(terms[k]);
+  }
+  constexpr int VN = Vec<T>::N;
+  constexpr int UNROLL = (NT <= 2) ? 2 : 1;
+  size_t nvec = aligned ? n / VN : 0;
+  if (nvec > 0) {
+    size_t per_block = (size_t)256 * UNROLL;
+    ssprk_stage_vec_kernel<T, C, NT, UNROLL><<<(unsigned)((nvec + per_block - 1) / per_block), 256, 0, ctx->stream>>>(a, nvec);
+    CTS_LAUNCH_CHECK(ctx);
+  }
+  size_t done = nvec * VN;
+  if (done < n) {
+    ssprk_stage_scalar_kernel<T, C, NT><<<(unsigned)((n - done + 255) / 256), 256, 0, ctx->stream>>>(a, done, n);
+    CTS_LAUNCH_CHECK(ctx);
+  }
+  return CTS_OK;
+}
+
+template <typename T, typename C>
+int dispatch_ssprk(cts_ctx* ctx, size_t n, int nt, void* U_exp_out, void* U_out, void* temp_out, const void* U_exp,
+                   const void* T_exp, const void* u, double dt, int dt_native, double beta, double omb,
+                   const double* coef, const void* const* terms, int final_update) {
+  switch (nt) {
+#define CASE(N)                                                                                  \
+  case N: {                                                                                      \
+    SspArgs<N> a{};                                                                              \
+    a.ax.out = U_out; a.ax.out2 = temp_out; a.ax.base = nullptr; a.ax.c0 = 1.0; a.ax.n1 = N; a.ax.scale_base = 0; \
+    a.xexp = U_exp; a.texp = T_exp; a.u = u; a.out_exp = U_exp_out;                              \
+    a.dt = dt; a.beta = beta; a.omb = omb; a.dt_native = dt_native; a.final_update = final_update; \
+    return launch_ssprk<T, C, N>(ctx, n, a, coef, terms);                                        \
+  }
+    CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+    default:
+      return cts_fail(ctx, CTS_EINVAL, "cts_ssprk_stage: more than 8 implicit terms");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // generic small element-wise kernels: out = f(a, b, c)
 // ---------------------------------------------------------------------------------------------
 template <typename T, int NIN, typename F>
@@ -241,6 +392,23 @@ int cts_axpy_n(cts_ctx* ctx, cts_dtype ft, size_t n, void* out, void* out2, doub
   if (ft == CTS_F64) return dispatch_axpy<double, double>(ctx, n, out, out2, c0, base, n_grp1, nt, coef, terms);
   if (compute_native) return dispatch_axpy<float, float>(ctx, n, out, out2, c0, base, n_grp1, nt, coef, terms);
   return dispatch_axpy<float, double>(ctx, n, out, out2, c0, base, n_grp1, nt, coef, terms);
+}
+
+int cts_ssprk_stage(cts_ctx* ctx, cts_dtype ft, size_t n, void* U_exp_out, void* U_out, void* temp_out, const void* U_exp,
+                    const void* T_exp, const void* u, double dt, int dt_native, double beta, double one_minus_beta,
+                    int n_imp, const double* coef, const void* const* terms, int compute_native, int final_update) {
+  CTS_CHECK_CTX(ctx);
+  if (n == 0) return CTS_OK;
+  if (!U_exp || !u || n_imp < 0 || (n_imp > 0 && (!coef || !terms)) || (!U_exp_out && !U_out))
+    return cts_fail(ctx, CTS_EINVAL, "cts_ssprk_stage: bad arguments");
+  if (ft == CTS_F64)
+    return dispatch_ssprk<double, double>(ctx, n, n_imp, U_exp_out, U_out, temp_out, U_exp, T_exp, u, dt, 0, beta,
+                                          one_minus_beta, coef, terms, final_update);
+  if (compute_native)
+    return dispatch_ssprk<float, float>(ctx, n, n_imp, U_exp_out, U_out, temp_out, U_exp, T_exp, u, dt, dt_native, beta,
+                                        one_minus_beta, coef, terms, final_update);
+  return dispatch_ssprk<float, double>(ctx, n, n_imp, U_exp_out, U_out, temp_out, U_exp, T_exp, u, dt, dt_native, beta,
+                                       one_minus_beta, coef, terms, final_update);
 }
 
 int cts_newton_residual(cts_ctx* ctx, cts_dtype ft, size_t n, void* r, const void* U0, double dtgamma, const void* Up) {

@@ -778,37 +778,50 @@ int ssprk_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
     const double t_imp = t + dt * tab.c_imp[i];
     const double aii = A(tab.a_imp, s, i, i);
     const double dtg = dt * aii;
+    Increment inc_imp = has_T_imp ? raw_increment(c, dt, &tab.a_imp[i * s], i, c->T_imp) : Increment{};
+    const bool no_imp = !has_T_imp || aii == 0;
+    const bool has_imp_terms = col_nonzero(tab.a_imp, s, i) || tab.b_imp[i] != 0;
+    const bool fuse_column = fuse_op && !no_imp;
+    // `temp = U` (:190) can ride along with the assembly when no hook touches U in between
+    const bool temp_rides = !no_imp && !fuse_column && i != 0 && !f.dss && !f.constrain_state && !f.cache_imp;
+    bool assembled = false, temp_done = false;
     if (i == 0) {
       cts_prof_scope ps(c->ctx, CTS_PROF_STAGE_ASSEMBLY);
       CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->U_exp, nullptr, 1.0, u, 0, 0, nullptr, nullptr, 0));  // :155
     } else if (c->beta[i - 1] != 0) {
-      if (f.has_lim) {
-        CTS_TRY(axpy_dt(c, c->U_lim, c->U_exp, dt, c->T_lim1, dt_is_f32));
-        if (f.lim) HOOK(c->ctx, f.lim(f.ud, c->U_lim, t_exp, c->U_exp));
-        CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->U_exp, nullptr, 1.0, c->U_lim, 0, 0, nullptr, nullptr, 0));
-      }
-      if (has_T_exp) CTS_TRY(axpy_dt(c, c->U_exp, c->U_exp, dt, c->T_exp1, dt_is_f32));
-      // `@. U_exp = (1 - β) * u + β * U_exp`  :165
       const double b = beta_c(c->beta[i - 1]);
       const double omb = native ? (double)(1.0f - (float)b) : 1.0 - b;
-      double coef[1] = {b};
-      const void* terms[1] = {c->U_exp};
-      {
+      if (!f.has_lim && c->fusion && inc_imp.n <= 8) {
+        // K11: `U_exp += dt*T_exp` :162, `U_exp = (1-β)u + βU_exp` :165, `U = U_exp + inc_imp` :169 (and `temp = U`)
+        // in one pass; the fused column stage assembles U itself, so only U_exp is produced for it.
+        cts_prof_scope ps(c->ctx, CTS_PROF_STAGE_ASSEMBLY);
+        CTS_TRY(cts_ssprk_stage(c->ctx, c->ft, c->n, c->U_exp, fuse_column ? nullptr : c->U, temp_rides ? c->temp : nullptr,
+                                c->U_exp, has_T_exp ? c->T_exp1 : nullptr, u, dt, (dt_is_f32 && c->ft == CTS_F32) ? 1 : 0, b,
+                                omb, fuse_column ? 0 : inc_imp.n, inc_imp.coef, inc_imp.term, native, 0));
+        assembled = !fuse_column;
+        temp_done = temp_rides;
+      } else {
+        if (f.has_lim) {
+          CTS_TRY(axpy_dt(c, c->U_lim, c->U_exp, dt, c->T_lim1, dt_is_f32));
+          if (f.lim) HOOK(c->ctx, f.lim(f.ud, c->U_lim, t_exp, c->U_exp));
+          CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->U_exp, nullptr, 1.0, c->U_lim, 0, 0, nullptr, nullptr, 0));
+        }
+        if (has_T_exp) CTS_TRY(axpy_dt(c, c->U_exp, c->U_exp, dt, c->T_exp1, dt_is_f32));
+        // `@. U_exp = (1 - β) * u + β * U_exp`  :165
+        double coef[1] = {b};
+        const void* terms[1] = {c->U_exp};
         cts_prof_scope ps(c->ctx, CTS_PROF_STAGE_ASSEMBLY);
         CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->U_exp, nullptr, omb, u, 1, 0, coef, terms, native));
+        // NB: c0 == 1 would skip the multiply; (1-β) == 1 only when β == 0, which this branch excludes.
       }
-      // NB: c0 == 1 would skip the multiply; (1-β) == 1 only when β == 0, which this branch excludes.
     }
-    Increment inc_imp = has_T_imp ? raw_increment(c, dt, &tab.a_imp[i * s], i, c->T_imp) : Increment{};
-    const bool no_imp = !has_T_imp || aii == 0;
-    const bool has_imp_terms = col_nonzero(tab.a_imp, s, i) || tab.b_imp[i] != 0;
     bool stage_done = false;
-    if (fuse_op && !no_imp) {
+    if (fuse_column) {
       CTS_TRY(fused_implicit_stage(c, fuse_op, c->U, 1.0, c->U_exp, inc_imp, Increment{}, dtg, t_imp,
                                    has_imp_terms ? c->T_imp[i] : nullptr));
       CTS_TRY(call_dss(c, c->U, t_imp));
       stage_done = true;
-    } else {
+    } else if (!assembled) {
       CTS_TRY(assign_with_increments(c, c->U, nullptr, 1.0, c->U_exp, inc_imp, Increment{}));  // :169
     }
     if (!stage_done) {
@@ -821,7 +834,7 @@ int ssprk_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
       if (!no_imp) {
         if (!c->ncfg.present || !c->nm) return cts_fail(c->ctx, CTS_EINVAL, "implicit stage without a NewtonsMethod");
         if (i != 0) CTS_TRY(call_state(c, f.cache_imp, c->U, t_imp));
-        {
+        if (!temp_done) {
           cts_prof_scope ps(c->ctx, CTS_PROF_NEWTON_EW);
           CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->temp, nullptr, 1.0, c->U, 0, 0, nullptr, nullptr, 0));  // :190
         }
@@ -849,7 +862,14 @@ int ssprk_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
   CTS_TRY(flush_pending_jacobian(c));
   const double t_final = t + dt;
   Increment inc_imp = has_T_imp ? raw_increment(c, dt, tab.b_imp, s, c->T_imp) : Increment{};
-  if (c->beta[s - 1] != 0) {
+  if (c->beta[s - 1] != 0 && !f.has_lim && c->fusion && inc_imp.n <= 8) {
+    // K11, final form: `U_exp += dt*T_exp` :117 and `u = (1-β)u + βU_exp + inc_imp` :120-122 in one pass
+    const double b = beta_c(c->beta[s - 1]);
+    const double omb = native ? (double)(1.0f - (float)b) : 1.0 - b;
+    cts_prof_scope ps(c->ctx, CTS_PROF_FINAL_UPDATE);
+    CTS_TRY(cts_ssprk_stage(c->ctx, c->ft, c->n, nullptr, u, nullptr, c->U_exp, has_T_exp ? c->T_exp1 : nullptr, u, dt,
+                            (dt_is_f32 && c->ft == CTS_F32) ? 1 : 0, b, omb, inc_imp.n, inc_imp.coef, inc_imp.term, native, 1));
+  } else if (c->beta[s - 1] != 0) {
     if (f.has_lim) {
       CTS_TRY(axpy_dt(c, c->U_lim, c->U_exp, dt, c->T_lim1, dt_is_f32));
       if (f.lim) HOOK(c->ctx, f.lim(f.ud, c->U_lim, t_final, c->U_exp));

@@ -106,6 +106,15 @@ int cts_prof_read(cts_ctx* ctx, double* ms_per_category /*[CTS_PROF_NCAT]*/, uin
 int cts_axpy_n(cts_ctx* ctx, cts_dtype ft, size_t n, void* out, void* out2, double c0, const void* base,
                int n_grp1, int n_grp2, const double* coef /*host*/, const void* const* terms /*host array of device ptrs*/,
                int compute_native);
+
+/* K11 -- one Shu-Osher stage assembly of IMEX-SSPRK in a single pass; replaces the chained broadcasts
+ * `@. U_exp += dt*T_exp` (imex_ssprk.jl:117,162), `@. U_exp = (1-β)*u + β*U_exp` (:165), `@. U = U_exp + inc_imp` (:169)
+ * and `@. temp = U` (:190), or with final_update != 0 `@. u = (1-β)*u + β*U_exp + inc_imp` (:120-122).  Each operation
+ * is rounded exactly as in the separate passes.  U_exp_out / U_out / temp_out may be NULL (not both of the first two);
+ * T_exp may be NULL (no explicit tendency); in-place use (U_exp_out == U_exp, U_out == u) is allowed. */
+int cts_ssprk_stage(cts_ctx* ctx, cts_dtype ft, size_t n, void* U_exp_out, void* U_out, void* temp_out, const void* U_exp,
+                    const void* T_exp, const void* u, double dt, int dt_native, double beta, double one_minus_beta,
+                    int n_imp, const double* coef, const void* const* terms, int compute_native, int final_update);
 /* K3  `@. residual = U0 + dtγ * residual - U'` (imex_ark.jl:297); r holds T_imp(U') on entry */
 int cts_newton_residual(cts_ctx* ctx, cts_dtype ft, size_t n, void* r, const void* U0, double dtgamma, const void* Up);
 /* K5  `x .-= Δx` (newtons_method.jl:651) */

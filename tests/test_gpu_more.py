@@ -266,3 +266,47 @@ def test_T_exp_shapes_bit_exact(cts, shape, halo, dtype):
     got = cts.B200Vector.zeros(model.n, dtype)
     op.T_exp(got, u, None, 0.3)
     np.testing.assert_array_equal(got.to_host(), want)
+
+
+@pytest.mark.parametrize("dtype,native", [("f64", 0), ("f32", 0), ("f32", 1)])
+@pytest.mark.parametrize("n_imp", [0, 1, 2])
+@pytest.mark.parametrize("final", [0, 1])
+def test_K11_ssprk_stage_equals_chained_passes(cts, dtype, native, n_imp, final):
+    # cts_ssprk_stage against the chain of cts_axpy_n passes it replaces (imex_ssprk.jl:117-122,162-169)
+    import ctypes as C
+    from cts_b200 import _lib as L
+    ctx = cts.Context.default()
+    lib = ctx.lib
+    np_dt = np.float64 if dtype == "f64" else np.float32
+    ft = 1 if dtype == "f64" else 0
+    ft = L.DTYPE[dtype] if hasattr(L, "DTYPE") else ft
+    n = 4099  # odd: exercises the scalar tail
+    mk = lambda seed: dev(cts, (M.fill_hash(n, seed) - 0.5).astype(np_dt))
+    u, xexp, texp = mk(1), mk(2), mk(3)
+    timp = [mk(10 + k) for k in range(n_imp)]
+    coef = (C.c_double * max(1, n_imp))(*[0.013 * (k + 1) for k in range(n_imp)])
+    terms = (C.c_void_p * max(1, n_imp))(*[t.ptr for t in timp])
+    dt, beta = 0.0371, 2.0 / 3.0
+    b = float(np.float32(beta)) if native else beta
+    omb = float(np.float32(1) - np.float32(b)) if native else 1.0 - b
+    dt_native = 1 if (native and dtype == "f32") else 0
+    # chained reference on the device
+    e = cts.B200Vector.zeros(n, np_dt)
+    one_c, one_t = (C.c_double * 1)(dt), (C.c_void_p * 1)(texp.ptr)
+    ctx.check(lib.cts_axpy_n(ctx.handle, ft, n, e.ptr, None, 1.0, xexp.ptr, 1, 0, one_c, one_t, dt_native))
+    ref_U, ref_exp = cts.B200Vector.zeros(n, np_dt), cts.B200Vector.zeros(n, np_dt)
+    bc, bt = (C.c_double * 1)(b), (C.c_void_p * 1)(e.ptr)
+    if final:
+        allc = (C.c_double * (1 + n_imp))(b, *[coef[k] for k in range(n_imp)])
+        allt = (C.c_void_p * (1 + n_imp))(e.ptr, *[t.ptr for t in timp])
+        ctx.check(lib.cts_axpy_n(ctx.handle, ft, n, ref_U.ptr, None, omb, u.ptr, 1, n_imp, allc, allt, native))
+    else:
+        ctx.check(lib.cts_axpy_n(ctx.handle, ft, n, ref_exp.ptr, None, omb, u.ptr, 1, 0, bc, bt, native))
+        ctx.check(lib.cts_axpy_n(ctx.handle, ft, n, ref_U.ptr, None, 1.0, ref_exp.ptr, n_imp, 0, coef, terms, native))
+    got_U, got_exp, got_temp = (cts.B200Vector.zeros(n, np_dt) for _ in range(3))
+    ctx.check(lib.cts_ssprk_stage(ctx.handle, ft, n, None if final else got_exp.ptr, got_U.ptr, got_temp.ptr, xexp.ptr, texp.ptr,
+                                  u.ptr, dt, dt_native, b, omb, n_imp, coef, terms, native, final))
+    np.testing.assert_array_equal(got_U.to_host(), ref_U.to_host())
+    np.testing.assert_array_equal(got_temp.to_host(), ref_U.to_host())
+    if not final:
+        np.testing.assert_array_equal(got_exp.to_host(), ref_exp.to_host())
