@@ -10,7 +10,7 @@ from ._lib import CTSError, LIB_PATH
 from .algorithms import (SSP, ConstantForcing, EisenstatWalkerForcing, ExplicitAlgorithm, ForwardDiffJVP,
                          ForwardDiffStepSize1, ForwardDiffStepSize2, ForwardDiffStepSize3, IMEXAlgorithm,
                          KrylovMethod, LowStorageRungeKutta2N, LSRK54CarpenterKennedy, LSRK144NiegemannDiehlBusch,
-                         LSRKEulerMethod, NewtonsMethod, TimeSteppingAlgorithm, Unconstrained)
+                         LSRKEulerMethod, NewtonsMethod, RosenbrockAlgorithm, TimeSteppingAlgorithm, Unconstrained)
 from .device import B200Vector, Context, axpy_n
 from .functions import (ClimaODEFunction, EndOfStage, EndOfStep, IncrementingODEFunction, NewNewtonIteration,
                         NewNewtonSolve, NewTimeStep, ODEFunction, ODEProblem, ODESolution, Returns_nothing,
@@ -20,6 +20,6 @@ from .integrators import (CallbackSet, DiscreteCallback, EveryXSimulationSteps, 
                           solve_, step_)
 from .operators import AdvectionOperator, ColumnOperator, ColumnTridiag
 from .parallel import SlabPartition, attach_communicator
-from .solvers import IMEXCache, LSRKCache, init_cache, step_u
+from .solvers import IMEXCache, LSRKCache, RosenbrockCache, init_cache, step_u
 from .tableaus import *  # noqa: F401,F403  (named tableaux: ARS343, SSP333, ...)
-from .tableaus import IMEX_NAMES, EXPLICIT_NAMES, IMEXTableau, is_fsal
+from .tableaus import IMEX_NAMES, EXPLICIT_NAMES, IMEXTableau, RosenbrockTableau, SSPKnoth, is_fsal, tableau

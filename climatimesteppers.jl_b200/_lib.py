@@ -57,6 +57,11 @@ class ImexTableau(C.Structure):
                 ("cast_to_state_eltype", C.c_int)]
 
 
+class RosenbrockTableau(C.Structure):
+    _fields_ = [("s", C.c_int), ("A", C.c_double * 64), ("alpha", C.c_double * 64), ("C", C.c_double * 64),
+                ("Gamma", C.c_double * 64), ("m", C.c_double * 8)]
+
+
 class NewtonConfig(C.Structure):
     _fields_ = [("present", C.c_int), ("max_iters", C.c_int), ("update_j", UpdateHandler), ("use_krylov", C.c_int),
                 ("jacobian_free_jvp", C.c_int), ("jvp_step_kind", C.c_int), ("jvp_step_adjustment", C.c_double),
@@ -103,6 +108,12 @@ SIGNATURES = [
     ("cts_memcpy_d2h_sync", _I, [_P, _P, _P, _SZ]),
     ("cts_memcpy_d2d", _I, [_P, _P, _P, _SZ]),
     ("cts_axpy_n", _I, [_P, _I, _SZ, _P, _P, _D, _P, _I, _I, c_double_p, c_void_pp, _I]),
+    ("cts_axpy_chain", _I, [_P, _I, _SZ, _P, _P, _I, c_double_p, c_void_pp, _D, _I]),
+    ("cts_rosenbrock_cache_create", _I, [_P, _I, _SZ, _P, _P, TENDENCY_FN, _P]),
+    ("cts_rosenbrock_cache_destroy", _I, [_P]),
+    ("cts_rosenbrock_step", _I, [_P, _P, _D, _D]),
+    ("cts_rosenbrock_cache_buffer", _I, [_P, C.c_char_p, _P]),
+    ("cts_rosenbrock_cache_stats", _I, [_P, _P]),
     ("cts_ssprk_stage", _I, [_P, _I, _SZ, _P, _P, _P, _P, _P, _P, _D, _I, _D, _D, _I, c_double_p, c_void_pp, _I, _I]),
     ("cts_newton_residual", _I, [_P, _I, _SZ, _P, _P, _D, _P]),
     ("cts_sub_inplace", _I, [_P, _I, _SZ, _P, _P]),

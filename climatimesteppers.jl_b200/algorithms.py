@@ -134,6 +134,15 @@ def ExplicitAlgorithm(name_or_tableau, constraint: Optional[str] = None) -> IMEX
     return IMEXAlgorithm(name_or_tableau, None, constraint)
 
 
+class RosenbrockAlgorithm(TimeSteppingAlgorithm):
+    """``RosenbrockAlgorithm(tableau)`` (rosenbrock.jl:48-70): one linear solve per stage, no Newton iteration."""
+
+    def __init__(self, tableau: T.RosenbrockTableau):
+        if not isinstance(tableau, T.RosenbrockTableau):
+            raise TypeError("RosenbrockAlgorithm takes a RosenbrockTableau, e.g. tableau(SSPKnoth())")
+        self.tableau = tableau
+
+
 # ---- low-storage RK --------------------------------------------------------------------------------
 class LowStorageRungeKutta2N(TimeSteppingAlgorithm):
     def tableau(self, dtype):

@@ -272,6 +272,112 @@ int dispatch_ssprk(cts_ctx* ctx, size_t n, int nt, void* U_exp_out, void* U_out,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Chained accumulation  out = ((((base + c1*x1) + c2*x2) + ...) + cn*xn) * scale,  every operation rounded in Float64
+// and the result rounded to T once: what a sequence of `y .+= c .* x` broadcasts followed by `y .*= s` computes when the
+// intermediate array is Float64 -- or T == double.  (For a Float32 state the reference rounds to Float32 after each
+// pass; that case is handled by `round_each`.)  base == nullptr starts from a literal zero (`fill!(y, 0)`).
+// Used by the Rosenbrock step (rosenbrock.jl:178-214,231-233).
+template <typename T, int NT, int UNROLL>
+__global__ void __launch_bounds__(256) axpy_chain_vec_kernel(const AxpyArgs<NT> a, double scale, int has_scale, int round_each,
+                                                             size_t nvec) {
+  using V = typename Vec<T>::type;
+  constexpr int VN = Vec<T>::N;
+  constexpr int NTS = NT > 0 ? NT : 1;
+  const size_t tile = (size_t)blockIdx.x * (blockDim.x * UNROLL);
+  V vb[UNROLL], vt[NTS][UNROLL];
+  bool ok[UNROLL];
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    size_t i = tile + (size_t)u * blockDim.x + threadIdx.x;
+    ok[u] = i < nvec;
+    if (ok[u]) {
+      if (a.base) vb[u] = reinterpret_cast<const V*>(a.base)[i];
+#pragma unroll
+      for (int k = 0; k < NT; ++k) vt[k][u] = reinterpret_cast<const V*>(a.terms[k])[i];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    if (!ok[u]) continue;
+    size_t i = tile + (size_t)u * blockDim.x + threadIdx.x;
+    T eb[VN], eo[VN], et[NTS][VN];
+    if (a.base) vec_unpack<T>(vb[u], eb);
+#pragma unroll
+    for (int k = 0; k < NT; ++k) vec_unpack<T>(vt[k][u], et[k]);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      double r = a.base ? (double)eb[e] : 0.0;
+#pragma unroll
+      for (int k = 0; k < NT; ++k) {
+        r = op_add(r, op_mul(a.coef[k], (double)et[k][e]));
+        if (round_each) r = (double)(T)r;
+      }
+      if (has_scale) r = op_mul(r, scale);
+      eo[e] = (T)r;
+    }
+    reinterpret_cast<V*>(a.out)[i] = vec_pack<T>(eo);
+  }
+}
+
+template <typename T, int NT>
+__global__ void __launch_bounds__(256) axpy_chain_scalar_kernel(const AxpyArgs<NT> a, double scale, int has_scale,
+                                                                int round_each, size_t begin, size_t n) {
+  size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double r = a.base ? (double)reinterpret_cast<const T*>(a.base)[i] : 0.0;
+#pragma unroll
+  for (int k = 0; k < NT; ++k) {
+    r = op_add(r, op_mul(a.coef[k], (double)reinterpret_cast<const T*>(a.terms[k])[i]));
+    if (round_each) r = (double)(T)r;
+  }
+  if (has_scale) r = op_mul(r, scale);
+  reinterpret_cast<T*>(a.out)[i] = (T)r;
+}
+
+template <typename T, int NT>
+int launch_chain(cts_ctx* ctx, size_t n, void* out, const void* base, const double* coef, const void* const* terms,
+                 double scale, int has_scale) {
+  AxpyArgs<NT> a{};
+  a.base = base;
+  a.out = out;
+  bool aligned = (!base || cts_aligned16(base)) && cts_aligned16(out);
+  for (int k = 0; k < NT; ++k) {
+    a.terms[k] = terms[k];
+    a.coef[k] = coef[k];
+    aligned = aligned && cts_aligned16(terms[k]);
+  }
+  constexpr int VN = Vec<T>::N;
+  constexpr int UNROLL = (NT <= 1) ? 4 : (NT <= 4 ? 2 : 1);
+  const int round_each = sizeof(T) == 4;
+  size_t nvec = aligned ? n / VN : 0;
+  if (nvec > 0) {
+    size_t per_block = (size_t)256 * UNROLL;
+    axpy_chain_vec_kernel<T, NT, UNROLL><<<(unsigned)((nvec + per_block - 1) / per_block), 256, 0, ctx->stream>>>(a, scale, has_scale, round_each, nvec);
+    CTS_LAUNCH_CHECK(ctx);
+  }
+  size_t done = nvec * VN;
+  if (done < n) {
+    axpy_chain_scalar_kernel<T, NT><<<(unsigned)((n - done + 255) / 256), 256, 0, ctx->stream>>>(a, scale, has_scale, round_each, done, n);
+    CTS_LAUNCH_CHECK(ctx);
+  }
+  return CTS_OK;
+}
+
+template <typename T>
+int dispatch_chain(cts_ctx* ctx, size_t n, int nt, void* out, const void* base, const double* coef,
+                   const void* const* terms, double scale, int has_scale) {
+  switch (nt) {
+#define CASE(N) \
+  case N:       \
+    return launch_chain<T, N>(ctx, n, out, base, coef, terms, scale, has_scale);
+    CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
+#undef CASE
+    default:
+      return cts_fail(ctx, CTS_EINVAL, "cts_axpy_chain: more than 12 operands");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // generic small element-wise kernels: out = f(a, b, c)
 // ---------------------------------------------------------------------------------------------
 template <typename T, int NIN, typename F>
@@ -409,6 +515,15 @@ int cts_ssprk_stage(cts_ctx* ctx, cts_dtype ft, size_t n, void* U_exp_out, void*
                                         one_minus_beta, coef, terms, final_update);
   return dispatch_ssprk<float, double>(ctx, n, n_imp, U_exp_out, U_out, temp_out, U_exp, T_exp, u, dt, dt_native, beta,
                                        one_minus_beta, coef, terms, final_update);
+}
+
+int cts_axpy_chain(cts_ctx* ctx, cts_dtype ft, size_t n, void* out, const void* base, int nterms, const double* coef,
+                   const void* const* terms, double scale, int has_scale) {
+  CTS_CHECK_CTX(ctx);
+  if (n == 0) return CTS_OK;
+  if (!out || nterms < 0 || (nterms > 0 && (!coef || !terms))) return cts_fail(ctx, CTS_EINVAL, "cts_axpy_chain: bad arguments");
+  if (ft == CTS_F64) return dispatch_chain<double>(ctx, n, nterms, out, base, coef, terms, scale, has_scale);
+  return dispatch_chain<float>(ctx, n, nterms, out, base, coef, terms, scale, has_scale);
 }
 
 int cts_newton_residual(cts_ctx* ctx, cts_dtype ft, size_t n, void* r, const void* U0, double dtgamma, const void* Up) {

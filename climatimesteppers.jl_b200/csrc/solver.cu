@@ -1193,3 +1193,219 @@ int cts_lsrk_cache_stats(cts_lsrk_cache* c, cts_solver_stats* out) {
 }
 
 }  // extern "C"
+
+// =============================================================================================
+// RosenbrockAlgorithm (src/solvers/rosenbrock.jl:85-239)
+// =============================================================================================
+struct cts_rosenbrock_cache {
+  cts_ctx* ctx = nullptr;
+  cts_dtype ft = CTS_F64;
+  size_t n = 0;
+  cts_rosenbrock_tableau tab{};
+  cts_ode_function f{};
+  cts_tendency_fn tgrad = nullptr;
+  void* U = nullptr;
+  void* fU = nullptr;
+  void* fU_imp = nullptr;
+  void* fU_exp = nullptr;
+  void* fU_lim = nullptr;
+  void* dYdt = nullptr;
+  void* k[CTS_MAX_STAGES] = {};
+  cts_solver_stats stats{};
+};
+
+namespace {
+
+int ros_state(cts_rosenbrock_cache* c, cts_state_fn fn, void* u, double t, int cat = CTS_PROF_OTHER_HOOKS) {
+  if (fn) {
+    cts_prof_scope ps(c->ctx, cat);
+    HOOK(c->ctx, fn(c->f.ud, u, t));
+  }
+  return CTS_OK;
+}
+
+void ros_free(cts_rosenbrock_cache* c) {
+  void* bufs[] = {c->U, c->fU, c->fU_imp, c->fU_exp, c->fU_lim, c->dYdt};
+  for (void* b : bufs)
+    if (b) cts_free(c->ctx, b);
+  for (int i = 0; i < CTS_MAX_STAGES; ++i)
+    if (c->k[i]) cts_free(c->ctx, c->k[i]);
+}
+
+}  // namespace
+
+extern "C" {
+
+int cts_rosenbrock_cache_create(cts_ctx* ctx, cts_dtype ft, size_t n, const cts_rosenbrock_tableau* tab,
+                                const cts_ode_function* f, cts_tendency_fn tgrad, cts_rosenbrock_cache** out) {
+  CTS_CHECK_CTX(ctx);
+  if (!tab || !f || !out || tab->s < 1 || tab->s > CTS_MAX_STAGES) return cts_fail(ctx, CTS_EINVAL, "cts_rosenbrock_cache_create: bad arguments");
+  if (f->T_imp && (!f->Wfact || !f->ldiv || !f->W)) return cts_fail(ctx, CTS_EINVAL, "Rosenbrock: T_imp! needs Wfact, ldiv! and a jac_prototype");
+  auto* c = new cts_rosenbrock_cache();
+  c->ctx = ctx;
+  c->ft = ft;
+  c->n = n;
+  c->tab = *tab;
+  c->f = *f;
+  c->tgrad = f->T_imp ? tgrad : nullptr;
+  const size_t bytes = n * cts_sizeof(ft);
+  void** bufs[] = {&c->U, &c->fU, &c->fU_imp, &c->fU_exp, &c->fU_lim, &c->dYdt};  // rosenbrock.jl:100-108
+  int r = CTS_OK;
+  for (void** b : bufs)
+    if (r == CTS_OK) r = cts_alloc(ctx, bytes, b);
+  for (int i = 0; i < tab->s && r == CTS_OK; ++i) r = cts_alloc(ctx, bytes, &c->k[i]);
+  if (r != CTS_OK) {
+    ros_free(c);
+    delete c;
+    return r;
+  }
+  *out = c;
+  return CTS_OK;
+}
+
+int cts_rosenbrock_cache_destroy(cts_rosenbrock_cache* c) {
+  if (!c) return CTS_EINVAL;
+  ros_free(c);
+  delete c;
+  return CTS_OK;
+}
+
+int cts_rosenbrock_cache_buffer(cts_rosenbrock_cache* c, const char* name, void** dptr) {
+  if (!c || !name || !dptr) return CTS_EINVAL;
+  std::string s(name);
+  *dptr = nullptr;
+  if (s == "U") *dptr = c->U;
+  else if (s == "fU") *dptr = c->fU;
+  else if (s == "fU_imp") *dptr = c->fU_imp;
+  else if (s == "fU_exp") *dptr = c->fU_exp;
+  else if (s == "fU_lim") *dptr = c->fU_lim;
+  else if (s == "dYdt") *dptr = c->dYdt;
+  else if (s.size() > 1 && s[0] == 'k') {
+    int i = atoi(s.c_str() + 1);
+    if (i >= 1 && i <= c->tab.s) *dptr = c->k[i - 1];
+  }
+  return *dptr ? CTS_OK : cts_fail(c->ctx, CTS_EINVAL, "unknown buffer name");
+}
+
+int cts_rosenbrock_cache_stats(cts_rosenbrock_cache* c, cts_solver_stats* out) {
+  if (!c || !out) return CTS_EINVAL;
+  *out = c->stats;
+  return CTS_OK;
+}
+
+// step_u!(int, cache::RosenbrockCache)  rosenbrock.jl:136-239.  The reference's chains of `.+=` broadcasts become one
+// chained pass each (cts_axpy_chain: same operations, same order, same roundings); terms whose coefficient is exactly
+// zero are not read (the reference multiplies them by zero).
+int cts_rosenbrock_step(cts_rosenbrock_cache* c, void* u, double t, double dt) {
+  if (!c || !u) return CTS_EINVAL;
+  cts_ctx* ctx = c->ctx;
+  const cts_rosenbrock_tableau& tab = c->tab;
+  const cts_ode_function& f = c->f;
+  const int s = tab.s;
+  const double dtg = dt * tab.Gamma[0];  // "only valid when Γ[i, i] is constant" :151-153
+  if (f.T_imp) {
+    cts_prof_scope ps(ctx, CTS_PROF_WFACT);
+    HOOK(ctx, f.Wfact(f.ud, f.W, u, dtg, t));
+    c->stats.wfact_evals++;
+  }
+  if (c->tgrad) {
+    cts_prof_scope ps(ctx, CTS_PROF_OTHER_HOOKS);
+    HOOK(ctx, c->tgrad(f.ud, c->dYdt, u, t));
+  }
+  for (int i = 0; i < s; ++i) {
+    double ai = 0.0, gi = 0.0;
+    for (int j = 0; j < i; ++j) ai += tab.alpha[i * s + j];
+    for (int j = 0; j <= i; ++j) gi += tab.Gamma[i * s + j];
+    const double ti = t + ai * dt;
+    double coef[2 * CTS_MAX_STAGES + 4];
+    const void* terms[2 * CTS_MAX_STAGES + 4];
+    // `U .= u; U .+= A[i, j] .* k[j]`  :178-181  (stage 1: U is only read, so it aliases u)
+    void* U = c->U;
+    int nt = 0;
+    for (int j = 0; j < i; ++j)
+      if (tab.A[i * s + j] != 0) {
+        coef[nt] = tab.A[i * s + j];
+        terms[nt++] = c->k[j];
+      }
+    if (i == 0) {
+      U = u;
+    } else {
+      cts_prof_scope ps(ctx, CTS_PROF_STAGE_ASSEMBLY);
+      CTS_TRY(cts_axpy_chain(ctx, c->ft, c->n, U, u, nt, coef, terms, 1.0, 0));
+    }
+    if (i != 0) {
+      if (f.dss) {
+        CTS_TRY(ros_state(c, f.dss, U, ti, CTS_PROF_DSS));
+        c->stats.dss_calls++;
+      }
+      if (needs_update(f.update_constrain_state, CTS_SIG_END_OF_STAGE)) CTS_TRY(ros_state(c, f.constrain_state, U, ti));
+      if (needs_update(f.update_cache, CTS_SIG_END_OF_STAGE)) CTS_TRY(ros_state(c, f.cache, U, ti));
+    }
+    nt = 0;
+    if (f.T_imp) {
+      cts_prof_scope ps(ctx, CTS_PROF_T_IMP);
+      HOOK(ctx, f.T_imp(f.ud, c->fU_imp, U, ti));
+      coef[nt] = 1.0;
+      terms[nt++] = c->fU_imp;
+    }
+    if (f.T_exp_T_lim) {
+      cts_prof_scope ps(ctx, CTS_PROF_T_EXP);
+      HOOK(ctx, f.T_exp_T_lim(f.ud, c->fU_exp, c->fU_lim, U, ti));
+      coef[nt] = 1.0;
+      terms[nt++] = c->fU_exp;
+      if (f.has_lim) {
+        coef[nt] = 1.0;
+        terms[nt++] = c->fU_lim;
+      }
+    }
+    if (c->tgrad) {
+      coef[nt] = gi * dt;  // `γi .* float(dt) .* ∂Y∂t`
+      terms[nt++] = c->dYdt;
+    }
+    for (int j = 0; j < i; ++j)
+      if (tab.C[i * s + j] != 0) {
+        coef[nt] = tab.C[i * s + j] / dt;
+        terms[nt++] = c->k[j];
+      }
+    void* rhs = f.T_imp ? c->fU : c->k[i];
+    {
+      // `fill!(fU, 0); fU .+= ...; fU .*= -dtγ`  :164,198-214 ; without T_imp! `k[i] .= .-fU` folds into the scale
+      cts_prof_scope ps(ctx, CTS_PROF_NEWTON_EW);
+      if (f.T_imp) {
+        CTS_TRY(cts_axpy_chain(ctx, c->ft, c->n, rhs, nullptr, nt, coef, terms, -dtg, 1));
+      } else {
+        CTS_TRY(cts_axpy_chain(ctx, c->ft, c->n, c->fU, nullptr, nt, coef, terms, -dtg, 1));
+        double m1[1] = {-1.0};
+        const void* t1[1] = {c->fU};
+        CTS_TRY(cts_axpy_chain(ctx, c->ft, c->n, c->k[i], nullptr, 1, m1, t1, 1.0, 0));
+      }
+    }
+    if (f.T_imp) {
+      cts_prof_scope ps(ctx, CTS_PROF_LDIV);
+      HOOK(ctx, f.ldiv(f.ud, c->k[i], f.W, c->fU));
+      c->stats.ldiv_calls++;
+    }
+  }
+  {
+    // `u .+= m[i] .* k[i]`  :231-233
+    double coef[CTS_MAX_STAGES];
+    const void* terms[CTS_MAX_STAGES];
+    int nt = 0;
+    for (int i = 0; i < s; ++i)
+      if (tab.m[i] != 0) {
+        coef[nt] = tab.m[i];
+        terms[nt++] = c->k[i];
+      }
+    cts_prof_scope ps(ctx, CTS_PROF_FINAL_UPDATE);
+    CTS_TRY(cts_axpy_chain(ctx, c->ft, c->n, u, u, nt, coef, terms, 1.0, 0));
+  }
+  if (f.dss) {
+    CTS_TRY(ros_state(c, f.dss, u, t + dt, CTS_PROF_DSS));
+    c->stats.dss_calls++;
+  }
+  if (needs_update(f.update_constrain_state, CTS_SIG_END_OF_STEP)) CTS_TRY(ros_state(c, f.constrain_state, u, t + dt));
+  if (needs_update(f.update_cache, CTS_SIG_END_OF_STEP)) CTS_TRY(ros_state(c, f.cache, u, t + dt));
+  return CTS_OK;
+}
+
+}  // extern "C"

@@ -14,7 +14,7 @@ from typing import Any, Dict, List, Optional
 import numpy as np
 
 from . import _lib as L
-from .algorithms import SSP, IMEXAlgorithm, LowStorageRungeKutta2N
+from .algorithms import SSP, IMEXAlgorithm, LowStorageRungeKutta2N, RosenbrockAlgorithm
 from .device import B200Vector, Context
 from .functions import ClimaODEFunction, IncrementingODEFunction, Returns_nothing
 from .operators import ColumnTridiag, NativeHook
@@ -226,6 +226,80 @@ class IMEXCache:
             pass
 
 
+class RosenbrockCache:
+    """RosenbrockCache (rosenbrock.jl:72-124) living in the library: U, fU, fU_imp, fU_exp, fU_lim, ∂Y∂t, k[1..N]."""
+
+    def __init__(self, prob, alg: RosenbrockAlgorithm):
+        u0: B200Vector = prob.u0
+        f: ClimaODEFunction = prob.f
+        self.ctx, self.alg, self.n, self.dtype = u0.ctx, alg, len(u0), u0.dtype
+        self.views = _Views(self.ctx, self.n, self.dtype)
+        self.views.add(u0)
+        T_imp = f.T_imp
+        self.jac = None
+        if T_imp is not None:
+            if getattr(T_imp, "Wfact", None) is None or getattr(T_imp, "jac_prototype", None) is None:
+                raise ValueError("RosenbrockAlgorithm needs T_imp!.Wfact and T_imp!.jac_prototype")
+            # `W = prob.f.T_imp!.jac_prototype` (:117): the prototype itself; the library's lazy column prototype is
+            # materialised first
+            self.jac = T_imp.jac_prototype
+            if isinstance(self.jac, ColumnTridiag) and self.jac.handle is None:
+                self.jac = self.jac.zero()
+        self.hooks = _HookTable(f, prob.p, self.views, self.jac)
+        keep = self.hooks.keep
+        tgrad = getattr(T_imp, "tgrad", None) if T_imp is not None else None
+        if tgrad is not None:
+            hooks = self.hooks
+
+            @_guard
+            def tg(hooks_self, ud, du, u, t):
+                tgrad(hooks.views.get(du), hooks.views.get(u), hooks.p, t)
+
+            cb = L.TENDENCY_FN(lambda *a: tg(hooks, *a))
+            keep.append(cb)
+        else:
+            cb = C.cast(None, L.TENDENCY_FN)
+        tab_c = alg.tableau.to_c()
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.cts_rosenbrock_cache_create(self.ctx.handle, u0.ft, self.n, C.byref(tab_c),
+                                                                C.byref(self.hooks.c), cb, C.byref(h)), "init_cache")
+        self.handle = h
+        self._keep = (tab_c, cb)
+
+    def buffer(self, name: str) -> Optional[B200Vector]:
+        p = C.c_void_p()
+        self.ctx.check(self.ctx.lib.cts_rosenbrock_cache_buffer(self.handle, name.encode(), C.byref(p)), "cache buffer")
+        return self.views.get(p.value)
+
+    @property
+    def k(self):
+        return [self.buffer(f"k{i + 1}") for i in range(self.alg.tableau.s)]
+
+    def stats(self) -> dict:
+        s = L.SolverStats()
+        self.ctx.check(self.ctx.lib.cts_rosenbrock_cache_stats(self.handle, C.byref(s)))
+        return s.as_dict()
+
+    def set_fusion(self, enabled: bool):
+        pass
+
+    def step_u(self, integrator):
+        u: B200Vector = integrator.u
+        self.views.add(u)
+        r = self.ctx.lib.cts_rosenbrock_step(self.handle, u.ptr, float(integrator.t), float(integrator.dt))
+        exc, self.hooks.pending_exception = self.hooks.pending_exception, None
+        if exc is not None:
+            raise exc
+        self.ctx.check(r, "step_u!")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.ctx.lib.cts_rosenbrock_cache_destroy(self.handle)
+        except Exception:
+            pass
+
+
 class LSRKCache:
     """LowStorageRungeKutta2NIncCache (lsrk.jl:44-52)."""
 
@@ -300,6 +374,8 @@ def init_cache(prob, alg, **kwargs):
         return IMEXCache(prob, alg)
     if isinstance(alg, LowStorageRungeKutta2N):
         return LSRKCache(prob, alg)
+    if isinstance(alg, RosenbrockAlgorithm):
+        return RosenbrockCache(prob, alg)
     raise TypeError(f"no B200 step_u! for {type(alg).__name__} (out of the hot-path scope, SURVEY §8)")
 
 

@@ -418,6 +418,57 @@ class RK4(ERKAlgorithmName):
 EXPLICIT_NAMES = ["SSP22Heuns", "SSP33ShuOsher", "RK4"]
 
 
+# ---- Rosenbrock (rosenbrock.jl:25-46, 241-267) ---------------------------------------------------
+class RosenbrockTableau:
+    """``RosenbrockTableau(α, Γ, b)``: stores A = α Γ⁻¹, C = diag(Γ⁻¹) − Γ⁻¹ and m = b Γ⁻¹ next to α and Γ."""
+
+    def __init__(self, alpha, Gamma, b):
+        alpha, Gamma, b = (np.array(x, dtype=np.float64) for x in (alpha, Gamma, b))
+        n = len(b)
+        assert alpha.shape == (n, n) and Gamma.shape == (n, n)
+        inv = np.linalg.inv(Gamma)
+        if np.allclose(np.diag(Gamma), 1.0) and np.allclose(np.triu(Gamma, 1), 0.0) and n <= 3:
+            # unit lower-triangular Γ with dyadic entries: forward substitution is exact
+            inv = np.eye(n)
+            for i in range(n):
+                for j in range(i):
+                    inv[i, j] = -sum(Gamma[i, k] * inv[k, j] for k in range(j, i))
+        self.alpha, self.Gamma, self.s = alpha, Gamma, n
+        self.A = np.array([[sum(alpha[i, k] * inv[k, j] for k in range(n)) for j in range(n)] for i in range(n)])
+        self.C = np.diag(np.diag(inv)) - inv
+        self.m = np.array([sum(b[k] * inv[k, j] for k in range(n)) for j in range(n)])
+
+    def to_c(self):
+        from . import _lib as L
+        t = L.RosenbrockTableau()
+        t.s = self.s
+        for name, M in (("A", self.A), ("alpha", self.alpha), ("C", self.C), ("Gamma", self.Gamma)):
+            arr = getattr(t, name)
+            for i in range(self.s):
+                for j in range(self.s):
+                    arr[i * self.s + j] = float(M[i, j])
+        for i in range(self.s):
+            t.m[i] = float(self.m[i])
+        return t
+
+
+class RosenbrockAlgorithmName(AbstractAlgorithmName):
+    pass
+
+
+class SSPKnoth(RosenbrockAlgorithmName):
+    """3-stage, 2nd-order Rosenbrock method (rosenbrock.jl:241-267)."""
+
+    def tableau(self) -> RosenbrockTableau:
+        return RosenbrockTableau([[0, 0, 0], [1, 0, 0], [1 / 4, 1 / 4, 0]], [[1, 0, 0], [0, 1, 0], [-3 / 4, -3 / 4, 1]],
+                                 [1 / 6, 1 / 6, 2 / 3])
+
+
+def tableau(name):
+    """``CTS.tableau(name)``."""
+    return name.tableau()
+
+
 # ---- low-storage 2N coefficient sets (lsrk.jl:117-217) ----------------------------------------
 def _rt(dtype):
     t = np.dtype(dtype).type

@@ -115,6 +115,13 @@ int cts_axpy_n(cts_ctx* ctx, cts_dtype ft, size_t n, void* out, void* out2, doub
 int cts_ssprk_stage(cts_ctx* ctx, cts_dtype ft, size_t n, void* U_exp_out, void* U_out, void* temp_out, const void* U_exp,
                     const void* T_exp, const void* u, double dt, int dt_native, double beta, double one_minus_beta,
                     int n_imp, const double* coef, const void* const* terms, int compute_native, int final_update);
+
+/* out = ((((base + c1*x1) + c2*x2) + ...) + cn*xn) [* scale]: the chains of `y .+= c .* x` broadcasts (and the trailing
+ * `y .*= s`) of the Rosenbrock step (rosenbrock.jl:178-214,231-233) in one pass.  Float64 arithmetic with Float64
+ * coefficients; a Float32 state is rounded after every term, as each of the reference's passes stores it.
+ * base == NULL starts from zero (`fill!(y, 0)`); out may alias base. */
+int cts_axpy_chain(cts_ctx* ctx, cts_dtype ft, size_t n, void* out, const void* base, int nterms, const double* coef,
+                   const void* const* terms, double scale, int has_scale);
 /* K3  `@. residual = U0 + dtγ * residual - U'` (imex_ark.jl:297); r holds T_imp(U') on entry */
 int cts_newton_residual(cts_ctx* ctx, cts_dtype ft, size_t n, void* r, const void* U0, double dtgamma, const void* Up);
 /* K5  `x .-= Δx` (newtons_method.jl:651) */
@@ -273,6 +280,30 @@ int cts_lsrk_cache_destroy(cts_lsrk_cache* c);
 int cts_lsrk_step(cts_lsrk_cache* c, void* u, double t, double dt, int dt_is_f32);
 int cts_lsrk_cache_buffer(cts_lsrk_cache* c, const char* name, void** dptr); /* "du" */
 int cts_lsrk_cache_set_fusion(cts_lsrk_cache* c, int enabled);
+
+/* ---- RosenbrockAlgorithm (src/solvers/rosenbrock.jl) -------------------------------------------
+ * Transformed tableau as runtime data (rosenbrock.jl:25-46): row-major s x s matrices A = αΓ⁻¹, α, C = diag(Γ⁻¹) − Γ⁻¹, Γ
+ * and the weights m = bΓ⁻¹ (the host computes them as RosenbrockTableau's constructor does). */
+typedef struct {
+  int s;
+  double A[CTS_MAX_STAGES * CTS_MAX_STAGES];
+  double alpha[CTS_MAX_STAGES * CTS_MAX_STAGES];
+  double C[CTS_MAX_STAGES * CTS_MAX_STAGES];
+  double Gamma[CTS_MAX_STAGES * CTS_MAX_STAGES];
+  double m[CTS_MAX_STAGES];
+} cts_rosenbrock_tableau;
+typedef struct cts_rosenbrock_cache cts_rosenbrock_cache;
+/* `init_cache(prob, alg::RosenbrockAlgorithm)` (rosenbrock.jl:100-124): U, fU, fU_imp, fU_exp, fU_lim, ∂Y∂t and k[1..s],
+ * zero-filled; `f->W` is the user's jac_prototype itself (the reference does not copy it here).  `tgrad` is
+ * `T_imp!.tgrad` (may be NULL).  `step_u!` (rosenbrock.jl:136-239): Wfact once per step with dtγ = dt·Γ[1,1], one
+ * `ldiv!` per stage, `dss!` on every stage value but the first and on the final state. */
+int cts_rosenbrock_cache_create(cts_ctx* ctx, cts_dtype ft, size_t n, const cts_rosenbrock_tableau* tab,
+                                const cts_ode_function* f, cts_tendency_fn tgrad, cts_rosenbrock_cache** out);
+int cts_rosenbrock_cache_destroy(cts_rosenbrock_cache* c);
+int cts_rosenbrock_step(cts_rosenbrock_cache* c, void* u, double t, double dt);
+/* "U","fU","fU_imp","fU_exp","fU_lim","dYdt","k<i>" (1-based i) */
+int cts_rosenbrock_cache_buffer(cts_rosenbrock_cache* c, const char* name, void** dptr);
+int cts_rosenbrock_cache_stats(cts_rosenbrock_cache* c, cts_solver_stats* out);
 int cts_lsrk_cache_stats(cts_lsrk_cache* c, cts_solver_stats* out);
 
 /* Newton's method on its own (`solve_newton!`, newtons_method.jl:609-665) for unit tests of the solver:

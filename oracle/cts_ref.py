@@ -941,6 +941,108 @@ def lsrk_step(u, du, p, t, dt, f_incr, tab):
 
 
 # --------------------------------------------------------------------------------------
+# Rosenbrock  (src/solvers/rosenbrock.jl)
+# --------------------------------------------------------------------------------------
+class RosenbrockTableau:
+    """rosenbrock.jl:25-46: A = α Γ⁻¹, C = diag(Γ⁻¹) − Γ⁻¹, m = b Γ⁻¹ (Float64).  For SSPKnoth Γ⁻¹ is exact in binary
+    floating point, so the only rounding is in m = b Γ⁻¹, evaluated here as the row-times-matrix product in increasing
+    column order (StaticArrays' `b / Γ` cannot be run in this container: last-bit unpinned for m)."""
+
+    def __init__(self, alpha, Gamma, b):
+        alpha, Gamma, b = (np.array(x, dtype=np.float64) for x in (alpha, Gamma, b))
+        n = len(b)
+        inv = np.linalg.inv(Gamma)
+        # a unit-lower-triangular Γ with dyadic entries inverts exactly; make that explicit for the 3-stage tableau
+        if np.allclose(np.diag(Gamma), 1.0) and np.allclose(np.triu(Gamma, 1), 0.0) and n <= 3:
+            inv = np.eye(n)
+            for i in range(n):
+                for j in range(i):
+                    inv[i, j] = -sum(Gamma[i, k] * inv[k, j] for k in range(j, i))
+        self.alpha, self.Gamma = alpha, Gamma
+        self.A = np.array([[sum(alpha[i, k] * inv[k, j] for k in range(n)) for j in range(n)] for i in range(n)])
+        self.C = np.diag(np.diag(inv)) - inv
+        self.m = np.array([sum(b[k] * inv[k, j] for k in range(n)) for j in range(n)])
+        self.s = n
+
+
+def ssp_knoth() -> RosenbrockTableau:
+    """tableau(::SSPKnoth), rosenbrock.jl:252-267."""
+    return RosenbrockTableau([[0, 0, 0], [1, 0, 0], [1 / 4, 1 / 4, 0]], [[1, 0, 0], [0, 1, 0], [-3 / 4, -3 / 4, 1]],
+                             [1 / 6, 1 / 6, 2 / 3])
+
+
+@dataclass
+class RosenbrockAlgorithm:
+    tableau: RosenbrockTableau
+
+
+def init_cache_rosenbrock(u0, f: ClimaODEFunction, alg: RosenbrockAlgorithm):
+    """rosenbrock.jl:100-124: U, fU, fU_imp, fU_exp, fU_lim, ∂Y∂t, k[1..N]; W is the jac_prototype ITSELF (not a copy)."""
+    z = lambda: np.zeros_like(u0)
+    return dict(U=z(), fU=z(), fU_imp=z(), fU_exp=z(), fU_lim=z(), dYdt=z(), k=[z() for _ in range(alg.tableau.s)],
+                W=f.T_imp.jac_prototype if f.T_imp is not None else None)
+
+
+def rosenbrock_step(u, p, t, dt, f: ClimaODEFunction, alg: RosenbrockAlgorithm, cache):
+    """step_u!(int, cache::RosenbrockCache), rosenbrock.jl:136-239 — every `.=`/`.+=` below is its own pass, evaluated in
+    Float64 (the tableau is Float64) and rounded to the state type on store."""
+    tab = alg.tableau
+    U, fU, fU_imp, fU_exp, fU_lim, dYdt, k, W = (cache[x] for x in ("U", "fU", "fU_imp", "fU_exp", "fU_lim", "dYdt", "k", "W"))
+    T_imp, T_exp_T_lim = f.T_imp, f.T_exp_T_lim
+    tgrad = None if T_imp is None else T_imp.tgrad
+    st = u.dtype
+    w = lambda x: x.astype(np.float64)
+    fdt = float(dt)
+    dtg = fdt * tab.Gamma[0, 0]
+    if T_imp is not None:
+        T_imp.Wfact(W, u, p, dtg, t)
+    if tgrad is not None:
+        tgrad(dYdt, u, p, t)
+    for i in range(tab.s):
+        fU[...] = 0
+        ai = 0.0
+        gi = 0.0
+        for j in range(i):
+            ai += tab.alpha[i, j]
+        for j in range(i + 1):
+            gi += tab.Gamma[i, j]
+        U[...] = u
+        for j in range(i):
+            U[...] = (w(U) + tab.A[i, j] * w(k[j])).astype(st)
+        ti = t + ai * dt
+        if i != 0:
+            f.dss(U, p, ti)
+            if f.update_constrain_state.needs_update("EndOfStage"):
+                f.constrain_state(U, p, ti)
+            if f.update_cache.needs_update("EndOfStage"):
+                f.cache(U, p, ti)
+        if T_imp is not None:
+            T_imp(fU_imp, U, p, ti)
+            fU[...] = fU + fU_imp
+        if T_exp_T_lim is not None:
+            T_exp_T_lim(fU_exp, fU_lim, U, p, ti)
+            fU[...] = fU + fU_exp
+            if f.has_T_lim:
+                fU[...] = fU + fU_lim
+        if tgrad is not None:
+            fU[...] = (w(fU) + (gi * fdt) * w(dYdt)).astype(st)
+        for j in range(i):
+            fU[...] = (w(fU) + (tab.C[i, j] / fdt) * w(k[j])).astype(st)
+        fU[...] = (w(fU) * (-float(dtg))).astype(st)
+        if T_imp is not None:
+            W.ldiv(k[i], fU)
+        else:
+            k[i][...] = -fU
+    for i in range(tab.s):
+        u[...] = (w(u) + tab.m[i] * w(k[i])).astype(st)
+    f.dss(u, p, t + dt)
+    if f.update_constrain_state.needs_update("EndOfStep"):
+        f.constrain_state(u, p, t + dt)
+    if f.update_cache.needs_update("EndOfStep"):
+        f.cache(u, p, t + dt)
+
+
+# --------------------------------------------------------------------------------------
 # integrator driver  (src/integrators.jl:187-257, 345-351, 410-439)
 # --------------------------------------------------------------------------------------
 def solve(u0, p, tspan, dt, step_fn, *, save_everystep=False):
@@ -972,7 +1074,10 @@ def solve(u0, p, tspan, dt, step_fn, *, save_everystep=False):
 
 
 def make_stepper(f, alg, u0):
-    """init_cache dispatch (imex_ark.jl:35 for Unconstrained, imex_ssprk.jl:33 for SSP)."""
+    """init_cache dispatch (imex_ark.jl:35 for Unconstrained, imex_ssprk.jl:33 for SSP, rosenbrock.jl:100)."""
+    if isinstance(alg, RosenbrockAlgorithm):
+        cache = init_cache_rosenbrock(u0, f, alg)
+        return cache, (lambda u, p, t, dt: rosenbrock_step(u, p, t, dt, f, alg, cache))
     if alg.constraint == "SSP":
         cache = init_cache_ssprk(u0, f, alg)
         return cache, (lambda u, p, t, dt: imex_ssprk_step(u, p, t, dt, f, alg, cache))
