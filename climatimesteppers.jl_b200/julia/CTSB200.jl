@@ -209,6 +209,40 @@ CTS.step_u!(integrator, cache::B200LSRKCache) =
     (check(integrator.u.ctx.handle, ccall((:cts_lsrk_step, libcts), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Cint),
         cache.handle, integrator.u.ptr, Float64(integrator.t), Float64(integrator.dt), integrator.dt isa Float32)); integrator.u)
 
+# Rosenbrock (rosenbrock.jl:100-124, 136-239)
+struct RosenbrockTableauC
+    s::Cint; A::NTuple{64, Cdouble}; alpha::NTuple{64, Cdouble}; C::NTuple{64, Cdouble}; Gamma::NTuple{64, Cdouble}; m::NTuple{8, Cdouble}
+end
+function RosenbrockTableauC(tab::CTS.RosenbrockTableau{N}) where {N}
+    pad(M) = ntuple(k -> (i = (k - 1) ÷ N + 1; j = (k - 1) % N + 1; k <= N * N ? Cdouble(M[i, j]) : 0.0), 64)   # row-major s x s
+    RosenbrockTableauC(N, pad(tab.A), pad(tab.α), pad(tab.C), pad(tab.Γ), ntuple(k -> k <= N ? Cdouble(tab.m[k]) : 0.0, 8))
+end
+mutable struct B200RosenbrockCache
+    handle::Ptr{Cvoid}; env::HookEnv; keep::Any
+end
+function CTS.init_cache(prob::CTS.ODEProblem{<:Any, <:B200Vector{FT}}, alg::CTS.RosenbrockAlgorithm; kwargs...) where {FT}
+    u0, f = prob.u0, prob.f
+    jac = isnothing(f.T_imp!) ? nothing : f.T_imp!.jac_prototype                          # the prototype itself (:117)
+    env = HookEnv{typeof(f), typeof(prob.p), FT}(f, prob.p, u0.ctx, length(u0), jac, nothing)
+    tbl, keep = hook_table(env)
+    tg = (isnothing(f.T_imp!) || isnothing(f.T_imp!.tgrad)) ? C_NULL :
+         @cfunction($((ud, dT, u, t) -> (f.T_imp!.tgrad(view_of(u0.ctx, dT, length(u0), FT), view_of(u0.ctx, u, length(u0), FT), prob.p, t); Cint(0))),
+                    Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(u0.ctx.handle, ccall((:cts_rosenbrock_cache_create, libcts), Cint,
+        (Ptr{Cvoid}, Cint, Csize_t, Ref{RosenbrockTableauC}, Ref{OdeFunction}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+        u0.ctx.handle, ft(FT), length(u0), RosenbrockTableauC(alg.tableau), tbl, tg, h))
+    c = B200RosenbrockCache(h[], env, (keep, tg))
+    finalizer(x -> ccall((:cts_rosenbrock_cache_destroy, libcts), Cint, (Ptr{Cvoid},), x.handle), c)
+end
+function CTS.step_u!(integrator, cache::B200RosenbrockCache)
+    (; u, t, dt) = integrator
+    rc = ccall((:cts_rosenbrock_step, libcts), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble), cache.handle, u.ptr, Float64(t), Float64(dt))
+    isnothing(cache.env.err) || (e = cache.env.err; cache.env.err = nothing; throw(e))
+    check(u.ctx.handle, rc)
+    return u
+end
+
 # ------------------------------------------------------------------------------------------------ column tridiagonal W
 """Batched tridiagonal `jac_prototype` for column-stacked states: `zero` + `ldiv!` (cts_tridiag_solve_batched)."""
 struct Tridiag
