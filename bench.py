@@ -424,7 +424,11 @@ def run_c4(cts, ctx, stream, dtype):
     cts.step_(integ)
     s0 = integ.cache.stats()
     steps = 2
+    ctx.prof_read()
+    ctx.prof_enable(True)
     ms = timed(stream, lambda: cts.step_(integ), steps, warm=0)
+    prof = ctx.prof_read()
+    ctx.prof_enable(False)
     s1 = integ.cache.stats()
     kit = (s1["krylov_iters"] - s0["krylov_iters"]) / steps
     nit = (s1["newton_iters"] - s0["newton_iters"]) / steps
@@ -433,6 +437,8 @@ def run_c4(cts, ctx, stream, dtype):
     finite = bool(torch.isfinite(u.tensor).all())
     res = {"ms_per_step": ms, "dof_stage_per_s": n * 3 / (ms * 1e-3), "krylov_iters_per_step": kit, "newton_iters_per_step": nit,
            "rtol": rtol, "dt": 2e-3, "finite": finite, "jvp_step_adjustment": adj,
+           "kernels_ms_per_step": {k: round(v[0] / steps, 3) for k, v in prof.items() if v[1]},
+           "launches_per_step": sum(v[1] for v in prof.values()) / steps,
            "note": "Newton-Krylov work is data dependent; bytes/step = sum over executed kernels, see DESIGN.md"}
     del integ, op, u, K
     return res

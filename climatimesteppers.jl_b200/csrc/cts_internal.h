@@ -125,6 +125,10 @@ struct cts_fused_stage_args {
 };
 int cts_column_fused_stage(cts_op_column* op, const cts_fused_stage_args* a);
 bool cts_column_fusable(const cts_op_column* op);
+// Newton residual (dx == NULL) or forward-difference JVP of the stage equation for the column operator in one pass
+bool cts_column_residual_fusable(const cts_op_column* op);
+int cts_column_fused_residual(cts_op_column* op, void* out, const void* x, const void* dx, double eps, const void* U0,
+                              const void* f, double dtgamma);
 bool cts_op_column_is_linear(const cts_op_column* op);
 bool cts_op_column_matrix_free(const cts_op_column* op);
 cts_ctx* cts_op_column_ctx(const cts_op_column* op);

@@ -68,6 +68,11 @@ struct cts_newton_cache {
   std::vector<void*> V;
   double ew_prev_norm_f = 0.0, ew_prev_rtol = 0.0;
   cts_solver_stats stats{};
+  // Set by solve_implicit_equation! while the stage equation's T_imp! is the library's column operator and no hook
+  // runs before f!: the residual (and the JVP built on it) is then one fused kernel instead of T_imp! + K3 (+ K7, K8).
+  cts_op_column* fused_op = nullptr;
+  const void* fused_U0 = nullptr;
+  double fused_dtg = 0.0;
 };
 
 namespace {
@@ -290,6 +295,13 @@ int solve_krylov(cts_newton_cache* c, void* dx, const void* x, const ResidualFn&
     }
     double e = 0;  // jvp! :173-182
     CTS_TRY(jvp_step(c, v, x, &e));
+    if (c->fused_op) {  // K7 + T_imp! + K3 + K8 in one pass (x2 and f2 are never materialised)
+      cts_prof_scope ps(ctx, CTS_PROF_NEWTON_EW);
+      CTS_TRY(cts_column_fused_residual(c->fused_op, out, x, v, e, c->fused_U0, f, c->fused_dtg));
+      c->stats.f_evals++;
+      c->stats.jvp_evals++;
+      return CTS_OK;
+    }
     {
       cts_prof_scope ps(ctx, CTS_PROF_NEWTON_EW);
       CTS_TRY(cts_jvp_perturb(ctx, c->ft, c->n, c->x2, x, e, v));
@@ -561,7 +573,21 @@ int call_state(cts_imex_cache* c, cts_state_fn fn, void* u, double t) {
 // solve_implicit_equation! (imex_ark.jl:283-308)
 int solve_implicit_equation(cts_imex_cache* c, void* U, const void* U0, double t_imp, double dtg) {
   cts_ctx* ctx = c->ctx;
+  // library column operator as T_imp! and nothing to run before f! (cache_imp! is the reference's prepare_for_f!):
+  // residual and JVP go through the fused kernel
+  cts_op_column* rop = nullptr;
+  if (c->fusion && c->f.T_imp == cts_op_column_T_imp && !c->f.cache_imp && c->f.ud) {
+    auto* op = static_cast<cts_op_column*>(c->f.ud);
+    if (cts_op_column_ctx(op) == ctx && cts_op_column_dtype(op) == c->ft && cts_op_column_ndof(op) == c->n &&
+        cts_column_residual_fusable(op) && cts_aligned16(U) && cts_aligned16(U0) && cts_aligned16(c->nm->f) &&
+        cts_aligned16(c->nm->dx))
+      rop = op;
+  }
   ResidualFn f_ = [&](void* res, const void* Up) -> int {
+    if (rop && cts_aligned16(res) && cts_aligned16(Up)) {
+      cts_prof_scope ps(ctx, CTS_PROF_NEWTON_EW);
+      return cts_column_fused_residual(rop, res, Up, nullptr, 0.0, U0, nullptr, dtg);
+    }
     {
       cts_prof_scope ps(ctx, CTS_PROF_T_IMP);
       HOOK(ctx, c->f.T_imp(c->f.ud, res, Up, t_imp));
@@ -569,6 +595,13 @@ int solve_implicit_equation(cts_imex_cache* c, void* U, const void* U0, double t
     cts_prof_scope ps(ctx, CTS_PROF_NEWTON_EW);
     return cts_newton_residual(ctx, c->ft, c->n, res, U0, dtg, Up);  // K3
   };
+  struct FusedScope {  // the JVP of solve_krylov! sees the operator only for the duration of this solve
+    cts_newton_cache* nm;
+    ~FusedScope() { nm->fused_op = nullptr; }
+  } fused_scope{c->nm};
+  c->nm->fused_op = rop;
+  c->nm->fused_U0 = U0;
+  c->nm->fused_dtg = dtg;
   JacFn j_ = [&](void* W, const void* Up) -> int {
     cts_prof_scope ps(ctx, CTS_PROF_WFACT);
     HOOK(ctx, c->f.Wfact(c->f.ud, W, Up, dtg, t_imp));
