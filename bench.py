@@ -399,7 +399,32 @@ def run_extras(cts, ctx, stream, op, u):
     for dtype, name in ((np.float64, "f64"), (np.float32, "f32")):
         out[f"C4_ssp333_jfnk_{name}"] = run_c4(cts, ctx, stream, dtype)
         torch.cuda.empty_cache()
+    out["C3_ars343_column_f32"] = run_c3_f32(cts, ctx, stream)
+    torch.cuda.empty_cache()
     return out
+
+
+def run_c3_f32(cts, ctx, stream):
+    """The default workload (C3: ARS343, 2^21 columns x 64 levels, stored W, halo dss!) with a Float32 state: element-wise
+    arithmetic in Float64 with Float64 tableau coefficients, rounded on store; the solve is Float32."""
+    import numpy as np
+    K = cts.B200Vector.zeros((NY + 2) * NX, np.float32, ctx).fill_hash(2, 0, 0.25, 2.0)
+    u = cts.B200Vector.zeros((NY + 2) * NX * NLEV, np.float32, ctx).fill_hash(3)
+    z = (np.arange(NLEV) + 1) / (NLEV + 1)
+    S = cts.B200Vector.from_host((5.0 * np.exp(-((z - 0.3) ** 2) / 0.01)).astype(np.float32), ctx)
+    op = cts.ColumnOperator(NLEV, NX, NY, K, S_lev=S, nu=NU, halo=1, ctx=ctx)
+    alg = cts.IMEXAlgorithm(cts.ARS343(), cts.NewtonsMethod(max_iters=1, update_j=cts.UpdateEvery(cts.NewTimeStep)))
+    integ = cts.init(cts.ODEProblem(op.ode_function(), u, (0.0, 1.0e9), None), alg, dt=DT, save=False)
+    op.dss(u, None, 0.0)
+    ms = timed(stream, lambda: cts.step_(integ), 5, warm=3)
+    import torch
+    n = NX * NY * NLEV
+    model = step_bytes_per_dof(True) // 2
+    res = {"ms_per_step": ms, "dof_stage_per_s": n * STAGES / (ms * 1e-3), "bytes_per_dof_step": model,
+           "GBs": model * op.ndof / (ms * 1e-3) / 1e9, "frac": model * op.ndof / (ms * 1e-3) / 1e9 / peaks()[0],
+           "finite": bool(torch.isfinite(u.tensor).all())}
+    del integ, op, u, K
+    return res
 
 
 def run_c4(cts, ctx, stream, dtype):

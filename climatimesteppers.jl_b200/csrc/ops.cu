@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_MIN_BLOCKS) column_fu
 // barrier disappears.  Arithmetic is identical to the kernel above.  (Measured on B200: capping registers at 80 to fit
 // 6 CTAs per SM costs the solver more than the extra CTA gives: 6.1 ms vs 5.4 ms per step; 64/96-thread CTAs have too
 // few loads in flight: 6.7 ms.  So: 128 threads, <= 96 registers, 5 CTAs per SM.)
-constexpr int kKeep = (kTileCols * 32 + kFusedThreads - 1) / kFusedThreads;  // U0 vectors per thread at 32 vectors/column
+constexpr int kKeep = (kTileCols * 32 + kFusedThreads - 1) / kFusedThreads;  // U0 vectors per thread (f64: 16 cols x <= 32 vectors, f32: 32 x <= 16)
 
 #ifndef CTS_FUSED_REG_MIN_BLOCKS
 #define CTS_FUSED_REG_MIN_BLOCKS 5
@@ -660,9 +660,11 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
   using V = typename Vec<T>::type;
   constexpr int VN = Vec<T>::N;
   constexpr int NTS = NT > 0 ? NT : 1;
+  constexpr int kCols = TileShape<T>::kCols;       // 16 columns of Float64, 32 of Float32
+  constexpr int kSolvers = TileShape<T>::kThreads;  // solver threads: a lane pair per column
   extern __shared__ __align__(128) char smem[];
   const int pitch = a.pitch;
-  const int tile_bytes = kTileCols * pitch;
+  const int tile_bytes = kCols * pitch;
   char* sx = smem;                   // residual -> rp -> dx
   char* sfac = smem + tile_bytes;    // matrix-free: cp scratch; stored: dl tile (d and du follow)
   char* sdl = sfac;
@@ -672,8 +674,8 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
   T* sAcol = reinterpret_cast<T*>(smem + (MATRIX_FREE ? 2 : 4) * tile_bytes + 16);
 
   const int nlev = a.nlev;
-  const size_t col0 = (size_t)blockIdx.x * kTileCols;
-  const int nvalid = (int)((a.ncols - col0) < (size_t)kTileCols ? (a.ncols - col0) : (size_t)kTileCols);
+  const size_t col0 = (size_t)blockIdx.x * kCols;
+  const int nvalid = (int)((a.ncols - col0) < (size_t)kCols ? (a.ncols - col0) : (size_t)kCols);
   const int col_bytes = nlev * (int)sizeof(T);
   const size_t goff = col0 * (size_t)nlev;
   if (MATRIX_FREE && (int)threadIdx.x < nvalid) sAcol[threadIdx.x] = ((const T*)a.Kcol)[col0 + threadIdx.x];
@@ -760,7 +762,7 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
   __syncthreads();
 
   // ---- phase B (solver warps): two-sided product-form Thomas, a lane pair per column ---------------------
-  if (threadIdx.x < kTileThreads) {
+  if (threadIdx.x < kSolvers) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int col = warp * 16 + lane_column(lane);
     const bool is_up = lane_is_up(lane);
@@ -779,7 +781,7 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
   } else if (MATRIX_FREE && a.emit_w) {
     // the warps that only move data write W = dtγJ - I (same expressions as column_wfact_kernel) while the solver
     // warp works: the stores overlap the elimination instead of lengthening the epilogue
-    for (int q = (int)threadIdx.x - kTileThreads; q < total; q += kFusedThreads - kTileThreads) {
+    for (int q = (int)threadIdx.x - kSolvers; q < total; q += kFusedThreads - kSolvers) {
       const int c = q >> cshift, k = q & (cpc - 1);
       const size_t gi = (goff * sizeof(T) + (size_t)c * col_bytes + (size_t)k * 16) / 16;
       const double o = __dmul_rn(a.dtg, (double)sAcol[c]);
@@ -856,8 +858,10 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
   static const bool timeline = getenv("CTS_FUSED_TIMELINE") != nullptr;  // developer aid: per-phase clock64 averages
   static const bool no_reg = getenv("CTS_FUSED_NO_REG") != nullptr;      // developer aid: force the 5-tile kernel
   const int cpc = op->d.nlev * (int)sizeof(T) / 16;
-  if (!timeline && !no_reg && cpc >= 1 && cpc <= 32 && (cpc & (cpc - 1)) == 0) {
-    size_t smem_reg = (size_t)(mf ? 2 : 4) * kTileCols * a.pitch + 16 + kTileCols * sizeof(T);
+  constexpr int kCols = TileShape<T>::kCols;
+  if (!timeline && !no_reg && cpc >= 1 && cpc * kCols <= kKeep * kFusedThreads && (cpc & (cpc - 1)) == 0) {
+    tiles = (op->ncols + kCols - 1) / kCols;
+    size_t smem_reg = (size_t)(mf ? 2 : 4) * kCols * a.pitch + 16 + kCols * sizeof(T);
     a.dbg = nullptr;
     if (mf) {
       auto k = column_fused_stage_reg_kernel<T, C, NT, true>;
