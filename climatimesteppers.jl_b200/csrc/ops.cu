@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_MIN_BLOCKS) column_fu
 // barrier disappears.  Arithmetic is identical to the kernel above.  (Measured on B200: capping registers at 80 to fit
 // 6 CTAs per SM costs the solver more than the extra CTA gives: 6.1 ms vs 5.4 ms per step; 64/96-thread CTAs have too
 // few loads in flight: 6.7 ms.  So: 128 threads, <= 96 registers, 5 CTAs per SM.)
-constexpr int kKeep = (kTileCols * 32 + kFusedThreads - 1) / kFusedThreads;  // U0 vectors per thread (f64: 16 cols x <= 32 vectors, f32: 32 x <= 16)
+constexpr int kKeep = (CTS_FUSED_TILE_COLS * 32 + kFusedThreads - 1) / kFusedThreads;  // U0 vectors per thread (f64: 16 cols x <= 32 vectors, f32: 32 x <= 16)
 
 #ifndef CTS_FUSED_REG_MIN_BLOCKS
 #define CTS_FUSED_REG_MIN_BLOCKS 5
