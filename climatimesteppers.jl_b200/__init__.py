@@ -7,7 +7,8 @@ The directory is called ``climatimesteppers.jl_b200``; import it as ``cts_b200``
 """
 from . import _lib
 from ._lib import CTSError, LIB_PATH
-from .algorithms import (SSP, ConstantForcing, EisenstatWalkerForcing, ExplicitAlgorithm, ForwardDiffJVP,
+from .algorithms import (SSP, ConstantForcing, ConvergenceChecker, LineSearch, MaximumError, MaximumErrorReduction,
+                         MaximumRelativeError, MinimumRateOfConvergence, MultipleConditions, EisenstatWalkerForcing, ExplicitAlgorithm, ForwardDiffJVP,
                          ForwardDiffStepSize1, ForwardDiffStepSize2, ForwardDiffStepSize3, IMEXAlgorithm,
                          KrylovMethod, LowStorageRungeKutta2N, LSRK54CarpenterKennedy, LSRK144NiegemannDiehlBusch,
                          LSRKEulerMethod, NewtonsMethod, RosenbrockAlgorithm, TimeSteppingAlgorithm, Unconstrained)

@@ -62,6 +62,19 @@ class RosenbrockTableau(C.Structure):
                 ("Gamma", C.c_double * 64), ("m", C.c_double * 8)]
 
 
+COND_MAX_ERROR, COND_MAX_REL_ERROR, COND_MAX_ERROR_REDUCTION, COND_MIN_RATE, COND_ALL, COND_ANY = range(6)
+MAX_COND_NODES = 16
+
+
+class CondNode(C.Structure):
+    _fields_ = [("kind", C.c_int), ("nchildren", C.c_int), ("p0", C.c_double), ("p1", C.c_double)]
+
+
+class ConvergenceCheckerC(C.Structure):
+    _fields_ = [("n_norm", C.c_int), ("norm_cond", CondNode * MAX_COND_NODES), ("n_comp", C.c_int),
+                ("comp_cond", CondNode * MAX_COND_NODES), ("combiner_or", C.c_int)]
+
+
 class NewtonConfig(C.Structure):
     _fields_ = [("present", C.c_int), ("max_iters", C.c_int), ("update_j", UpdateHandler), ("use_krylov", C.c_int),
                 ("jacobian_free_jvp", C.c_int), ("jvp_step_kind", C.c_int), ("jvp_step_adjustment", C.c_double),
@@ -108,6 +121,12 @@ SIGNATURES = [
     ("cts_memcpy_d2h_sync", _I, [_P, _P, _P, _SZ]),
     ("cts_memcpy_d2d", _I, [_P, _P, _P, _SZ]),
     ("cts_axpy_n", _I, [_P, _I, _SZ, _P, _P, _D, _P, _I, _I, c_double_p, c_void_pp, _I]),
+    ("cts_newton_cache_set_convergence_checker", _I, [_P, _P]),
+    ("cts_newton_cache_set_line_search", _I, [_P, _I]),
+    ("cts_newton_cache_is_converged", _I, [_P, _P, _P, _I, _P]),
+    ("cts_imex_cache_newton", _I, [_P, _P]),
+    ("cts_component_check", _I, [_P, _I, _SZ, _P, _P, _I, _P, _P, _I, _P, _P]),
+    ("cts_component_update", _I, [_P, _I, _SZ, _P, _P, _I, _P, _P, _I]),
     ("cts_axpy_chain", _I, [_P, _I, _SZ, _P, _P, _I, c_double_p, c_void_pp, _D, _I]),
     ("cts_rosenbrock_cache_create", _I, [_P, _I, _SZ, _P, _P, TENDENCY_FN, _P]),
     ("cts_rosenbrock_cache_destroy", _I, [_P]),

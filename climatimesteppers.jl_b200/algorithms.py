@@ -73,6 +73,95 @@ class KrylovMethod:
     batch_gram_schmidt: bool = False    # B200 option: one fused sweep of dots per Arnoldi step (classical GS)
 
 
+# ---- ConvergenceChecker / LineSearch ---------------------------------------------------------------
+class ConvergenceCondition:
+    """convergence_condition.jl:31-33; ``nodes()`` flattens the condition tree into the postfix list the C ABI takes."""
+
+    def nodes(self):
+        raise NotImplementedError
+
+
+@dataclass
+class MaximumError(ConvergenceCondition):
+    max_err: float
+
+    def nodes(self):
+        return [(L.COND_MAX_ERROR, 0, float(self.max_err), 0.0)]
+
+
+@dataclass
+class MaximumRelativeError(ConvergenceCondition):
+    max_rel_err: float
+
+    def nodes(self):
+        return [(L.COND_MAX_REL_ERROR, 0, float(self.max_rel_err), 0.0)]
+
+
+@dataclass
+class MaximumErrorReduction(ConvergenceCondition):
+    max_reduction: float
+
+    def nodes(self):
+        return [(L.COND_MAX_ERROR_REDUCTION, 0, float(self.max_reduction), 0.0)]
+
+
+@dataclass
+class MinimumRateOfConvergence(ConvergenceCondition):
+    rate: float
+    order: float = 1
+
+    def nodes(self):
+        return [(L.COND_MIN_RATE, 0, float(self.rate), float(self.order))]
+
+
+class MultipleConditions(ConvergenceCondition):
+    """``MultipleConditions(condition_combiner = all, conditions...)`` (convergence_condition.jl:116-143)."""
+
+    def __init__(self, *args):
+        if args and args[0] in (all, any):
+            self.condition_combiner, self.conditions = args[0], tuple(args[1:])
+        else:
+            self.condition_combiner, self.conditions = all, tuple(args)
+        if not self.conditions or not all(isinstance(c, ConvergenceCondition) for c in self.conditions):
+            raise TypeError("MultipleConditions takes ConvergenceConditions")
+
+    def nodes(self):
+        out = []
+        for c in reversed(self.conditions):  # the evaluator pops children in reverse order; all/any are symmetric anyway
+            out += c.nodes()
+        out.append((L.COND_ALL if self.condition_combiner is all else L.COND_ANY, len(self.conditions), 0.0, 0.0))
+        return out
+
+
+@dataclass
+class ConvergenceChecker:
+    """``ConvergenceChecker(; norm_condition, component_condition, condition_combiner = &)`` with ``norm =
+    LinearAlgebra.norm`` (convergence_checker.jl:32-43)."""
+    norm_condition: Optional[ConvergenceCondition] = None
+    component_condition: Optional[ConvergenceCondition] = None
+    condition_combiner: str = "&"
+
+    def to_c(self) -> "L.ConvergenceCheckerC":
+        if self.norm_condition is None and self.component_condition is None:
+            raise ValueError("ConvergenceChecker must have at least one ConvergenceCondition")  # :47-49
+        c = L.ConvergenceCheckerC()
+        for cond, count, arr in ((self.norm_condition, "n_norm", c.norm_cond), (self.component_condition, "n_comp", c.comp_cond)):
+            nodes = [] if cond is None else cond.nodes()
+            if len(nodes) > L.MAX_COND_NODES:
+                raise ValueError("condition tree too large")
+            setattr(c, count, len(nodes))
+            for k, (kind, nch, p0, p1) in enumerate(nodes):
+                arr[k].kind, arr[k].nchildren, arr[k].p0, arr[k].p1 = kind, nch, p0, p1
+        assert self.condition_combiner in ("&", "|")
+        c.combiner_or = int(self.condition_combiner == "|")
+        return c
+
+
+@dataclass
+class LineSearch:
+    """``LineSearch()`` (line_search.jl:23-25): backtracking by halving, at most 5 times, on ``norm(f)``."""
+
+
 @dataclass
 class NewtonsMethod:
     """newtons_method.jl:568-581."""
@@ -83,9 +172,7 @@ class NewtonsMethod:
     line_search: Any = None
 
     def to_c(self, keep: list) -> L.NewtonConfig:
-        if self.convergence_checker is not None or self.line_search is not None:
-            raise NotImplementedError("convergence_checker / line_search are outside the B200 hot path (SURVEY §2 #12,#13)")
-        c = L.NewtonConfig()
+        c = L.NewtonConfig()  # (convergence_checker / line_search are attached to the Newton cache, see configure_cache)
         c.present = 1
         c.max_iters = int(self.max_iters)
         c.update_j = self.update_j.to_c(keep)
@@ -109,6 +196,15 @@ class NewtonsMethod:
                 c.ew_initial_rtol, c.ew_gamma, c.ew_alpha = float(ft.initial_rtol), float(ft.gamma), float(ft.alpha)
                 c.ew_min_rtol_threshold, c.ew_max_rtol = float(ft.min_rtol_threshold), float(ft.max_rtol)
         return c
+
+    def configure_cache(self, ctx, newton_handle):
+        """`allocate_cache(::NewtonsMethod, ...)` extras (newtons_method.jl:583-598): checker cache, line search."""
+        import ctypes as C
+        if self.convergence_checker is not None:
+            cc = self.convergence_checker.to_c()
+            ctx.check(ctx.lib.cts_newton_cache_set_convergence_checker(newton_handle, C.byref(cc)), "convergence_checker")
+        if self.line_search is not None:
+            ctx.check(ctx.lib.cts_newton_cache_set_line_search(newton_handle, 1), "line_search")
 
 
 # ---- IMEX / explicit ------------------------------------------------------------------------------

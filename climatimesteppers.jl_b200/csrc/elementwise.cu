@@ -6,6 +6,7 @@
 // grids sized from the problem (>= several waves of 148 SMs at the 2^27-DOF target size), no shared
 // memory.  Arithmetic uses __dmul_rn/__dadd_rn so nothing is contracted into FMAs: the results are
 // bit-identical to the reference's broadcast evaluation order.
+#include <algorithm>
 #include "cts_internal.h"
 #include "ew_device.cuh"
 
@@ -378,6 +379,87 @@ int dispatch_chain(cts_ctx* ctx, size_t n, int nt, void* out, const void* base, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Component-wise ConvergenceCondition trees (convergence_checker.jl:62-73,97-105): the tree travels by value in postfix
+// order; node k's per-element cache is caches[k].
+struct CondTree {
+  int n;
+  cts_cond_node node[CTS_MAX_COND_NODES];
+  void* cache[CTS_MAX_COND_NODES];
+};
+
+template <typename T>
+__device__ __forceinline__ T cond_pow(T err, double order) {
+  // Julia's x^p for the Integer orders 1, 2, 3 is x, x*x, x*x*x; other orders go through pow
+  if (order == 1.0) return err;
+  if (order == 2.0) return op_mul(err, err);
+  if (order == 3.0) return op_mul(op_mul(err, err), err);
+  return (T)pow((double)err, order);
+}
+
+template <typename T>
+__device__ __forceinline__ bool cond_eval(const CondTree& t, size_t i, T val, T err, int iter) {
+  bool st[CTS_MAX_COND_NODES];
+  int sp = 0;
+  for (int k = 0; k < t.n; ++k) {
+    const cts_cond_node& nd = t.node[k];
+    bool r;
+    switch (nd.kind) {
+      case CTS_COND_MAX_ERROR: r = (double)err <= nd.p0; break;
+      case CTS_COND_MAX_REL_ERROR: r = (double)err <= __dmul_rn(nd.p0, (double)val); break;
+      case CTS_COND_MAX_ERROR_REDUCTION: r = iter >= 1 && err <= reinterpret_cast<const T*>(t.cache[k])[i]; break;
+      case CTS_COND_MIN_RATE: r = iter >= 1 && err >= reinterpret_cast<const T*>(t.cache[k])[i]; break;
+      default: {
+        r = nd.kind == CTS_COND_ALL;
+        for (int c = 0; c < nd.nchildren; ++c) {
+          const bool v = st[--sp];
+          r = nd.kind == CTS_COND_ALL ? (r && v) : (r || v);
+        }
+      }
+    }
+    st[sp++] = r;
+  }
+  return st[sp - 1];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) component_check_kernel(const CondTree t, const T* __restrict__ val,
+                                                              const T* __restrict__ err, size_t n, int iter,
+                                                              double* __restrict__ nfail) {
+  unsigned local = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    local += cond_eval<T>(t, i, (T)fabs((double)val[i]), (T)fabs((double)err[i]), iter) ? 0u : 1u;
+  local = __reduce_add_sync(0xffffffffu, local);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(nfail, (double)local);  // a count: any order gives the same sum
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) component_update_kernel(const CondTree t, const T* __restrict__ val,
+                                                               const T* __restrict__ err, size_t n, int iter) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const T e = (T)fabs((double)err[i]);
+    for (int k = 0; k < t.n; ++k) {
+      const cts_cond_node& nd = t.node[k];
+      if (nd.kind == CTS_COND_MAX_ERROR_REDUCTION && iter == 0)
+        reinterpret_cast<T*>(t.cache[k])[i] = (T)__dmul_rn(nd.p0, (double)e);
+      else if (nd.kind == CTS_COND_MIN_RATE)
+        reinterpret_cast<T*>(t.cache[k])[i] = (T)__dmul_rn(nd.p0, (double)cond_pow<T>(e, nd.p1));
+    }
+  }
+}
+
+int make_tree(cts_ctx* ctx, int nnodes, const cts_cond_node* nodes, void* const* caches, CondTree& t) {
+  if (nnodes < 1 || nnodes > CTS_MAX_COND_NODES || !nodes) return cts_fail(ctx, CTS_EINVAL, "condition tree: bad node count");
+  t.n = nnodes;
+  for (int k = 0; k < nnodes; ++k) {
+    t.node[k] = nodes[k];
+    t.cache[k] = caches ? caches[k] : nullptr;
+    const bool needs = nodes[k].kind == CTS_COND_MAX_ERROR_REDUCTION || nodes[k].kind == CTS_COND_MIN_RATE;
+    if (needs && !t.cache[k]) return cts_fail(ctx, CTS_EINVAL, "condition tree: missing cache array");
+  }
+  return CTS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // generic small element-wise kernels: out = f(a, b, c)
 // ---------------------------------------------------------------------------------------------
 template <typename T, int NIN, typename F>
@@ -524,6 +606,42 @@ int cts_axpy_chain(cts_ctx* ctx, cts_dtype ft, size_t n, void* out, const void* 
   if (!out || nterms < 0 || (nterms > 0 && (!coef || !terms))) return cts_fail(ctx, CTS_EINVAL, "cts_axpy_chain: bad arguments");
   if (ft == CTS_F64) return dispatch_chain<double>(ctx, n, nterms, out, base, coef, terms, scale, has_scale);
   return dispatch_chain<float>(ctx, n, nterms, out, base, coef, terms, scale, has_scale);
+}
+
+int cts_component_check(cts_ctx* ctx, cts_dtype ft, size_t n, const void* val, const void* err, int nnodes,
+                        const cts_cond_node* nodes, void* const* caches, int iter, double* dev_scratch, int* all_converged) {
+  CTS_CHECK_CTX(ctx);
+  if (!val || !err || !dev_scratch || !all_converged) return cts_fail(ctx, CTS_EINVAL, "cts_component_check: bad arguments");
+  CondTree t;
+  CTS_TRY(make_tree(ctx, nnodes, nodes, caches, t));
+  CTS_CUDA(ctx, cudaMemsetAsync(dev_scratch, 0, sizeof(double), ctx->stream));
+  const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
+  if (ft == CTS_F64)
+    component_check_kernel<double><<<blocks, 256, 0, ctx->stream>>>(t, (const double*)val, (const double*)err, n, iter, dev_scratch);
+  else
+    component_check_kernel<float><<<blocks, 256, 0, ctx->stream>>>(t, (const float*)val, (const float*)err, n, iter, dev_scratch);
+  CTS_LAUNCH_CHECK(ctx);
+  if (ctx->nranks > 1) CTS_TRY(cts_allreduce_sum_f64(ctx, dev_scratch, 1));  // every rank must take the same branch
+  double nfail = 0;
+  CTS_CUDA(ctx, cudaMemcpyAsync(&nfail, dev_scratch, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *all_converged = nfail == 0.0;
+  return CTS_OK;
+}
+
+int cts_component_update(cts_ctx* ctx, cts_dtype ft, size_t n, const void* val, const void* err, int nnodes,
+                         const cts_cond_node* nodes, void* const* caches, int iter) {
+  CTS_CHECK_CTX(ctx);
+  if (!val || !err) return cts_fail(ctx, CTS_EINVAL, "cts_component_update: bad arguments");
+  CondTree t;
+  CTS_TRY(make_tree(ctx, nnodes, nodes, caches, t));
+  const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
+  if (ft == CTS_F64)
+    component_update_kernel<double><<<blocks, 256, 0, ctx->stream>>>(t, (const double*)val, (const double*)err, n, iter);
+  else
+    component_update_kernel<float><<<blocks, 256, 0, ctx->stream>>>(t, (const float*)val, (const float*)err, n, iter);
+  CTS_LAUNCH_CHECK(ctx);
+  return CTS_OK;
 }
 
 int cts_newton_residual(cts_ctx* ctx, cts_dtype ft, size_t n, void* r, const void* U0, double dtgamma, const void* Up) {

@@ -73,6 +73,13 @@ struct cts_newton_cache {
   cts_op_column* fused_op = nullptr;
   const void* fused_U0 = nullptr;
   double fused_dtg = 0.0;
+  // ConvergenceChecker (convergence_checker.jl) and LineSearch (line_search.jl)
+  bool has_checker = false;
+  cts_convergence_checker checker{};
+  double norm_cache[CTS_MAX_COND_NODES] = {};   // per-node scalar caches of the norm condition
+  void* comp_cache[CTS_MAX_COND_NODES] = {};    // per-node element caches of the component condition
+  double* dev_scratch = nullptr;
+  bool line_search = false;
 };
 
 namespace {
@@ -107,6 +114,9 @@ void newton_free(cts_newton_cache* c) {
     if (p) cts_free(c->ctx, p);
   for (void* v : c->V) cts_free(c->ctx, v);
   c->V.clear();
+  for (int k = 0; k < CTS_MAX_COND_NODES; ++k)
+    if (c->comp_cache[k]) cts_free(c->ctx, c->comp_cache[k]);
+  if (c->dev_scratch) cts_free(c->ctx, c->dev_scratch);
 }
 
 double eps_of(cts_dtype ft) { return ft == CTS_F64 ? std::numeric_limits<double>::epsilon() : (double)std::numeric_limits<float>::epsilon(); }
@@ -327,6 +337,116 @@ int solve_krylov(cts_newton_cache* c, void* dx, const void* x, const ResidualFn&
 }
 
 // solve_newton! (newtons_method.jl:609-665); no line search, no convergence checker
+// has_converged / updated_cache of a condition tree on scalars (the norm condition), convergence_condition.jl:41-143
+bool norm_tree_converged(const cts_newton_cache* c, double val, double err, int iter) {
+  bool st[CTS_MAX_COND_NODES];
+  int sp = 0;
+  for (int k = 0; k < c->checker.n_norm; ++k) {
+    const cts_cond_node& nd = c->checker.norm_cond[k];
+    bool r;
+    switch (nd.kind) {
+      case CTS_COND_MAX_ERROR: r = err <= nd.p0; break;
+      case CTS_COND_MAX_REL_ERROR: r = err <= nd.p0 * val; break;
+      case CTS_COND_MAX_ERROR_REDUCTION: r = iter >= 1 && err <= c->norm_cache[k]; break;
+      case CTS_COND_MIN_RATE: r = iter >= 1 && err >= c->norm_cache[k]; break;
+      default:
+        r = nd.kind == CTS_COND_ALL;
+        for (int j = 0; j < nd.nchildren; ++j) {
+          const bool v = st[--sp];
+          r = nd.kind == CTS_COND_ALL ? (r && v) : (r || v);
+        }
+    }
+    st[sp++] = r;
+  }
+  return st[sp - 1];
+}
+
+bool tree_needs_update(const cts_cond_node* nodes, int n, int iter) {
+  for (int k = 0; k < n; ++k)
+    if ((nodes[k].kind == CTS_COND_MAX_ERROR_REDUCTION && iter == 0) || nodes[k].kind == CTS_COND_MIN_RATE) return true;
+  return false;
+}
+
+void norm_tree_update(cts_newton_cache* c, double err, int iter) {
+  auto store = [&](double v) { return c->ft == CTS_F32 ? (double)(float)v : v; };  // the cache has the state eltype
+  for (int k = 0; k < c->checker.n_norm; ++k) {
+    const cts_cond_node& nd = c->checker.norm_cond[k];
+    if (nd.kind == CTS_COND_MAX_ERROR_REDUCTION && iter == 0) c->norm_cache[k] = store(nd.p0 * err);
+    if (nd.kind == CTS_COND_MIN_RATE) {
+      double p = nd.p1 == 1.0 ? err : nd.p1 == 2.0 ? err * err : nd.p1 == 3.0 ? err * err * err : std::pow(err, nd.p1);
+      c->norm_cache[k] = store(nd.p0 * p);
+    }
+  }
+}
+
+// is_converged!(alg, cache, val, err, iter)  convergence_checker.jl:75-108
+int is_converged(cts_newton_cache* c, const void* val, const void* err, int iter, bool* out) {
+  *out = false;
+  if (!c->has_checker) return CTS_OK;
+  cts_ctx* ctx = c->ctx;
+  const cts_convergence_checker& k = c->checker;
+  bool converged = false;
+  double norm_val = 0, norm_err = 0;
+  auto component = [&](bool* r) -> int {
+    int all = 0;
+    CTS_TRY(cts_component_check(ctx, c->ft, c->n, val, err, k.n_comp, k.comp_cond, c->comp_cache, iter, c->dev_scratch, &all));
+    *r = all != 0;
+    return CTS_OK;
+  };
+  if (k.n_norm == 0) {
+    CTS_TRY(component(&converged));
+  } else {
+    CTS_TRY(cts_nrm2(ctx, c->ft, c->n, val, &norm_val));
+    CTS_TRY(cts_nrm2(ctx, c->ft, c->n, err, &norm_err));
+    converged = norm_tree_converged(c, norm_val, norm_err, iter);
+    if (k.n_comp > 0) {
+      bool cc = false;
+      if (!k.combiner_or) {
+        if (converged) {
+          CTS_TRY(component(&cc));
+          converged = cc;
+        }
+      } else if (!converged) {
+        CTS_TRY(component(&cc));
+        converged = cc;
+      }
+    }
+  }
+  if (!converged) {  // only update caches if they will be needed for future iters
+    if (k.n_norm > 0 && tree_needs_update(k.norm_cond, k.n_norm, iter)) norm_tree_update(c, norm_err, iter);
+    if (k.n_comp > 0 && tree_needs_update(k.comp_cond, k.n_comp, iter))
+      CTS_TRY(cts_component_update(ctx, c->ft, c->n, val, err, k.n_comp, k.comp_cond, c->comp_cache, iter));
+  }
+  *out = converged;
+  return CTS_OK;
+}
+
+// line_search!(alg, x, Δx, f, f!, prepare_for_f!)  line_search.jl:28-47
+int line_search(cts_newton_cache* c, void* x, const ResidualFn& f_, const PrepareFn* prepare) {
+  cts_ctx* ctx = c->ctx;
+  double normf0 = 0, normf = 0;
+  CTS_TRY(cts_nrm2(ctx, c->ft, c->n, c->f, &normf0));
+  if (prepare) CTS_TRY((*prepare)(x));
+  CTS_TRY(f_(c->f, x));
+  c->stats.f_evals++;
+  CTS_TRY(cts_nrm2(ctx, c->ft, c->n, c->f, &normf));
+  double alpha = 0.5;
+  for (int i = 1; ((normf > normf0) || !std::isfinite(normf)) && i <= 5; ++i) {
+    {
+      cts_prof_scope ps(ctx, CTS_PROF_NEWTON_EW);
+      double coef[1] = {alpha};
+      const void* terms[1] = {c->dx};
+      CTS_TRY(cts_axpy_n(ctx, c->ft, c->n, x, nullptr, 1.0, x, 1, 0, coef, terms, 0));  // `x .+= α * Δx`
+    }
+    if (prepare) CTS_TRY((*prepare)(x));
+    CTS_TRY(f_(c->f, x));
+    c->stats.f_evals++;
+    CTS_TRY(cts_nrm2(ctx, c->ft, c->n, c->f, &normf));
+    alpha /= 2;
+  }
+  return CTS_OK;
+}
+
 int solve_newton(cts_newton_cache* c, void* x, const ResidualFn& f_, const JacFn* j_, const PrepareFn* prepare) {
   cts_ctx* ctx = c->ctx;
   const cts_newton_config& cfg = c->cfg;
@@ -357,7 +477,11 @@ int solve_newton(cts_newton_cache* c, void* x, const ResidualFn& f_, const JacFn
       cts_prof_scope ps(ctx, CTS_PROF_NEWTON_EW);
       CTS_TRY(cts_sub_inplace(ctx, c->ft, c->n, x, c->dx));  // K5
     }
-    if (n < cfg.max_iters) {
+    if (c->line_search) CTS_TRY(line_search(c, x, f_, prepare));  // :652
+    bool converged = false;
+    CTS_TRY(is_converged(c, x, c->dx, n, &converged));  // :656
+    if (converged) break;
+    if (n < cfg.max_iters && !c->line_search) {  // :658-660
       if (prepare) CTS_TRY((*prepare)(x));
       CTS_TRY(f_(c->f, x));
       c->stats.f_evals++;
@@ -424,6 +548,47 @@ int cts_newton_solve(cts_newton_cache* c, void* x, cts_residual_fn f, cts_jac_fn
 int cts_newton_cache_stats(cts_newton_cache* c, cts_solver_stats* out) {
   if (!c || !out) return CTS_EINVAL;
   *out = c->stats;
+  return CTS_OK;
+}
+
+int cts_newton_cache_set_convergence_checker(cts_newton_cache* c, const cts_convergence_checker* checker) {
+  if (!c) return CTS_EINVAL;
+  cts_ctx* ctx = c->ctx;
+  for (int k = 0; k < CTS_MAX_COND_NODES; ++k) {
+    if (c->comp_cache[k]) cts_free(ctx, c->comp_cache[k]);
+    c->comp_cache[k] = nullptr;
+    c->norm_cache[k] = std::nan("");
+  }
+  c->has_checker = false;
+  if (!checker) return CTS_OK;
+  if (checker->n_norm == 0 && checker->n_comp == 0)
+    return cts_fail(ctx, CTS_EINVAL, "ConvergenceChecker must have at least one ConvergenceCondition");
+  if (checker->n_norm < 0 || checker->n_norm > CTS_MAX_COND_NODES || checker->n_comp < 0 || checker->n_comp > CTS_MAX_COND_NODES)
+    return cts_fail(ctx, CTS_EINVAL, "ConvergenceChecker: too many condition nodes");
+  c->checker = *checker;
+  if (!c->dev_scratch) CTS_TRY(cts_alloc(ctx, 64, (void**)&c->dev_scratch));
+  const size_t es = cts_sizeof(c->ft);
+  for (int k = 0; k < checker->n_comp; ++k) {
+    const int kind = checker->comp_cond[k].kind;
+    if (kind != CTS_COND_MAX_ERROR_REDUCTION && kind != CTS_COND_MIN_RATE) continue;
+    CTS_TRY(cts_alloc(ctx, c->n * es, &c->comp_cache[k]));
+    CTS_CUDA(ctx, cudaMemsetAsync(c->comp_cache[k], 0xff, c->n * es, ctx->stream));  // all-ones bit pattern == NaN
+  }
+  c->has_checker = true;
+  return CTS_OK;
+}
+
+int cts_newton_cache_set_line_search(cts_newton_cache* c, int enabled) {
+  if (!c) return CTS_EINVAL;
+  c->line_search = enabled != 0;
+  return CTS_OK;
+}
+
+int cts_newton_cache_is_converged(cts_newton_cache* c, const void* val, const void* err, int iter, int* converged) {
+  if (!c || !val || !err || !converged) return CTS_EINVAL;
+  bool r = false;
+  CTS_TRY(is_converged(c, val, err, iter, &r));
+  *converged = r ? 1 : 0;
   return CTS_OK;
 }
 
@@ -615,6 +780,7 @@ int solve_implicit_equation(cts_imex_cache* c, void* U, const void* U0, double t
 cts_op_column* fusable_column_op(const cts_imex_cache* c) {
   const cts_ode_function& f = c->f;
   if (!c->fusion || !c->ncfg.present || c->ncfg.max_iters != 1 || c->ncfg.use_krylov) return nullptr;
+  if (c->nm && (c->nm->has_checker || c->nm->line_search)) return nullptr;  // is_converged! / line_search! must run
   if (f.T_imp != cts_op_column_T_imp || f.Wfact != cts_op_column_Wfact || f.ldiv != cts_op_column_ldiv) return nullptr;
   if (f.has_lim) return nullptr;
   if (f.dss && f.dss != cts_op_column_dss) return nullptr;  // the library dss! only rewrites ghost rows
@@ -1081,6 +1247,12 @@ int cts_imex_cache_buffer(cts_imex_cache* c, const char* name, void** dptr) {
   else if (idx("T_lim") >= 0) *dptr = c->T_lim[idx("T_lim")];
   else if (idx("T_imp") >= 0) *dptr = c->T_imp[idx("T_imp")];
   else return cts_fail(c->ctx, CTS_EINVAL, "unknown buffer name");
+  return CTS_OK;
+}
+
+int cts_imex_cache_newton(cts_imex_cache* c, cts_newton_cache** out) {
+  if (!c || !out) return CTS_EINVAL;
+  *out = c->nm;
   return CTS_OK;
 }
 

@@ -189,6 +189,12 @@ class IMEXCache:
                                                  C.byref(ncfg), C.byref(h)), "init_cache")
         self.handle = h
         self._keep = (tab_c, ncfg)
+        if alg.newtons_method is not None:
+            nm = C.c_void_p()
+            self.ctx.check(lib.cts_imex_cache_newton(h, C.byref(nm)))
+            self.newton_handle = nm
+            if nm.value:
+                alg.newtons_method.configure_cache(self.ctx, nm)
 
     def buffer(self, name: str) -> Optional[B200Vector]:
         p = C.c_void_p()

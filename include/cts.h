@@ -318,6 +318,41 @@ int cts_newton_cache_destroy(cts_newton_cache* c);
 int cts_newton_solve(cts_newton_cache* c, void* x, cts_residual_fn f, cts_jac_fn j, cts_prepare_fn prepare, void* ud);
 int cts_newton_cache_stats(cts_newton_cache* c, cts_solver_stats* out);
 
+/* ConvergenceChecker (src/utilities/convergence_checker.jl:32-108) with ConvergenceCondition trees
+ * (convergence_condition.jl:41-143) in postfix order: leaves first, then the MultipleConditions node that combines the
+ * `nchildren` results below it.  p0 = max_err | max_rel_err | max_reduction | rate; p1 = order (MinimumRateOfConvergence).
+ * `norm` is LinearAlgebra.norm (the deterministic device reduction, all-reduced over ranks); custom norms are a host-side
+ * concern of the binding.  Condition caches start as NaN (the reference leaves them uninitialised), so a condition that
+ * reads its cache before the first update is false. */
+typedef enum {
+  CTS_COND_MAX_ERROR = 0, CTS_COND_MAX_REL_ERROR = 1, CTS_COND_MAX_ERROR_REDUCTION = 2, CTS_COND_MIN_RATE = 3,
+  CTS_COND_ALL = 4, CTS_COND_ANY = 5
+} cts_cond_kind;
+typedef struct { int kind; int nchildren; double p0, p1; } cts_cond_node;
+#define CTS_MAX_COND_NODES 16
+typedef struct {
+  int n_norm;                                   /* 0: norm_condition === nothing      */
+  cts_cond_node norm_cond[CTS_MAX_COND_NODES];
+  int n_comp;                                   /* 0: component_condition === nothing */
+  cts_cond_node comp_cond[CTS_MAX_COND_NODES];
+  int combiner_or;                              /* condition_combiner: 0 = &, 1 = |   */
+} cts_convergence_checker;
+/* `NewtonsMethod(; convergence_checker, line_search)` (newtons_method.jl:568-581): NULL / 0 = nothing.  Allocates the
+ * checker cache (`allocate_cache`, convergence_checker.jl:45-60).  A Newton solve with either of them set always runs
+ * the generic iteration (no fused column stage). */
+int cts_newton_cache_set_convergence_checker(cts_newton_cache* c, const cts_convergence_checker* checker);
+int cts_newton_cache_set_line_search(cts_newton_cache* c, int enabled);   /* LineSearch(), line_search.jl:23-47 */
+/* `is_converged!(checker, cache, val, err, iter)` on its own (test/utils/convergence_checker.jl) */
+int cts_newton_cache_is_converged(cts_newton_cache* c, const void* val, const void* err, int iter, int* converged);
+/* the Newton cache embedded in an IMEX cache (NULL when the algorithm has no NewtonsMethod) */
+int cts_imex_cache_newton(cts_imex_cache* c, cts_newton_cache** out);
+/* all(component_condition) over |val|, |err| (convergence_checker.jl:62-73) and the cache update (:97-105);
+ * caches[k] is the per-element cache of node k (NULL for nodes without one) */
+int cts_component_check(cts_ctx* ctx, cts_dtype ft, size_t n, const void* val, const void* err, int nnodes,
+                        const cts_cond_node* nodes, void* const* caches, int iter, double* dev_scratch, int* all_converged);
+int cts_component_update(cts_ctx* ctx, cts_dtype ft, size_t n, const void* val, const void* err, int nnodes,
+                         const cts_cond_node* nodes, void* const* caches, int iter);
+
 /* ------------------------------------------------------------------ library-native operators -- */
 /* These are the "user model" pieces (layer L5 of the reference) of the synthetic benchmark problems of
  * SURVEY §8d, provided as device code so the whole step stays on the GPU.  Each exposes hook functions

@@ -469,6 +469,166 @@ class NewtonsMethod:  # :568-581
     update_j: Any = field(default_factory=lambda: UpdateEvery("NewNewtonIteration"))
     krylov_method: Optional[KrylovMethod] = None
     convergence_checker: Any = None
+    line_search: Any = None
+
+
+# --------------------------------------------------------------------------------------
+# ConvergenceChecker / ConvergenceCondition / LineSearch
+# (src/utilities/convergence_condition.jl:41-143, convergence_checker.jl:32-108, line_search.jl:23-47)
+# --------------------------------------------------------------------------------------
+class ConvergenceCondition:
+    has_cache = False
+
+    def needs_cache_update(self, it):
+        return False
+
+
+@dataclass
+class MaximumError(ConvergenceCondition):  # :41-44
+    max_err: float
+
+    def has_converged(self, cache, val, err, it):
+        return err <= self.max_err
+
+
+@dataclass
+class MaximumRelativeError(ConvergenceCondition):  # :52-56
+    max_rel_err: float
+
+    def has_converged(self, cache, val, err, it):
+        return err <= self.max_rel_err * val
+
+
+@dataclass
+class MaximumErrorReduction(ConvergenceCondition):  # :66-75
+    max_reduction: float
+    has_cache = True
+
+    def has_converged(self, cache, val, err, it):
+        return (err <= cache) if it >= 1 else (err != err) & False  # `iter >= 1 && err <= cache.max_err`
+
+    def needs_cache_update(self, it):
+        return it == 0
+
+    def updated_cache(self, cache, val, err, it):
+        return self.max_reduction * err
+
+
+@dataclass
+class MinimumRateOfConvergence(ConvergenceCondition):  # :96-108
+    rate: float
+    order: float = 1
+    has_cache = True
+
+    def has_converged(self, cache, val, err, it):
+        return (err >= cache) if it >= 1 else (err != err) & False
+
+    def needs_cache_update(self, it):
+        return True
+
+    def updated_cache(self, cache, val, err, it):
+        return self.rate * err ** self.order
+
+
+class MultipleConditions(ConvergenceCondition):  # :116-143
+    has_cache = True
+
+    def __init__(self, *args):
+        if args and args[0] in (all, any):
+            self.combiner, self.conditions = args[0], tuple(args[1:])
+        else:
+            self.combiner, self.conditions = all, tuple(args)
+
+    def has_converged(self, caches, val, err, it):
+        res = [c.has_converged(k, val, err, it) for c, k in zip(self.conditions, caches)]
+        if isinstance(res[0], np.ndarray) or any(isinstance(r, np.ndarray) for r in res):
+            res = [np.broadcast_to(np.asarray(r, dtype=bool), np.shape(err)) for r in res]
+            return np.logical_and.reduce(res) if self.combiner is all else np.logical_or.reduce(res)
+        return self.combiner(bool(r) for r in res)
+
+    def needs_cache_update(self, it):
+        return any(c.needs_cache_update(it) for c in self.conditions)
+
+    def updated_cache(self, caches, val, err, it):
+        return tuple(c.updated_cache(k, val, err, it) if c.needs_cache_update(it) else k
+                     for c, k in zip(self.conditions, caches))
+
+
+def _empty_cond_cache(cond, proto):
+    """`Ref{cache_type(...)}()` / `similar(val_prototype, cache_type(...))`: uninitialised in the reference; NaN here, so a
+    condition that reads its cache before the first update is false (documented deviation from undefined behaviour)."""
+    if isinstance(cond, MultipleConditions):
+        return tuple(_empty_cond_cache(c, proto) for c in cond.conditions)
+    if not cond.has_cache:
+        return None
+    return np.nan if proto is None else np.full_like(proto, np.nan)
+
+
+@dataclass
+class ConvergenceChecker:  # convergence_checker.jl:32-43
+    norm_condition: Any = None
+    component_condition: Any = None
+    condition_combiner: str = "&"
+    norm: Callable = None
+
+    def allocate_cache(self, val_prototype):  # :45-60
+        if self.norm_condition is None and self.component_condition is None:
+            raise ValueError("ConvergenceChecker must have at least one ConvergenceCondition")
+        return {"norm_cache": None if self.norm_condition is None else _empty_cond_cache(self.norm_condition, None),
+                "component_cache": None if self.component_condition is None
+                else _empty_cond_cache(self.component_condition, val_prototype)}
+
+
+def is_converged(alg: Optional[ConvergenceChecker], cache, val, err, it) -> bool:
+    """is_converged!, convergence_checker.jl:75-108."""
+    if alg is None:
+        return False
+    nc, cc = alg.norm_condition, alg.component_condition
+    nrm = alg.norm if alg.norm is not None else norm2
+
+    def comp():
+        r = cc.has_converged(cache["component_cache"], np.abs(val), np.abs(err), it)
+        return bool(np.all(np.broadcast_to(np.asarray(r, dtype=bool), np.shape(val))))
+
+    if nc is None:
+        converged = comp()
+    else:
+        norm_val, norm_err = nrm(val), nrm(err)
+        converged = bool(nc.has_converged(cache["norm_cache"], norm_val, norm_err, it))
+        if cc is not None:
+            converged = (converged and comp()) if alg.condition_combiner == "&" else (converged or comp())
+    if not converged:
+        if nc is not None and nc.needs_cache_update(it):
+            cache["norm_cache"] = nc.updated_cache(cache["norm_cache"], norm_val, norm_err, it)
+        if cc is not None and cc.needs_cache_update(it):
+            cache["component_cache"] = cc.updated_cache(cache["component_cache"], np.abs(val), np.abs(err), it)
+    return converged
+
+
+@dataclass
+class LineSearch:  # line_search.jl:23-25
+    norm: Callable = None
+
+
+def line_search(alg: Optional[LineSearch], x, dx, f, f_, prepare_for_f):
+    """line_search!, line_search.jl:27-47: x already holds x_old - Δx, f holds f(x_old)."""
+    if alg is None:
+        return
+    nrm = alg.norm if alg.norm is not None else norm2
+    normf0 = nrm(f)
+    if prepare_for_f is not None:
+        prepare_for_f(x)
+    f_(f, x)
+    normf = nrm(f)
+    i, alpha = 1, 0.5
+    while ((normf > normf0) or not math.isfinite(normf)) and i <= 5:
+        x[...] = (x.astype(np.float64) + alpha * dx.astype(np.float64)).astype(x.dtype)  # `x .+= α * Δx`
+        if prepare_for_f is not None:
+            prepare_for_f(x)
+        f_(f, x)
+        normf = nrm(f)
+        alpha /= 2
+        i += 1
 
 
 def sym_givens(a: float, b: float):
@@ -602,7 +762,8 @@ def allocate_newton_cache(alg: NewtonsMethod, x_prototype, j_prototype=None):
     km = alg.krylov_method
     assert not (j_prototype is None and (km is None or km.jacobian_free_jvp is None))
     cache = {"dx": np.zeros_like(x_prototype), "f": np.zeros_like(x_prototype),
-             "j": None if j_prototype is None else j_prototype.zero(), "stats": []}
+             "j": None if j_prototype is None else j_prototype.zero(), "stats": [],
+             "checker": None if alg.convergence_checker is None else alg.convergence_checker.allocate_cache(x_prototype)}
     if km is not None:
         cache["forcing"] = {}
         if km.jacobian_free_jvp is not None:
@@ -612,7 +773,7 @@ def allocate_newton_cache(alg: NewtonsMethod, x_prototype, j_prototype=None):
 
 
 def solve_newton(alg: NewtonsMethod, cache, x, f_, j_=None, prepare_for_f=None):
-    """newtons_method.jl:609-665 (no line search; convergence_checker = nothing)."""
+    """newtons_method.jl:609-665."""
     if cache is None:
         return
     dx, f, j = cache["dx"], cache["f"], cache["j"]
@@ -628,10 +789,16 @@ def solve_newton(alg: NewtonsMethod, cache, x, f_, j_=None, prepare_for_f=None):
         else:
             _solve_krylov(km, cache, dx, x, f_, f, n - 1, prepare_for_f, j)
         x[...] = x - dx  # :651
-        if n < alg.max_iters:  # :658-660
+        line_search(alg.line_search, x, dx, f, f_, prepare_for_f)  # :652
+        if is_converged(alg.convergence_checker, cache.get("checker"), x, dx, n):  # :656
+            cache["newton_iters"] = cache.get("newton_iters", 0) + n
+            break
+        elif n < alg.max_iters and alg.line_search is None:  # :658-660
             if prepare_for_f is not None:
                 prepare_for_f(x)
             f_(f, x)
+    else:
+        cache["newton_iters"] = cache.get("newton_iters", 0) + alg.max_iters
 
 
 def _solve_krylov(km: KrylovMethod, cache, dx, x, f_, f, n, prepare_for_f, j):
