@@ -177,8 +177,40 @@ function CTS.init_cache(prob::CTS.ODEProblem{<:Any, <:B200Vector{FT}}, alg::CTS.
     check(u0.ctx.handle, ccall((:cts_imex_cache_create, libcts), Cint,
         (Ptr{Cvoid}, Cint, Csize_t, Ref{ImexTableau}, Cint, Ref{OdeFunction}, Ref{NewtonConfig}, Ref{Ptr{Cvoid}}),
         u0.ctx.handle, ft(FT), length(u0), tab, alg.constraint isa CTS.SSP ? 1 : 0, tbl, ncfg, h))
+    configure_newton(u0.ctx, h[], alg.newtons_method)
     c = B200IMEXCache(h[], env, keep)
     finalizer(x -> ccall((:cts_imex_cache_destroy, libcts), Cint, (Ptr{Cvoid},), x.handle), c)
+end
+
+# ConvergenceChecker / LineSearch (convergence_checker.jl, convergence_condition.jl, line_search.jl): condition trees are
+# flattened to postfix order for `cts_convergence_checker`
+struct CondNode
+    kind::Cint; nchildren::Cint; p0::Cdouble; p1::Cdouble
+end
+struct ConvergenceCheckerC
+    n_norm::Cint; norm_cond::NTuple{16, CondNode}; n_comp::Cint; comp_cond::NTuple{16, CondNode}; combiner_or::Cint
+end
+cond_nodes(c::CTS.MaximumError) = [CondNode(0, 0, c.max_err, 0)]
+cond_nodes(c::CTS.MaximumRelativeError) = [CondNode(1, 0, c.max_rel_err, 0)]
+cond_nodes(c::CTS.MaximumErrorReduction) = [CondNode(2, 0, c.max_reduction, 0)]
+cond_nodes(c::CTS.MinimumRateOfConvergence) = [CondNode(3, 0, c.rate, c.order)]
+cond_nodes(c::CTS.MultipleConditions) =
+    vcat(mapreduce(cond_nodes, vcat, reverse(collect(c.conditions))), [CondNode(c.condition_combiner === all ? 4 : 5, length(c.conditions), 0, 0)])
+cond_nodes(::Nothing) = CondNode[]
+pad16(v) = ntuple(k -> k <= length(v) ? v[k] : CondNode(0, 0, 0, 0), 16)
+function configure_newton(ctx, cache_handle, nm)
+    isnothing(nm) && return
+    (isnothing(nm.convergence_checker) && isnothing(nm.line_search)) && return
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx.handle, ccall((:cts_imex_cache_newton, libcts), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), cache_handle, h))
+    if !isnothing(nm.convergence_checker)
+        cc = nm.convergence_checker
+        cc.norm === LinearAlgebra.norm || error("the B200 path evaluates LinearAlgebra.norm only")
+        nn, nc = cond_nodes(cc.norm_condition), cond_nodes(cc.component_condition)
+        chk = ConvergenceCheckerC(length(nn), pad16(nn), length(nc), pad16(nc), cc.condition_combiner === (|) ? 1 : 0)
+        check(ctx.handle, ccall((:cts_newton_cache_set_convergence_checker, libcts), Cint, (Ptr{Cvoid}, Ref{ConvergenceCheckerC}), h[], chk))
+    end
+    isnothing(nm.line_search) || check(ctx.handle, ccall((:cts_newton_cache_set_line_search, libcts), Cint, (Ptr{Cvoid}, Cint), h[], 1))
 end
 
 function CTS.step_u!(integrator, cache::B200IMEXCache)                                   # integrators.jl:441-444
