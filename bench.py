@@ -263,11 +263,11 @@ def run_ours(args):
         host.copy_(u.tensor)
         barrier()
         ev0.record(stream)
-        for _ in range(e2e_steps):
-            u.tensor.copy_(host, non_blocking=True)
-            cts.step_(integ)
-            host.copy_(u.tensor, non_blocking=True)
-            stream.synchronize()
+        nbytes = u.tensor.numel() * 8
+        for _ in range(e2e_steps):  # every call below is a C-ABI entry point of libcts_sm100a.so on a HOST buffer
+            ctx.check(ctx.lib.cts_memcpy_h2d(ctx.handle, u.ptr, host.data_ptr(), nbytes), "h2d")
+            cts.step_(integ)                                                    # cts_imex_step
+            ctx.check(ctx.lib.cts_memcpy_d2h_sync(ctx.handle, host.data_ptr(), u.ptr, nbytes), "d2h")
         ev1.record(stream)
         barrier()
         ms_e2e = ev0.elapsed_time(ev1)
@@ -300,7 +300,7 @@ def run_ours(args):
                 "nominal_peak": 8000.0, "frac_of_nominal": achieved / 8000.0,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch (mean of the step's 3 launches) from the
                 # ncu --set full capture summarised in profiles/r1_step_kernels_ncu.txt; same workload, stored W only
-                "traffic": 9.668e9 if (stored_w and ndof_local == 134348800) else None,
+                "traffic": 9.668e9 if (stored_w and ndof_local == (NY + 2) * NX * NLEV) else None,
                 "algorithmic_bytes_per_launch": per_step / 3.0,
                 "launches": fs_n, "avg_launch_ms": fs_ms / fs_n,
                 "algorithmic_bytes_per_dof_per_launch": stage_bytes(stored_w),
@@ -318,7 +318,7 @@ def run_ours(args):
             "e2e": {"value": n_owned * world * STAGES * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(u.tensor.numel() * 8), "d2h_bytes_per_step": int(u.tensor.numel() * 8),
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
-                    "api": "cts_b200.step_(integrator) with the state uploaded from / downloaded to pinned host memory every step"},
+                    "api": "C ABI: cts_memcpy_h2d (pinned host state) + cts_imex_step (via cts_b200.step_) + cts_memcpy_d2h_sync, every step"},
             "gpu_launches": launches, "clocks": clocks, "solver_stats": stats, "finite": finite}
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_reference(2, 1)
