@@ -119,6 +119,7 @@ SIGNATURES = [
     ("cts_memset_zero", _I, [_P, _P, _SZ]),
     ("cts_memcpy_h2d", _I, [_P, _P, _P, _SZ]),
     ("cts_memcpy_d2h_sync", _I, [_P, _P, _P, _SZ]),
+    ("cts_memcpy_d2h", _I, [_P, _P, _P, _SZ]),
     ("cts_memcpy_d2d", _I, [_P, _P, _P, _SZ]),
     ("cts_axpy_n", _I, [_P, _I, _SZ, _P, _P, _D, _P, _I, _I, c_double_p, c_void_pp, _I]),
     ("cts_newton_cache_set_convergence_checker", _I, [_P, _P]),

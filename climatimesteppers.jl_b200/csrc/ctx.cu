@@ -147,6 +147,12 @@ int cts_memcpy_d2h_sync(cts_ctx* ctx, void* dst_host, const void* src_dev, size_
   return CTS_OK;
 }
 
+int cts_memcpy_d2h(cts_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+  CTS_CHECK_CTX(ctx);
+  if (bytes) CTS_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return CTS_OK;
+}
+
 int cts_memcpy_d2d(cts_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes) {
   CTS_CHECK_CTX(ctx);
   if (bytes) CTS_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));

@@ -65,6 +65,7 @@ int cts_free(cts_ctx* ctx, void* dptr);
 int cts_memset_zero(cts_ctx* ctx, void* dptr, size_t bytes);
 int cts_memcpy_h2d(cts_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);  /* stream-ordered; host buffer may be pageable (then synchronous) */
 int cts_memcpy_d2h_sync(cts_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int cts_memcpy_d2h(cts_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);       /* stream-ordered (pinned host buffer); the saving callback's async D2H */
 int cts_memcpy_d2d(cts_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);
 
 /* ------------------------------------------------------------------ per-kernel timing ---------- */
