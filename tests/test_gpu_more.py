@@ -310,3 +310,65 @@ def test_K11_ssprk_stage_equals_chained_passes(cts, dtype, native, n_imp, final)
     np.testing.assert_array_equal(got_temp.to_host(), ref_U.to_host())
     if not final:
         np.testing.assert_array_equal(got_exp.to_host(), ref_exp.to_host())
+
+
+def _host_mem_gib():
+    try:
+        import psutil
+        return psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        return 0.0
+
+
+def test_full_size_step_equals_c_oracle(cts):
+    # BASELINE configs[2] at its full size (2^21 columns x 64 levels = 2^27 DOF): one ARS343 step on the GPU (fused path,
+    # stored W) against the C oracle running the reference's pass structure on the host cores -- bit for bit
+    if _host_mem_gib() < 40:
+        pytest.skip("needs ~25 GiB of host memory for the C oracle at 2^27 DOF")
+    import torch
+    if torch.cuda.mem_get_info()[0] < 30 * 2 ** 30:
+        pytest.skip("needs ~20 GiB of device memory")
+    nlev, nx, ny = 64, 2048, 1024
+    K = CO.fill_hash((ny + 2) * nx, 2, 0, 0.25, 2.0)
+    z = (np.arange(nlev) + 1) / (nlev + 1)
+    S = 5.0 * np.exp(-((z - 0.3) ** 2) / 0.01)
+    co = CO.ColumnARK(nlev, nx, ny, K, S, 1.0, 1, tab=R.tableau("ARS343"), max_iters=1, update_j="NewTimeStep")
+    uo = CO.fill_hash((ny + 2) * nx * nlev, 3)
+    co.dss(uo)
+    co.step(uo, 0.0, 0.02)
+    op = cts.ColumnOperator(nlev, nx, ny, dev(cts, K), S_lev=dev(cts, S), nu=1.0, halo=1)
+    u = cts.B200Vector.zeros(op.ndof).fill_hash(3)
+    op.dss(u, None, 0.0)
+    integ = cts.init(cts.ODEProblem(op.ode_function(), u, (0.0, 1e9), None),
+                     cts.IMEXAlgorithm(cts.ARS343(), cts.NewtonsMethod(max_iters=1, update_j=cts.UpdateEvery(cts.NewTimeStep))),
+                     dt=0.02, save=False)
+    cts.step_(integ)
+    got = u.to_host()
+    assert got.shape == uo.shape and np.array_equal(got, uo)
+    assert integ.cache.stats()["fused_stage_launches"] == 3
+    del co, uo, got
+
+
+def test_full_size_power_of_two_linearity(cts):
+    # size-independent property at 2^27 DOF: without the source term the whole step is linear in the state, and scaling
+    # by a power of two commutes with every rounding -> step(4u) == 4 step(u) exactly
+    import torch
+    if torch.cuda.mem_get_info()[0] < 60 * 2 ** 30:
+        pytest.skip("needs ~45 GiB of device memory")
+    nlev, nx, ny = 64, 2048, 1024
+    K = cts.B200Vector.zeros((ny + 2) * nx).fill_hash(2, 0, 0.25, 2.0)
+    outs = []
+    for scale in (1.0, 4.0):
+        op = cts.ColumnOperator(nlev, nx, ny, K, nu=1.0, halo=1)
+        u = cts.B200Vector.zeros(op.ndof).fill_hash(3)
+        u.tensor.mul_(scale)
+        op.dss(u, None, 0.0)
+        integ = cts.init(cts.ODEProblem(op.ode_function(), u, (0.0, 1e9), None),
+                         cts.IMEXAlgorithm(cts.ARS343(), cts.NewtonsMethod(max_iters=1, update_j=cts.UpdateEvery(cts.NewTimeStep))),
+                         dt=0.02, save=False)
+        cts.step_(integ)
+        cts.step_(integ)
+        outs.append(u)
+        del integ, op
+    assert bool(torch.equal(outs[0].tensor * 4.0, outs[1].tensor))
+    assert bool(torch.isfinite(outs[1].tensor).all())
