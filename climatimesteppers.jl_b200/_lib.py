@@ -128,6 +128,8 @@ SIGNATURES = [
     ("cts_imex_cache_newton", _I, [_P, _P]),
     ("cts_component_check", _I, [_P, _I, _SZ, _P, _P, _I, _P, _P, _I, _P, _P]),
     ("cts_component_update", _I, [_P, _I, _SZ, _P, _P, _I, _P, _P, _I]),
+    ("cts_axpby_dot", _I, [_P, _I, _SZ, _D, _P, _D, _P, _P, _P]),
+    ("cts_div_scalar_nrm2", _I, [_P, _I, _SZ, _P, _P, _D, _P]),
     ("cts_axpy_chain", _I, [_P, _I, _SZ, _P, _P, _I, c_double_p, c_void_pp, _D, _I]),
     ("cts_rosenbrock_cache_create", _I, [_P, _I, _SZ, _P, _P, TENDENCY_FN, _P]),
     ("cts_rosenbrock_cache_destroy", _I, [_P]),

@@ -80,6 +80,12 @@ struct cts_newton_cache {
   void* comp_cache[CTS_MAX_COND_NODES] = {};    // per-node element caches of the component condition
   double* dev_scratch = nullptr;
   bool line_search = false;
+  // values GMRES / jvp! would otherwise recompute (bit-identical reuse)
+  const void* known_norm_ptr = nullptr;  // a basis vector whose norm came out of the kernel that produced it
+  double known_norm = 0.0;
+  bool fuse_reductions = true;           // cleared together with the engine's fusion switch (reference pass structure)
+  bool xstat_valid = false;              // sum(1+|x|) (or norm(x)) of the current solve_krylov! call
+  double xstat = 0.0;
 };
 
 namespace {
@@ -151,21 +157,30 @@ void sym_givens(double a, double b, double& c, double& s, double& rho) {
 }
 
 // ForwardDiffJVP step (newtons_method.jl:107-135,177)
+// (norm(Δx) is reused when GMRES already produced it together with the basis vector; sum(1+|x|) / norm(x) are the same
+//  for every JVP of one solve_krylov! call -- x does not change -- and are computed once per call)
 int jvp_step(cts_newton_cache* c, const void* dx, const void* x, double* eps_out) {
   cts_ctx* ctx = c->ctx;
   double e = 0, ndx = 0;
   const double se = std::sqrt(eps_of(c->ft));
-  CTS_TRY(cts_nrm2(ctx, c->ft, c->n, dx, &ndx));
+  if (c->known_norm_ptr == dx && dx)
+    ndx = c->known_norm;
+  else
+    CTS_TRY(cts_nrm2(ctx, c->ft, c->n, dx, &ndx));
   if (c->cfg.jvp_step_kind == 1) {
     e = se / ndx;
   } else if (c->cfg.jvp_step_kind == 2) {
-    double nx = 0;
-    CTS_TRY(cts_nrm2(ctx, c->ft, c->n, x, &nx));
-    e = std::sqrt(eps_of(c->ft) * (1 + nx)) / ndx;
+    if (!c->xstat_valid || !c->fuse_reductions) {
+      CTS_TRY(cts_nrm2(ctx, c->ft, c->n, x, &c->xstat));
+      c->xstat_valid = true;
+    }
+    e = std::sqrt(eps_of(c->ft) * (1 + c->xstat)) / ndx;
   } else {
-    double s1 = 0;
-    CTS_TRY(cts_sum1pabs(ctx, c->ft, c->n, x, &s1));
-    e = se * s1 / ((double)global_length(ctx, c->n) * ndx);
+    if (!c->xstat_valid || !c->fuse_reductions) {
+      CTS_TRY(cts_sum1pabs(ctx, c->ft, c->n, x, &c->xstat));
+      c->xstat_valid = true;
+    }
+    e = se * c->xstat / ((double)global_length(ctx, c->n) * ndx);
   }
   double adj = c->cfg.jvp_step_adjustment == 0.0 ? 1.0 : c->cfg.jvp_step_adjustment;
   *eps_out = round_to(c->ft, round_to(c->ft, adj) * round_to(c->ft, e));
@@ -228,7 +243,15 @@ int gmres(cts_newton_cache* c, const std::function<int(void* out, const void* v)
     return CTS_OK;
   };
   CTS_TRY(ensure_vec(0));
-  CTS_TRY(cts_div_scalar(ctx, ft, n, c->V[0], r0, rNorm));
+  const bool fuse_red = c->fuse_reductions;
+  std::vector<double> vnorm(1, 0.0);  // norm(V[k]) for jvp!'s step size, produced together with V[k]
+  if (fuse_red && c->cfg.jacobian_free_jvp) {
+    cts_prof_scope ps(ctx, CTS_PROF_KRYLOV);
+    CTS_TRY(cts_div_scalar_nrm2(ctx, ft, n, c->V[0], r0, rNorm, &vnorm[0]));
+  } else {
+    cts_prof_scope ps(ctx, CTS_PROF_KRYLOV);
+    CTS_TRY(cts_div_scalar(ctx, ft, n, c->V[0], r0, rNorm));
+  }
   std::vector<double> z{beta}, cs, ss;
   std::vector<std::vector<double>> R;
   bool solved = rNorm <= eps_tol, breakdown = false;
@@ -236,12 +259,18 @@ int gmres(cts_newton_cache* c, const std::function<int(void* out, const void* v)
   while (!(solved || k >= itmax || breakdown)) {
     ++k;
     c->stats.krylov_iters++;
+    if (fuse_red && c->cfg.jacobian_free_jvp) {
+      c->known_norm_ptr = c->V[k - 1];
+      c->known_norm = vnorm[k - 1];
+    }
     CTS_TRY(matvec(w, c->V[k - 1]));
+    c->known_norm_ptr = nullptr;
     if (precond)
       CTS_TRY((*precond)(q, w));
     else
       CTS_TRY(cts_memcpy_d2d(ctx, q, w, bytes));
     std::vector<double> col(k);
+    double Hbis_fused = 0;
     if (c->cfg.batch_gram_schmidt) {  // classical GS: one fused sweep of k dots, then one k-term update
       std::vector<const void*> Vp(c->V.begin(), c->V.begin() + k);
       CTS_TRY(cts_multi_dot(ctx, ft, n, (int)k, Vp.data(), q, col.data()));
@@ -251,14 +280,29 @@ int gmres(cts_newton_cache* c, const std::function<int(void* out, const void* v)
         for (int i = 0; i < kk; ++i) coef[i] = -col[i0 + i];
         CTS_TRY(cts_axpy_n(ctx, ft, n, q, nullptr, 1.0, q, kk, 0, coef, Vp.data() + i0, 0));
       }
+    } else if (fuse_red) {  // modified GS, each update fused with the reduction that follows it (next dot, or the norm)
+      cts_prof_scope ps(ctx, CTS_PROF_KRYLOV);
+      CTS_TRY(cts_dot(ctx, ft, n, c->V[0], q, &col[0]));
+      for (size_t i = 0; i < k; ++i) {
+        double red = 0;
+        CTS_TRY(cts_axpby_dot(ctx, ft, n, -col[i], c->V[i], 1.0, q, i + 1 < k ? c->V[i + 1] : nullptr, &red));
+        if (i + 1 < k)
+          col[i + 1] = red;
+        else
+          Hbis_fused = std::sqrt(red);
+      }
     } else {  // modified GS (Krylov.jl order): k dependent dots
+      cts_prof_scope ps(ctx, CTS_PROF_KRYLOV);
       for (size_t i = 0; i < k; ++i) {
         CTS_TRY(cts_dot(ctx, ft, n, c->V[i], q, &col[i]));
         CTS_TRY(cts_axpby(ctx, ft, n, -col[i], c->V[i], 1.0, q));
       }
     }
     double Hbis = 0;
-    CTS_TRY(cts_nrm2(ctx, ft, n, q, &Hbis));
+    if (fuse_red && !c->cfg.batch_gram_schmidt)
+      Hbis = Hbis_fused;
+    else
+      CTS_TRY(cts_nrm2(ctx, ft, n, q, &Hbis));
     for (size_t i = 0; i + 1 < k; ++i) {
       double rtmp = cs[i] * col[i] + ss[i] * col[i + 1];
       col[i + 1] = ss[i] * col[i] - cs[i] * col[i + 1];
@@ -277,7 +321,12 @@ int gmres(cts_newton_cache* c, const std::function<int(void* out, const void* v)
     breakdown = Hbis <= btol;
     if (!(solved || k >= itmax || breakdown)) {
       CTS_TRY(ensure_vec(k));
-      CTS_TRY(cts_div_scalar(ctx, ft, n, c->V[k], q, Hbis));
+      vnorm.push_back(0.0);
+      cts_prof_scope ps(ctx, CTS_PROF_KRYLOV);
+      if (fuse_red && c->cfg.jacobian_free_jvp)
+        CTS_TRY(cts_div_scalar_nrm2(ctx, ft, n, c->V[k], q, Hbis, &vnorm[k]));
+      else
+        CTS_TRY(cts_div_scalar(ctx, ft, n, c->V[k], q, Hbis));
       z.push_back(zeta);
     }
   }
@@ -297,6 +346,11 @@ int solve_krylov(cts_newton_cache* c, void* dx, const void* x, const ResidualFn&
                  const PrepareFn* prepare) {
   cts_ctx* ctx = c->ctx;
   const bool jfree = c->cfg.jacobian_free_jvp != 0;
+  c->xstat_valid = false;  // x is fixed for the whole GMRES solve; with the reference pass structure recompute per JVP
+  struct XstatScope {
+    cts_newton_cache* c;
+    ~XstatScope() { c->xstat_valid = false; }
+  } xstat_scope{c};
   std::function<int(void*, const void*)> matvec = [&](void* out, const void* v) -> int {
     if (!jfree) {
       if (!c->jac_mul || !c->W) return cts_fail(ctx, CTS_EINVAL, "GMRES without JVP needs mul!(y, W, x)");
@@ -1280,6 +1334,7 @@ int cts_imex_cache_stats(cts_imex_cache* c, cts_solver_stats* out) {
 int cts_imex_cache_set_fusion(cts_imex_cache* c, int enabled) {
   if (!c) return CTS_EINVAL;
   c->fusion = enabled != 0;
+  if (c->nm) c->nm->fuse_reductions = c->fusion;
   return CTS_OK;
 }
 

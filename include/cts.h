@@ -152,6 +152,12 @@ int cts_nrm2(cts_ctx* ctx, cts_dtype ft, size_t n, const void* x, double* host_o
 int cts_sum1pabs(cts_ctx* ctx, cts_dtype ft, size_t n, const void* x, double* host_out);
 /* k dots against one vector in one pass + one all-reduce: out[j] = <V[j], q> (classical Gram-Schmidt sweep) */
 int cts_multi_dot(cts_ctx* ctx, cts_dtype ft, size_t n, int k, const void* const* V /*host array*/, const void* q, double* host_out);
+/* Producer + reduction in one pass, bit-identical to the two separate calls (same reduction tree):
+ *   cts_axpby_dot:       y = a*x + b*y, then *host_out = z ? dot(y, z) : sum(y_i^2)     (MGS update + next dot / norm)
+ *   cts_div_scalar_nrm2: y = x/denom,   then *host_norm = norm(y)                        (basis vector + its norm for jvp!) */
+int cts_axpby_dot(cts_ctx* ctx, cts_dtype ft, size_t n, double a, const void* x, double b, void* y, const void* z_or_null,
+                  double* host_out);
+int cts_div_scalar_nrm2(cts_ctx* ctx, cts_dtype ft, size_t n, void* y, const void* x, double denom, double* host_norm);
 /* restrict reductions to the owned (non-ghost) element range [offset, offset+count) of each vector */
 int cts_set_reduction_window(cts_ctx* ctx, size_t offset, size_t count);
 

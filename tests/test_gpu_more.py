@@ -372,3 +372,36 @@ def test_full_size_power_of_two_linearity(cts):
         del integ, op
     assert bool(torch.equal(outs[0].tensor * 4.0, outs[1].tensor))
     assert bool(torch.isfinite(outs[1].tensor).all())
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,window", [(100003, None), (1 << 16, None), (40000, (4096, 30000))])
+def test_fused_producer_reductions_equal_separate_calls(cts, dtype, n, window):
+    # cts_axpby_dot / cts_div_scalar_nrm2 (GMRES: MGS update + next dot, basis vector + its norm) against the two-call form
+    import ctypes as C
+    ctx = cts.Context.default()
+    lib = ctx.lib
+    ft = 1 if dtype == np.float64 else 0
+    x, y0, z = (dev(cts, (M.fill_hash(n, s) - 0.5).astype(dtype)) for s in (1, 2, 3))
+    if window:
+        ctx.set_reduction_window(*window)
+    try:
+        for with_z in (True, False):
+            ya, yb = y0.copy(), y0.copy()
+            ctx.check(lib.cts_axpby(ctx.handle, ft, n, -0.37, x.ptr, 1.0, ya.ptr))
+            ref = ya.dot(z) if with_z else ya.norm() ** 2
+            out = C.c_double()
+            ctx.check(lib.cts_axpby_dot(ctx.handle, ft, n, -0.37, x.ptr, 1.0, yb.ptr, z.ptr if with_z else None, C.byref(out)))
+            np.testing.assert_array_equal(yb.to_host(), ya.to_host())
+            if with_z:
+                assert out.value == ref
+            else:
+                assert np.sqrt(out.value) == ya.norm()
+        ya, yb = cts.B200Vector.zeros(n, dtype), cts.B200Vector.zeros(n, dtype)
+        ctx.check(lib.cts_div_scalar(ctx.handle, ft, n, ya.ptr, x.ptr, 1.7))
+        nr = C.c_double()
+        ctx.check(lib.cts_div_scalar_nrm2(ctx.handle, ft, n, yb.ptr, x.ptr, 1.7, C.byref(nr)))
+        np.testing.assert_array_equal(yb.to_host(), ya.to_host())
+        assert nr.value == ya.norm()
+    finally:
+        ctx.set_reduction_window(0, 0)
