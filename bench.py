@@ -391,10 +391,11 @@ def run_ours(args):
 
 
 def step_bytes_per_dof(stored_w):
-    """Whole fused ARS343 step (SURVEY §8d 'fused minimum'): 3 fused stages + final update (7 reads, 1 write)
-    + 4 T_exp! (1 read, 1 write).  Stored W: 344 B/DOF (Wfact is folded into the first implicit stage, which writes
-    W instead of reading it); matrix-free: 272 B/DOF."""
-    return sum(stage_bytes(stored_w)) + 8 * 8 + 4 * 2 * 8
+    """Whole fused ARS343 step: 3 fused stages + 3 T_exp! (1 read, 1 write) + the final update with the 4th T_exp! folded
+    in (reads u, U_4, 2 T_exp, 3 T_imp; writes u: 8w).  Stored W: 328 B/DOF (Wfact is folded into the first implicit
+    stage, which writes W instead of reading it; SURVEY §8d's "fused minimum" of 344 B/DOF still stores and re-reads
+    T_exp[4]); matrix-free: 256 B/DOF."""
+    return sum(stage_bytes(stored_w)) + 8 * 8 + 3 * 2 * 8
 
 
 def timed(stream, fn, reps, warm=2):
@@ -458,6 +459,18 @@ def run_extras(cts, ctx, stream, op, u):
         out[f"C4_ssp333_jfnk_{name}"] = run_c4(cts, ctx, stream, dtype)
         torch.cuda.empty_cache()
     out["C3_ars343_column_f32"] = run_c3_f32(cts, ctx, stream)
+    torch.cuda.empty_cache()
+    # --- the default workload with W regenerated in the stage kernel from K_col instead of stored (bit-identical results,
+    # 3w B/DOF less per implicit stage; `--matrix-free` runs the whole bench line this way)
+    part = cts.SlabPartition(NY, 1, 0)
+    op_mf, integ_mf, u_mf = build_problem(cts, ctx, part, True)
+    op_mf.dss(u_mf, None, 0.0)
+    ms = timed(stream, lambda: cts.step_(integ_mf), 5, warm=3)
+    model = step_bytes_per_dof(False)
+    out["C3_ars343_column_matrix_free"] = {"ms_per_step": ms, "dof_stage_per_s": op_mf.ndof_owned * STAGES / (ms * 1e-3),
+                                           "bytes_per_dof_step": model, "GBs": model * op_mf.ndof / (ms * 1e-3) / 1e9,
+                                           "frac": model * op_mf.ndof / (ms * 1e-3) / 1e9 / peak}
+    del integ_mf, op_mf, u_mf
     torch.cuda.empty_cache()
     return out
 

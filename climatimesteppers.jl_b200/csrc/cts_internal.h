@@ -125,6 +125,20 @@ struct cts_fused_stage_args {
 };
 int cts_column_fused_stage(cts_op_column* op, const cts_fused_stage_args* a);
 bool cts_column_fusable(const cts_op_column* op);
+// final update of an ARK step fused with the last stage's T_exp! (column operator recognised as T_exp_T_lim!)
+struct cts_final_update_args {
+  void* u;                 // in/out: state (base of the update)
+  const void* U_last;      // last stage value, already dss!-ed
+  double t_exp_last;       // t + dt*c_exp[s]
+  double coef_last;        // dt*b_exp[s]
+  int n_grp1, n_grp2;      // other explicit terms (j < s), implicit terms
+  double coef[CTS_MAX_TERMS];
+  const void* terms[CTS_MAX_TERMS];
+  int compute_native;
+};
+bool cts_column_final_fusable(const cts_op_column* op);
+bool cts_op_column_has_halo(const cts_op_column* op);
+int cts_column_fused_final_update(cts_op_column* op, const cts_final_update_args* a);
 // Newton residual (dx == NULL) or forward-difference JVP of the stage equation for the column operator in one pass
 bool cts_column_residual_fusable(const cts_op_column* op);
 int cts_column_fused_residual(cts_op_column* op, void* out, const void* x, const void* dx, double eps, const void* U0,

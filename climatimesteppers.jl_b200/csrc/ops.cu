@@ -19,6 +19,8 @@ using cts_ew::axpy_combine;
 using cts_ew::Vec;
 using cts_ew::vec_pack;
 using cts_ew::vec_unpack;
+using cts_ew::op_add;
+using cts_ew::op_mul;
 
 // =============================================================================================
 // 1-D periodic upwind advection (config C2)
@@ -433,6 +435,121 @@ __global__ void __launch_bounds__(256) column_texp_march_kernel(T* __restrict__ 
     const V vw = *reinterpret_cast<const V*>(crow + rw);
     const V ve = *reinterpret_cast<const V*>(crow + re);
     emit(jr, vw, ve, vn);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Final update of an IMEX-ARK step fused with the LAST stage's explicit tendency (imex_ark.jl:79-101 + :256-258): the last
+// T_exp! output is only ever read by the final update (a_exp[:, s] == 0), so instead of writing it and reading it back
+//   T_exp[s] = S*g(t) + nu*lap(U_s)                                   (column_texp_march_kernel)
+//   u        = (u + (Σ_{j<s} c_j T_exp[j] + c_s T_exp[s])) + Σ c'_j T_imp[j]      (axpy_n, fused_increment.jl:220-236)
+// run as one marching pass: 2w B/DOF less.  The tendency is rounded to T exactly as the stored array would be and the
+// left folds keep their order, so u is bit-identical.  Owned rows only (the halo dss! that follows rewrites the ghosts).
+template <int NT>
+struct FinalArgs {
+  AxpyArgs<NT> ax;     // base = out = u; terms = the OTHER tendencies (group 1: explicit j < s, then group 2: implicit)
+  const void* U;       // last stage value (stencil source)
+  const void* S;
+  double coef_last;    // dt*b_exp[s]
+  double g, nu;
+  unsigned nlev, nx, row_elems;
+  size_t ny_local;
+  int halo, has_src;
+};
+
+template <typename T, typename C, int NT, int ROWS>
+__global__ void __launch_bounds__(256) column_final_update_kernel(const FinalArgs<NT> a) {
+  using V = typename Vec<T>::type;
+  constexpr int VN = Vec<T>::N;
+  constexpr int NTS = NT > 0 ? NT : 1;
+  const unsigned r = (blockIdx.x * 256u + threadIdx.x) * VN;
+  if (r >= a.row_elems) return;
+  const T* __restrict__ U = reinterpret_cast<const T*>(a.U);
+  const size_t rows = a.ny_local + 2 * (size_t)a.halo;
+  const unsigned ix = r / a.nlev, lev = r - ix * a.nlev;
+  const unsigned wrap = (a.nx - 1) * a.nlev;
+  const unsigned rw = ix == 0 ? r + wrap : r - a.nlev;
+  const unsigned re = ix == a.nx - 1 ? r - wrap : r + a.nlev;
+  const T g = (T)a.g, nu = (T)a.nu;
+  T src[VN];
+#pragma unroll
+  for (int e = 0; e < VN; ++e) src[e] = T(0);
+  if (a.has_src) {
+    T t[VN];
+    vec_unpack<T>(*reinterpret_cast<const V*>(reinterpret_cast<const T*>(a.S) + lev), t);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) src[e] = rmul(t[e], g);
+  }
+  const size_t jr0 = (size_t)blockIdx.y * ROWS;
+  const size_t jr1 = jr0 + ROWS < a.ny_local ? jr0 + ROWS : a.ny_local;
+  auto local_row = [&](long long jr) -> size_t {
+    if (a.halo) return (size_t)(jr + 1);
+    return jr < 0 ? rows - 1 : ((size_t)jr == rows ? 0 : (size_t)jr);
+  };
+  V vs = *reinterpret_cast<const V*>(U + local_row((long long)jr0 - 1) * (size_t)a.row_elems + r);
+  V vc = *reinterpret_cast<const V*>(U + local_row((long long)jr0) * (size_t)a.row_elems + r);
+  constexpr int B = NT <= 2 ? 4 : 2;  // rows per batch: (3 + 1 + NT)*B independent 16-byte loads in flight per thread
+  auto row_update = [&](size_t jr, const V& vw, const V& ve, const V& vn, const V& vb, const V (&vt)[NTS]) {
+    T c[VN], w[VN], e_[VN], s_[VN], n_[VN], eb[VN], eo[VN], et[NTS][VN];
+    vec_unpack<T>(vc, c);
+    vec_unpack<T>(vw, w);
+    vec_unpack<T>(ve, e_);
+    vec_unpack<T>(vs, s_);
+    vec_unpack<T>(vn, n_);
+    vec_unpack<T>(vb, eb);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) vec_unpack<T>(vt[t], et[t]);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      const T lap = rsub(radd(radd(radd(w[e], e_[e]), s_[e]), n_[e]), rmul(T(4), c[e]));
+      const T te = radd(src[e], rmul(nu, lap));  // T_exp[s], rounded to T as the stored array would be
+      C rr = (C)eb[e];
+      C g1 = 0, g2 = 0;
+#pragma unroll
+      for (int k = 0; k < NT; ++k) {
+        const C p = op_mul((C)a.ax.coef[k], (C)et[k][e]);
+        if (k < a.ax.n1)
+          g1 = (k == 0) ? p : op_add(g1, p);
+        else
+          g2 = (k == a.ax.n1) ? p : op_add(g2, p);
+      }
+      const C pl = op_mul((C)a.coef_last, (C)te);
+      g1 = a.ax.n1 > 0 ? op_add(g1, pl) : pl;
+      rr = op_add(rr, g1);
+      if (a.ax.n1 < NT) rr = op_add(rr, g2);
+      eo[e] = (T)rr;
+    }
+    const size_t gi = local_row((long long)jr) * (size_t)a.row_elems + r;
+    *reinterpret_cast<V*>(reinterpret_cast<T*>(a.ax.out) + gi) = vec_pack<T>(eo);
+    vs = vc;
+    vc = vn;
+  };
+  size_t jr = jr0;
+  for (; jr + B <= jr1; jr += B) {
+    V vn[B], vw[B], ve[B], vb[B], vt[B][NTS];
+#pragma unroll
+    for (int k = 0; k < B; ++k) {
+      const size_t rowc = local_row((long long)(jr + k)) * (size_t)a.row_elems;
+      vn[k] = *reinterpret_cast<const V*>(U + local_row((long long)(jr + k) + 1) * (size_t)a.row_elems + r);
+      vw[k] = *reinterpret_cast<const V*>(U + rowc + rw);
+      ve[k] = *reinterpret_cast<const V*>(U + rowc + re);
+      vb[k] = *reinterpret_cast<const V*>(reinterpret_cast<const T*>(a.ax.base) + rowc + r);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) vt[k][t] = *reinterpret_cast<const V*>(reinterpret_cast<const T*>(a.ax.terms[t]) + rowc + r);
+    }
+#pragma unroll
+    for (int k = 0; k < B; ++k) row_update(jr + k, vw[k], ve[k], vn[k], vb[k], vt[k]);
+  }
+  for (; jr < jr1; ++jr) {
+    const size_t rowc = local_row((long long)jr) * (size_t)a.row_elems;
+    V vt[NTS];
+    const V vn = *reinterpret_cast<const V*>(U + local_row((long long)jr + 1) * (size_t)a.row_elems + r);
+    const V vw = *reinterpret_cast<const V*>(U + rowc + rw);
+    const V ve = *reinterpret_cast<const V*>(U + rowc + re);
+    const V vb = *reinterpret_cast<const V*>(reinterpret_cast<const T*>(a.ax.base) + rowc + r);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) vt[t] = *reinterpret_cast<const V*>(reinterpret_cast<const T*>(a.ax.terms[t]) + rowc + r);
+    row_update(jr, vw, ve, vn, vb, vt);
   }
 }
 
@@ -939,6 +1056,69 @@ int cts_column_fused_stage(cts_op_column* op, const cts_fused_stage_args* s) {
   return dispatch_fused<float, double>(op, s);
 }
 
+template <typename T, typename C, int NT>
+int launch_final(cts_op_column* op, const cts_final_update_args* s) {
+  cts_ctx* ctx = op->ctx;
+  const cts_column_desc& d = op->d;
+  FinalArgs<NT> a{};
+  a.ax.base = s->u;
+  a.ax.out = s->u;
+  a.ax.n1 = s->n_grp1;
+  for (int k = 0; k < NT; ++k) {
+    a.ax.terms[k] = s->terms[k];
+    a.ax.coef[k] = s->coef[k];
+  }
+  a.U = s->U_last;
+  a.S = d.S_lev;
+  a.coef_last = s->coef_last;
+  a.g = 1.0 + 0.5 * sin(2.0 * M_PI * s->t_exp_last);
+  a.nu = d.nu;
+  a.nlev = (unsigned)d.nlev;
+  a.nx = (unsigned)d.nx;
+  a.row_elems = (unsigned)(d.nx * (size_t)d.nlev);
+  a.ny_local = d.ny_local;
+  a.halo = d.halo;
+  a.has_src = d.S_lev != nullptr;
+  constexpr int ROWS = 8;
+  constexpr int VN = Vec<T>::N;
+  dim3 grid((unsigned)((a.row_elems / VN + 255) / 256), (unsigned)((d.ny_local + ROWS - 1) / ROWS));
+  column_final_update_kernel<T, C, NT, ROWS><<<grid, 256, 0, ctx->stream>>>(a);
+  CTS_LAUNCH_CHECK(ctx);
+  return CTS_OK;
+}
+
+template <typename T, typename C>
+int dispatch_final(cts_op_column* op, const cts_final_update_args* s) {
+  switch (s->n_grp1 + s->n_grp2) {
+#define CASE(N) \
+  case N:       \
+    return launch_final<T, C, N>(op, s);
+    CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
+#undef CASE
+    default:
+      return CTS_EUNSUPPORTED;
+  }
+}
+
+bool cts_column_final_fusable(const cts_op_column* op) {
+  const cts_column_desc& d = op->d;
+  const int vn = op->ft == CTS_F64 ? 2 : 4;
+  const size_t row_elems = d.nx * (size_t)d.nlev;
+  return d.nu != 0.0 && (d.nlev % vn) == 0 && row_elems < (1ull << 31) && (d.ny_local + 7) / 8 <= 65535 &&
+         (!d.S_lev || cts_aligned16(d.S_lev));
+}
+
+int cts_column_fused_final_update(cts_op_column* op, const cts_final_update_args* s) {
+  if (!op || !s || !s->u || !s->U_last || s->u == s->U_last) return CTS_EINVAL;
+  if (!cts_column_final_fusable(op) || s->n_grp1 + s->n_grp2 > 10) return CTS_EUNSUPPORTED;
+  bool aligned = cts_aligned16(s->u) && cts_aligned16(s->U_last);
+  for (int k = 0; k < s->n_grp1 + s->n_grp2; ++k) aligned = aligned && cts_aligned16(s->terms[k]);
+  if (!aligned) return CTS_EUNSUPPORTED;
+  if (op->ft == CTS_F64) return dispatch_final<double, double>(op, s);
+  if (s->compute_native) return dispatch_final<float, float>(op, s);
+  return dispatch_final<float, double>(op, s);
+}
+
 bool cts_column_residual_fusable(const cts_op_column* op) {
   const int vn = op->ft == CTS_F64 ? 2 : 4;
   return op->d.nlev >= vn && (op->d.nlev % vn) == 0;
@@ -970,6 +1150,7 @@ int cts_column_fused_residual(cts_op_column* op, void* out, const void* x, const
 }
 
 bool cts_op_column_is_linear(const cts_op_column* op) { return !op->d.nonlinear; }
+bool cts_op_column_has_halo(const cts_op_column* op) { return op->d.halo != 0; }
 bool cts_op_column_matrix_free(const cts_op_column* op) { return op->matrix_free; }
 cts_ctx* cts_op_column_ctx(const cts_op_column* op) { return op->ctx; }
 cts_dtype cts_op_column_dtype(const cts_op_column* op) { return op->ft; }

@@ -893,6 +893,21 @@ int fused_implicit_stage(cts_imex_cache* c, cts_op_column* op, void* U, double c
   return CTS_OK;
 }
 
+// Can the last stage's T_exp! be folded into the final update?  (library column operator as T_exp_T_lim!, no limiter,
+// the library halo dss!, and a tableau whose last explicit tendency feeds only the final update)
+cts_op_column* final_fusable_column_op(const cts_imex_cache* c) {
+  const cts_ode_function& f = c->f;
+  const cts_imex_tableau& tab = c->tab;
+  const int s = tab.s;
+  if (!c->fusion || f.has_lim || f.T_exp_T_lim != cts_op_column_T_exp || !f.ud) return nullptr;
+  if (tab.b_exp[s - 1] == 0 || col_nonzero(tab.a_exp, s, s - 1)) return nullptr;
+  auto* op = static_cast<cts_op_column*>(f.ud);
+  if (cts_op_column_ctx(op) != c->ctx || cts_op_column_dtype(op) != c->ft || cts_op_column_ndof(op) != c->n) return nullptr;
+  if (!cts_column_final_fusable(op)) return nullptr;
+  if (f.dss ? f.dss != cts_op_column_dss : cts_op_column_has_halo(op)) return nullptr;  // ghost rows are left to dss!
+  return op;
+}
+
 // ---------------------------------------------------------------------------------------------
 // step_u!(integrator, cache::IMEXARKCache)   imex_ark.jl:69-272
 // ---------------------------------------------------------------------------------------------
@@ -903,6 +918,10 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
   const bool has_T_exp = f.T_exp_T_lim != nullptr;
   const bool has_T_imp = f.T_imp != nullptr;
   cts_op_column* fuse_op = fusable_column_op(c);
+  cts_op_column* final_op = final_fusable_column_op(c);
+  bool fold_last_texp = false;
+  const void* U_last = nullptr;
+  double t_exp_last = 0.0;
   // (a matrix-free fused stage regenerates W in the kernel: the stored copy is never read)
   if (!(fuse_op && cts_op_column_matrix_free(fuse_op))) CTS_TRY(maybe_update_jacobian(c, u, t, dt, fuse_op != nullptr));
 
@@ -970,8 +989,14 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
 
     // evaluate_stage_tendencies!  :252-272
     if (has_exp_terms && f.T_exp_T_lim) {
-      cts_prof_scope ps(c->ctx, CTS_PROF_T_EXP);
-      HOOK(c->ctx, f.T_exp_T_lim(f.ud, c->T_exp[i], c->T_lim[i], U, t_exp));
+      if (i == s - 1 && final_op && U != u) {
+        fold_last_texp = true;  // evaluated inside the final update kernel (its only reader)
+        U_last = U;
+        t_exp_last = t_exp;
+      } else {
+        cts_prof_scope ps(c->ctx, CTS_PROF_T_EXP);
+        HOOK(c->ctx, f.T_exp_T_lim(f.ud, c->T_exp[i], c->T_lim[i], U, t_exp));
+      }
     }
     if (has_imp_terms && has_T_imp && !stage_done) {
       if (dtg == 0) {
@@ -994,6 +1019,39 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
     CTS_TRY(assign_with_increments(c, c->temp, nullptr, 1.0, u, inc_lim, Increment{}));
     if (f.lim) HOOK(c->ctx, f.lim(f.ud, c->temp, t_final, u));
     CTS_TRY(assign_with_increments(c, u, nullptr, 1.0, c->temp, inc_exp, inc_imp, CTS_PROF_FINAL_UPDATE));
+  } else if (fold_last_texp) {
+    cts_final_update_args a{};
+    a.u = u;
+    a.U_last = U_last;
+    a.t_exp_last = t_exp_last;
+    a.coef_last = coef_of(c, dt, tab.b_exp[s - 1]);
+    Increment others = raw_increment(c, dt, tab.b_exp, s - 1, c->T_exp);
+    a.n_grp1 = others.n;
+    a.n_grp2 = inc_imp.n;
+    int k = 0;
+    for (int j = 0; j < others.n; ++j, ++k) {
+      a.coef[k] = others.coef[j];
+      a.terms[k] = others.term[j];
+    }
+    for (int j = 0; j < inc_imp.n; ++j, ++k) {
+      a.coef[k] = inc_imp.coef[j];
+      a.terms[k] = inc_imp.term[j];
+    }
+    a.compute_native = native_flag(c);
+    int r;
+    {
+      cts_prof_scope ps(c->ctx, CTS_PROF_FINAL_UPDATE);
+      r = cts_column_fused_final_update(final_op, &a);
+    }
+    if (r == CTS_EUNSUPPORTED) {  // alignment / operand count: the two-pass form
+      {
+        cts_prof_scope ps(c->ctx, CTS_PROF_T_EXP);
+        HOOK(c->ctx, f.T_exp_T_lim(f.ud, c->T_exp[s - 1], c->T_lim[s - 1], const_cast<void*>(U_last), t_exp_last));
+      }
+      CTS_TRY(assign_with_increments(c, u, nullptr, 1.0, u, inc_exp, inc_imp, CTS_PROF_FINAL_UPDATE));
+    } else {
+      CTS_TRY(r);
+    }
   } else {
     CTS_TRY(assign_with_increments(c, u, nullptr, 1.0, u, inc_exp, inc_imp, CTS_PROF_FINAL_UPDATE));
   }

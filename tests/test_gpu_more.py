@@ -217,7 +217,7 @@ def test_benchmark_step_table(cts):
         cts.step_(integ)
         prof = ctx.prof_read()
         if fusion:
-            assert prof["fused_stage"][1] == 3 and prof["T_exp"][1] == 4 and prof["final_update"][1] == 1 and prof["dss"][1] == 4
+            assert prof["fused_stage"][1] == 3 and prof["T_exp"][1] == 3 and prof["final_update"][1] == 1 and prof["dss"][1] == 4  # the 4th T_exp! runs inside the final update
         else:
             # reference call counts for ARS343 with default hooks: 3 implicit stages x (T_imp!, Wfact, ldiv!), 10 dss!
             assert prof["T_imp"][1] == 3 and prof["Wfact"][1] == 3 and prof["ldiv"][1] == 3 and prof["dss"][1] == 10
