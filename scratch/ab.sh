@@ -3,5 +3,7 @@ run() {
   python -c "
 import json; d=json.load(open('/tmp/b.json')); print('$1 $2', round(d['value']/1e9,2), 'G DOF-stage/s', round(d['ms_per_step'],3), 'ms; fused', round(d['kernels']['fused_stage']['ms_per_step'],3), 'roof', round(d['roofline']['frac'],3))"
 }
-for pf in 0 148 740 1480 2960 5920; do CTS_FUSED_PF=$pf run pf$pf ""; done
-for pf in 0 740 2960; do CTS_FUSED_PF=$pf run pf$pf "--matrix-free"; done
+for mf in "" "--matrix-free"; do
+  run default "$mf"
+  for v in $(ls scratch/variants | sed 's/lib_//; s/.so//'); do CTS_LIB_PATH=$PWD/scratch/variants/lib_$v.so run $v "$mf"; done
+done
