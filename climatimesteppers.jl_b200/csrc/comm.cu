@@ -121,21 +121,7 @@ int cts_comm_rank(cts_ctx* ctx, int* rank, int* nranks) {
 int cts_halo_exchange(cts_ctx* ctx, cts_dtype ft, size_t count, const void* send_lo, const void* send_hi, void* recv_lo,
                       void* recv_hi) {
   CTS_CHECK_CTX(ctx);
-  if (!ctx->nccl_comm) return cts_fail(ctx, CTS_EINVAL, "cts_halo_exchange: no communicator attached");
-  NcclApi* api = nccl_api();
-  ncclComm_t comm = static_cast<ncclComm_t>(ctx->nccl_comm);
-  const ncclDataType_t dt = ft == CTS_F64 ? ncclDouble : ncclFloat;
-  const int lo = (ctx->rank - 1 + ctx->nranks) % ctx->nranks, hi = (ctx->rank + 1) % ctx->nranks;
-  // With 2 ranks lo == hi and NCCL matches the two messages of a pair in issue order: the peer's
-  // first send (its first row) must land in my recv_hi, its second (its last row) in my recv_lo.
-  CTS_NCCL(ctx, api, api->GroupStart());
-  CTS_NCCL(ctx, api, api->Send(send_lo, count, dt, lo, comm, ctx->stream));
-  CTS_NCCL(ctx, api, api->Send(send_hi, count, dt, hi, comm, ctx->stream));
-  CTS_NCCL(ctx, api, api->Recv(recv_hi, count, dt, hi, comm, ctx->stream));
-  CTS_NCCL(ctx, api, api->Recv(recv_lo, count, dt, lo, comm, ctx->stream));
-  CTS_NCCL(ctx, api, api->GroupEnd());
-  ctx->launches++;
-  return CTS_OK;
+  return cts_halo_exchange_on(ctx, ctx->stream, ft, count, send_lo, send_hi, recv_lo, recv_hi);
 }
 
 int cts_allreduce_sum_f64(cts_ctx* ctx, double* dev_buf, size_t count) {
@@ -162,3 +148,22 @@ int cts_allreduce_max_f64_host(cts_ctx* ctx, double* host_val) {
 }
 
 }  // extern "C"
+
+int cts_halo_exchange_on(cts_ctx* ctx, cudaStream_t stream, cts_dtype ft, size_t count, const void* send_lo,
+                         const void* send_hi, void* recv_lo, void* recv_hi) {
+  if (!ctx->nccl_comm) return cts_fail(ctx, CTS_EINVAL, "cts_halo_exchange: no communicator attached");
+  NcclApi* api = nccl_api();
+  ncclComm_t comm = static_cast<ncclComm_t>(ctx->nccl_comm);
+  const ncclDataType_t dt = ft == CTS_F64 ? ncclDouble : ncclFloat;
+  const int lo = (ctx->rank - 1 + ctx->nranks) % ctx->nranks, hi = (ctx->rank + 1) % ctx->nranks;
+  // With 2 ranks lo == hi and NCCL matches the two messages of a pair in issue order: the peer's
+  // first send (its first row) must land in my recv_hi, its second (its last row) in my recv_lo.
+  CTS_NCCL(ctx, api, api->GroupStart());
+  CTS_NCCL(ctx, api, api->Send(send_lo, count, dt, lo, comm, stream));
+  CTS_NCCL(ctx, api, api->Send(send_hi, count, dt, hi, comm, stream));
+  CTS_NCCL(ctx, api, api->Recv(recv_hi, count, dt, hi, comm, stream));
+  CTS_NCCL(ctx, api, api->Recv(recv_lo, count, dt, lo, comm, stream));
+  CTS_NCCL(ctx, api, api->GroupEnd());
+  ctx->launches++;
+  return CTS_OK;
+}

@@ -29,6 +29,8 @@ struct cts_ctx {
   // communicator (comm.cpp)
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
+  cudaStream_t comm_stream = nullptr;          // halo exchanges that overlap compute run here (created on first use)
+  cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
   // per-kernel timing (cts_prof_*)
   bool prof_on = false;
   struct ProfRec {
@@ -138,6 +140,12 @@ struct cts_final_update_args {
 };
 bool cts_column_final_fusable(const cts_op_column* op);
 bool cts_op_column_has_halo(const cts_op_column* op);
+// dss!(U) followed by T_exp!(du, U): the halo exchange runs on the communication stream while the rows that do not touch
+// a ghost row are evaluated; the boundary strips follow once the ghosts have arrived.  Same results as the two hooks.
+bool cts_column_overlap_ok(const cts_op_column* op);
+int cts_column_dss_T_exp_overlapped(cts_op_column* op, void* du_exp, void* U, double t_dss, double t_exp);
+int cts_halo_exchange_on(cts_ctx* ctx, cudaStream_t stream, cts_dtype ft, size_t count, const void* send_lo,
+                         const void* send_hi, void* recv_lo, void* recv_hi);
 int cts_column_fused_final_update(cts_op_column* op, const cts_final_update_args* a);
 // Newton residual (dx == NULL) or forward-difference JVP of the stage equation for the column operator in one pass
 bool cts_column_residual_fusable(const cts_op_column* op);

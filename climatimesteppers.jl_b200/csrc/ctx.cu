@@ -61,6 +61,12 @@ int cts_ctx_destroy(cts_ctx* ctx) {
   if (ctx->d_result) cudaFree(ctx->d_result);
   if (ctx->d_counter) cudaFree(ctx->d_counter);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
+  if (ctx->comm_stream) {
+    cudaStreamSynchronize(ctx->comm_stream);
+    cudaStreamDestroy(ctx->comm_stream);
+  }
+  if (ctx->ev_compute) cudaEventDestroy(ctx->ev_compute);
+  if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return CTS_OK;

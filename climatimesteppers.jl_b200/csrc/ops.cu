@@ -367,7 +367,7 @@ template <typename T, int VN, int ROWS>
 __global__ void __launch_bounds__(256) column_texp_march_kernel(T* __restrict__ out, const T* __restrict__ u,
                                                                 const T* __restrict__ S, T g, T nu, unsigned nlev,
                                                                 unsigned nx, unsigned row_elems, size_t ny_local,
-                                                                int halo, int has_src) {
+                                                                int halo, int has_src, size_t jr_begin, size_t jr_end) {
   using V = typename Vec<T>::type;
   const unsigned r = (blockIdx.x * 256u + threadIdx.x) * VN;
   if (r >= row_elems) return;
@@ -385,8 +385,8 @@ __global__ void __launch_bounds__(256) column_texp_march_kernel(T* __restrict__ 
 #pragma unroll
     for (int e = 0; e < VN; ++e) src[e] = rmul(t[e], g);
   }
-  const size_t jr0 = (size_t)blockIdx.y * ROWS;
-  const size_t jr1 = jr0 + ROWS < ny_local ? jr0 + ROWS : ny_local;
+  const size_t jr0 = jr_begin + (size_t)blockIdx.y * ROWS;  // owned rows [jr_begin, jr_end) of this launch
+  const size_t jr1 = jr0 + ROWS < jr_end ? jr0 + ROWS : jr_end;
   // row of the local array that holds owned row jr (jr = -1 and jr = ny_local are the neighbours across the slab
   // edge: ghost rows with a halo, the periodic wrap without)
   auto row_of = [&](long long jr) -> const T* {
@@ -1285,29 +1285,35 @@ int cts_op_column_jac_mul(void* vop, void* y, const void* vW, const void* x) {
   return cts_tridiag_matvec(op->ctx, op->ft, static_cast<const cts_tridiag*>(vW), x, y);
 }
 
-int cts_op_column_T_exp(void* vop, void* du_exp, void* du_lim, const void* u, double t) {
-  auto* op = static_cast<cts_op_column*>(vop);
+// T_exp! on the owned rows [jr_begin, jr_end)
+static int column_T_exp_rows(cts_op_column* op, void* du_exp, const void* u, double t, size_t jr_begin, size_t jr_end) {
   if (!op || !du_exp || !u || du_exp == u) return CTS_EINVAL;
+  if (jr_begin >= jr_end) return CTS_OK;
   cts_ctx* ctx = op->ctx;
   const cts_column_desc& d = op->d;
-  size_t n_owned = d.ny_local * d.nx * (size_t)d.nlev;
-  size_t blocks = (n_owned + 255) / 256;
   // time factor of the source, evaluated once on the host in Float64 (docs/src/tutorials/imex_diffusion.md:65-69)
   double g = 1.0 + 0.5 * sin(2.0 * M_PI * t);
   int has_src = d.S_lev != nullptr;
   const int vn = op->ft == CTS_F64 ? 2 : 4;
   const bool vec = (d.nlev % vn) == 0 && cts_aligned16(du_exp) && cts_aligned16(u) && (!has_src || cts_aligned16(d.S_lev));
   const size_t row_elems = d.nx * (size_t)d.nlev;
-  if (vec && row_elems < (1ull << 31) && d.nu != 0.0 && (d.ny_local + 7) / 8 <= 65535) {
+  const size_t nrows = jr_end - jr_begin;
+  if (vec && row_elems < (1ull << 31) && d.nu != 0.0 && (nrows + 7) / 8 <= 65535) {
     // strips of 8 rows (25 % of the rows are fetched twice, from L2): measured best of 8/16/32/64/128 on B200
     constexpr int ROWS = 8;
-    dim3 grid((unsigned)((row_elems / vn + 255) / 256), (unsigned)((d.ny_local + ROWS - 1) / ROWS));
+    dim3 grid((unsigned)((row_elems / vn + 255) / 256), (unsigned)((nrows + ROWS - 1) / ROWS));
     if (op->ft == CTS_F64)
-      column_texp_march_kernel<double, 2, ROWS><<<grid, 256, 0, ctx->stream>>>((double*)du_exp, (const double*)u, (const double*)d.S_lev, g, d.nu, (unsigned)d.nlev, (unsigned)d.nx, (unsigned)row_elems, d.ny_local, d.halo, has_src);
+      column_texp_march_kernel<double, 2, ROWS><<<grid, 256, 0, ctx->stream>>>((double*)du_exp, (const double*)u, (const double*)d.S_lev, g, d.nu, (unsigned)d.nlev, (unsigned)d.nx, (unsigned)row_elems, d.ny_local, d.halo, has_src, jr_begin, jr_end);
     else
-      column_texp_march_kernel<float, 4, ROWS><<<grid, 256, 0, ctx->stream>>>((float*)du_exp, (const float*)u, (const float*)d.S_lev, (float)g, (float)d.nu, (unsigned)d.nlev, (unsigned)d.nx, (unsigned)row_elems, d.ny_local, d.halo, has_src);
-  } else if (vec) {
-    size_t blocks = (n_owned / vn + 255) / 256;
+      column_texp_march_kernel<float, 4, ROWS><<<grid, 256, 0, ctx->stream>>>((float*)du_exp, (const float*)u, (const float*)d.S_lev, (float)g, (float)d.nu, (unsigned)d.nlev, (unsigned)d.nx, (unsigned)row_elems, d.ny_local, d.halo, has_src, jr_begin, jr_end);
+    CTS_LAUNCH_CHECK(ctx);
+    return CTS_OK;
+  }
+  if (jr_begin != 0 || jr_end != d.ny_local) return CTS_EUNSUPPORTED;  // the flat kernels take all owned rows
+  size_t n_owned = d.ny_local * d.nx * (size_t)d.nlev;
+  size_t blocks = (n_owned + 255) / 256;
+  if (vec) {
+    blocks = (n_owned / vn + 255) / 256;
     if (op->ft == CTS_F64)
       column_texp_kernel<double, 2><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)du_exp, (const double*)u, (const double*)d.S_lev, g, d.nu, d.nlev, d.nx, d.ny_local, d.halo, has_src);
     else
@@ -1320,6 +1326,12 @@ int cts_op_column_T_exp(void* vop, void* du_exp, void* du_lim, const void* u, do
   }
   CTS_LAUNCH_CHECK(ctx);
   return CTS_OK;
+}
+
+int cts_op_column_T_exp(void* vop, void* du_exp, void* du_lim, const void* u, double t) {
+  auto* op = static_cast<cts_op_column*>(vop);
+  if (!op) return CTS_EINVAL;
+  return column_T_exp_rows(op, du_exp, u, t, 0, op->d.ny_local);
 }
 
 int cts_op_column_dss(void* vop, void* u, double t) {
@@ -1343,3 +1355,44 @@ int cts_op_column_dss(void* vop, void* u, double t) {
 }
 
 }  // extern "C"
+
+bool cts_column_overlap_ok(const cts_op_column* op) {
+  const cts_column_desc& d = op->d;
+  const int vn = op->ft == CTS_F64 ? 2 : 4;
+  return op->ctx->nranks > 1 && d.halo == 1 && d.nu != 0.0 && (d.nlev % vn) == 0 && d.ny_local >= 32 &&
+         d.nx * (size_t)d.nlev < (1ull << 31);
+}
+
+int cts_column_dss_T_exp_overlapped(cts_op_column* op, void* du_exp, void* U, double t_dss, double t_exp) {
+  if (!op || !du_exp || !U) return CTS_EINVAL;
+  if (!cts_column_overlap_ok(op)) {
+    int r = cts_op_column_dss(op, U, t_dss);
+    return r != CTS_OK ? r : cts_op_column_T_exp(op, du_exp, nullptr, U, t_exp);
+  }
+  cts_ctx* ctx = op->ctx;
+  const cts_column_desc& d = op->d;
+  if (!ctx->comm_stream) {
+    CTS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    CTS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
+    CTS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
+  }
+  const size_t row = d.nx * (size_t)d.nlev;
+  const size_t es = cts_sizeof(op->ft);
+  char* b = static_cast<char*>(U);
+  // the stage value is complete on the compute stream -> the exchange may start
+  CTS_CUDA(ctx, cudaEventRecord(ctx->ev_compute, ctx->stream));
+  CTS_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_compute, 0));
+  CTS_TRY(cts_halo_exchange_on(ctx, ctx->comm_stream, op->ft, row, b + row * es, b + d.ny_local * row * es, b,
+                               b + (d.ny_local + 1) * row * es));
+  CTS_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+  // rows whose 5-point stencil stays inside the owned rows: no ghost row is read, nothing the exchange writes is touched
+  constexpr size_t kEdge = 8;
+  int r = column_T_exp_rows(op, du_exp, U, t_exp, kEdge, d.ny_local - kEdge);
+  // (if the marching kernel is not applicable the whole evaluation waits for the ghosts)
+  CTS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+  if (r == CTS_EUNSUPPORTED) return cts_op_column_T_exp(op, du_exp, nullptr, U, t_exp);
+  if (r != CTS_OK) return r;
+  CTS_TRY(column_T_exp_rows(op, du_exp, U, t_exp, 0, kEdge));
+  CTS_TRY(column_T_exp_rows(op, du_exp, U, t_exp, d.ny_local - kEdge, d.ny_local));
+  return CTS_OK;
+}

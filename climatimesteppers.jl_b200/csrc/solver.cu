@@ -938,12 +938,16 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
     Increment inc_exp = has_T_exp ? raw_increment(c, dt, &tab.a_exp[i * s], i, c->T_exp) : Increment{};
     Increment inc_imp = has_T_imp ? raw_increment(c, dt, &tab.a_imp[i * s], i, c->T_imp) : Increment{};
 
-    bool stage_done = false;
+    bool stage_done = false, overlap_dss = false;
     if (fuse_op && !no_imp) {
       // K1 + Newton + K6 in one kernel; the pre-Newton dss! calls only rewrite ghost rows that the column
       // solve never reads, so one post-Newton dss! leaves every owned DOF bit-identical.
       CTS_TRY(fused_implicit_stage(c, fuse_op, U, 1.0, u, inc_exp, inc_imp, dtg, t_imp, has_imp_terms ? c->T_imp[i] : nullptr));
-      CTS_TRY(call_dss(c, U, t_imp));
+      // multi-GPU: when the explicit tendency of this stage follows, its interior rows are evaluated while the halo
+      // exchange of dss!(U) is in flight (cts_column_dss_T_exp_overlapped); otherwise dss! runs here
+      overlap_dss = has_exp_terms && f.T_exp_T_lim == cts_op_column_T_exp && f.dss == cts_op_column_dss &&
+                    cts_column_overlap_ok(fuse_op) && !(i == s - 1 && final_op);
+      if (!overlap_dss) CTS_TRY(call_dss(c, U, t_imp));
       stage_done = true;
     } else if (fuse_op && no_imp && i == 0 && inc_exp.n == 0 && inc_imp.n == 0) {
       U = u;  // `@. U = u` followed only by tendency evaluations: alias instead of copying
@@ -993,6 +997,10 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
         fold_last_texp = true;  // evaluated inside the final update kernel (its only reader)
         U_last = U;
         t_exp_last = t_exp;
+      } else if (overlap_dss) {
+        cts_prof_scope ps(c->ctx, CTS_PROF_T_EXP);
+        CTS_TRY(cts_column_dss_T_exp_overlapped(fuse_op, c->T_exp[i], U, t_imp, t_exp));
+        c->stats.dss_calls++;
       } else {
         cts_prof_scope ps(c->ctx, CTS_PROF_T_EXP);
         HOOK(c->ctx, f.T_exp_T_lim(f.ud, c->T_exp[i], c->T_lim[i], U, t_exp));
