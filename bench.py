@@ -78,9 +78,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(steps, warmup, sample_cols_log2=18):
+def cpu_reference(steps, warmup, sample_cols_log2=18, threads=None):
     """The reference's pass structure (oracle/cts_oracle.c, OpenMP over all host cores) on a bounded sample
-    of the same workload: 2^sample_cols_log2 columns x 64 levels."""
+    of the same workload: 2^sample_cols_log2 columns x 64 levels.  `threads = 1` gives the single-core figure: the
+    reference on `Base.Array` is a single-threaded broadcast loop, the all-cores number is the generous one."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import cts_oracle as CO
@@ -88,6 +89,9 @@ def cpu_reference(steps, warmup, sample_cols_log2=18):
     lib = CO.load()
     nx = NX
     ny = max(1, (1 << sample_cols_log2) // nx)
+    all_threads = lib.oracle_num_threads()
+    if threads is not None:
+        lib.oracle_set_num_threads(int(threads))
     cores = lib.oracle_num_threads()
     ncol = (ny + 2) * nx
     K = CO.fill_hash(ncol, 2, 0, 0.25, 2.0)
@@ -107,6 +111,8 @@ def cpu_reference(steps, warmup, sample_cols_log2=18):
     el = time.perf_counter() - t0
     n_owned = ny * nx * NLEV
     assert np.isfinite(u).all()
+    if threads is not None:
+        lib.oracle_set_num_threads(all_threads)
     return {"value": n_owned * STAGES * steps / el, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{ny * nx} columns x {NLEV} levels ({n_owned} DOF), {steps} steps after {warmup} warm-up, "
                       f"oracle/cts_oracle.c (reference pass structure, OpenMP, -O3 -march=native -ffp-contract=off)",
@@ -381,6 +387,8 @@ def run_ours(args):
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_reference(2, 1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        one = cpu_reference(1, 1, sample_cols_log2=16, threads=1)   # the faithful single-threaded figure, smaller sample
+        line["cpu_baseline"]["single_core"] = {"value": one["value"], "cores": one["cores"], "sample": one["sample"]}
     else:
         line["cpu_baseline"] = None
     if extras:
