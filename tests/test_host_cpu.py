@@ -44,6 +44,8 @@ int main(void){
         sizeof(cts_solver_stats), sizeof(cts_tridiag), sizeof(cts_column_desc), sizeof(cts_update_handler));
  printf("%zu %zu %zu %zu\n", offsetof(cts_ode_function, W), offsetof(cts_ode_function, update_constrain_state),
         offsetof(cts_newton_config, forcing_rtol), offsetof(cts_imex_tableau, cast_to_state_eltype));
+ printf("%zu %zu %zu %zu %zu %zu\n", sizeof(cts_rosenbrock_tableau), sizeof(cts_cond_node), sizeof(cts_convergence_checker),
+        offsetof(cts_rosenbrock_tableau, m), offsetof(cts_convergence_checker, comp_cond), offsetof(cts_convergence_checker, combiner_or));
  return 0; }"""
     import tempfile
     with tempfile.TemporaryDirectory() as d:
@@ -55,8 +57,11 @@ int main(void){
     sizes = [int(x) for x in out]
     assert sizes[:7] == [C.sizeof(L.OdeFunction), C.sizeof(L.ImexTableau), C.sizeof(L.NewtonConfig), C.sizeof(L.SolverStats),
                          C.sizeof(L.Tridiag), C.sizeof(L.ColumnDesc), C.sizeof(L.UpdateHandler)]
-    assert sizes[7:] == [L.OdeFunction.W.offset, L.OdeFunction.update_constrain_state.offset,
-                         L.NewtonConfig.forcing_rtol.offset, L.ImexTableau.cast_to_state_eltype.offset]
+    assert sizes[7:11] == [L.OdeFunction.W.offset, L.OdeFunction.update_constrain_state.offset,
+                           L.NewtonConfig.forcing_rtol.offset, L.ImexTableau.cast_to_state_eltype.offset]
+    assert sizes[11:] == [C.sizeof(L.RosenbrockTableau), C.sizeof(L.CondNode), C.sizeof(L.ConvergenceCheckerC),
+                          L.RosenbrockTableau.m.offset, L.ConvergenceCheckerC.comp_cond.offset,
+                          L.ConvergenceCheckerC.combiner_or.offset]
 
 
 def test_no_gpu_means_loud_failure_not_fallback():
