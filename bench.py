@@ -137,13 +137,15 @@ def run_reference(args):
 
 def workload_config(n_gpus, stored_w):
     return {"workload": "ARS343 IMEX + NewtonsMethod(max_iters=1, update_j=NewTimeStep), column vertical diffusion "
-                        f"2^21 columns x 64 levels (2^27 DOF) per GPU, Float64, batched tridiagonal W "
+                        f"{NX * NY} columns x {NLEV} levels ({NX * NY * NLEV} DOF{', = 2^27' if NY == 1024 else ''}) per GPU, Float64, batched tridiagonal W "
                         f"({'stored dl/d/du' if stored_w else 'matrix-free'}), explicit source + 5-point horizontal coupling, "
                         "dss! = ghost-row halo exchange",
             "baseline_config": "BASELINE.json configs[2] (single GPU) / configs[4] (sharded)",
             "columns_per_gpu": NX * NY, "levels": NLEV, "dof_per_gpu": NX * NY * NLEV, "stages_per_step": STAGES, "dt": DT,
             "global_dof": NX * NY * NLEV * n_gpus, "parallelism": f"column slabs x{n_gpus}",
-            "cache_policy": "every operand array is 1 GiB >> 126 MB L2, so no L2 flush is needed between steps"}
+            "cache_policy": (f"every operand array is {NX * NY * NLEV * 8 / 2 ** 20:.0f} MiB "
+                             + (">> 126 MB L2, so no L2 flush is needed between steps" if NX * NY * NLEV * 8 > 4 * 126e6
+                                else "(non-default --rows-per-gpu: NOT large against the 126 MB L2, numbers are cache-assisted)"))}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -556,9 +558,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--matrix-free", action="store_true", help="regenerate W = dtγJ - I inside the fused stage kernel")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--rows-per-gpu", type=int, default=0,
+                    help="rows of 2048 columns per GPU (default 1024 = BASELINE's 2^27 DOF; e.g. 128 for the 2^24-DOF strong-scaling slab)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.rows_per_gpu:
+        global NY
+        NY = int(args.rows_per_gpu)
+        args.no_extras = True
     if args.impl == "reference":
         run_reference(args)
     else:
