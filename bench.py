@@ -89,9 +89,9 @@ def cpu_reference(steps, warmup, sample_cols_log2=18, threads=None):
     lib = CO.load()
     nx = NX
     ny = max(1, (1 << sample_cols_log2) // nx)
-    all_threads = lib.oracle_num_threads()
-    if threads is not None:
-        lib.oracle_set_num_threads(int(threads))
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers: not a property of the box)
+    all_threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib.oracle_set_num_threads(int(threads) if threads is not None else all_threads)
     cores = lib.oracle_num_threads()
     ncol = (ny + 2) * nx
     K = CO.fill_hash(ncol, 2, 0, 0.25, 2.0)
