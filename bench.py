@@ -357,7 +357,7 @@ def run_ours(args):
     roof = None
     if fs_n:
         achieved = per_step * (fs_n / 3.0) / (fs_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "column_fused_stage_kernel (K1+K2+T_imp+K3+K4+K5+K6 of one implicit stage)",
+        roof = {"bound": "hbm", "kernel": "column_fused_stage_reg_kernel (K1+K2+T_imp+K3+K4+K5+K6 of one implicit stage; the first one also writes W)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "nominal_peak": 8000.0, "frac_of_nominal": achieved / 8000.0,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch (mean of the step's 3 launches) from the
