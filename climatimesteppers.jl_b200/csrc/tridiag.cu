@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kTileThreads) tridiag_tile_kernel(const T* __r
   const int col = warp * 16 + lane_column(lane);
   const bool is_up = lane_is_up(lane);
   StoredRows<T> rows{sdl, sd, sdu};
-  babe_solve_lanepair<T>(rows, RhsFromTile<T>{}, sr, col * pitch, nlev, is_up, col < nvalid);
+  babe_solve_lanepair<T, StoredRows<T>, RhsFromTile<T>, true>(rows, RhsFromTile<T>{}, sr, col * pitch, nlev, is_up, col < nvalid);
 
   if (LOADER == 1) {
     fence_proxy_async_smem();  // generic-proxy writes of x -> visible to the async proxy
