@@ -769,6 +769,9 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_MIN_BLOCKS) column_fu
 // few loads in flight: 6.7 ms.  So: 128 threads, <= 96 registers, 5 CTAs per SM.)
 constexpr int kKeep = (CTS_FUSED_TILE_COLS * 32 + kFusedThreads - 1) / kFusedThreads;  // U0 vectors per thread (f64: 16 cols x <= 32 vectors, f32: 32 x <= 16)
 
+#ifndef CTS_FUSED_PINGPONG
+#define CTS_FUSED_PINGPONG false
+#endif
 #ifndef CTS_FUSED_REG_MIN_BLOCKS
 #define CTS_FUSED_REG_MIN_BLOCKS 5
 #endif
@@ -889,11 +892,11 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
       const T acol = valid ? sAcol[col] : T(0);
       const double o = __dmul_rn(a.dtg, (double)acol);
       ConstRows<T> rows{(T)o, (T)__dsub_rn(__dmul_rn(-2.0, o), 1.0), sfac};
-      babe_solve_lanepair<T>(rows, RhsFromTile<T>{}, sx, col_off, nlev, is_up, valid);
+      babe_solve_lanepair<T, ConstRows<T>, RhsFromTile<T>, CTS_FUSED_PINGPONG>(rows, RhsFromTile<T>{}, sx, col_off, nlev, is_up, valid);
     } else {
       mbar_wait(bar, 0);
       StoredRows<T> rows{sdl, sd, sdu};
-      babe_solve_lanepair<T>(rows, RhsFromTile<T>{}, sx, col_off, nlev, is_up, valid);
+      babe_solve_lanepair<T, StoredRows<T>, RhsFromTile<T>, CTS_FUSED_PINGPONG>(rows, RhsFromTile<T>{}, sx, col_off, nlev, is_up, valid);
     }
   } else if (MATRIX_FREE && a.emit_w) {
     // the warps that only move data write W = dtγJ - I (same expressions as column_wfact_kernel) while the solver
