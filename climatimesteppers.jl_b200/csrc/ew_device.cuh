@@ -88,4 +88,28 @@ __device__ __forceinline__ T axpy_combine(T b, const T (&x)[NT > 0 ? NT : 1], co
   return (T)r;
 }
 
+// Same combine with the group split known at compile time: one multiply and one add per term, no selects.  (With a
+// run-time n1 the compiler evaluates both "add to g1" and "add to g2" for every term and selects: 4 FSEL + 1 extra DADD per
+// term and element, which matters in the issue-bound fused column stage.)
+template <typename T, typename C, int NT, int N1>
+__device__ __forceinline__ T axpy_combine_n1(T b, const T (&x)[NT > 0 ? NT : 1], const AxpyArgs<NT>& a) {
+  static_assert(N1 >= 0 && N1 <= NT, "group-1 count");
+  C r = (C)b;
+  if (a.scale_base) r = op_mul((C)a.c0, r);
+  if (NT > 0) {
+    C g1 = 0, g2 = 0;
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+      C p = op_mul((C)a.coef[k], (C)x[k]);
+      if (k < N1)
+        g1 = (k == 0) ? p : op_add(g1, p);
+      else
+        g2 = (k == N1) ? p : op_add(g2, p);
+    }
+    if (N1 > 0) r = op_add(r, g1);
+    if (N1 < NT) r = op_add(r, g2);
+  }
+  return (T)r;
+}
+
 }  // namespace cts_ew

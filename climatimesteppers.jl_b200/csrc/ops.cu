@@ -6,6 +6,7 @@
 //                                 in one pass over the column tile, (2+nnz)w [+3w for stored W] B/DOF
 // Both produce results bit-identical to the un-fused hook sequence (tests/test_gpu_parity.py).
 #include <algorithm>
+#include <type_traits>
 #include <cmath>
 #include <cstdlib>
 
@@ -16,6 +17,7 @@
 using namespace cts_tile;
 using cts_ew::AxpyArgs;
 using cts_ew::axpy_combine;
+using cts_ew::axpy_combine_n1;
 using cts_ew::Vec;
 using cts_ew::vec_pack;
 using cts_ew::vec_unpack;
@@ -824,6 +826,9 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
   V keep[kKeep];
   constexpr int UN = 2;
   static_assert(kKeep % UN == 0, "rounds are processed in pairs");
+  // N1c: the number of group-1 terms as a compile-time constant (-1: take it from the arguments at run time)
+  auto phase_a = [&](auto N1c) {
+  constexpr int N1 = decltype(N1c)::value;
 #pragma unroll
   for (int r0 = 0; r0 < kKeep; r0 += UN) {
     V vb[UN], vt[NTS][UN];
@@ -858,7 +863,10 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
         T x[NTS];
 #pragma unroll
         for (int t = 0; t < NT; ++t) x[t] = et[t][e];
-        uu[e] = axpy_combine<T, C, NT>(eb[e], x, a.ax);
+        if constexpr (N1 >= 0)
+          uu[e] = axpy_combine_n1<T, C, NT, (N1 >= 0 ? N1 : 0)>(eb[e], x, a.ax);
+        else
+          uu[e] = axpy_combine<T, C, NT>(eb[e], x, a.ax);
       }
       keep[r0 + u] = vec_pack<T>(uu);
       // level neighbours across the vector boundary: the previous / next lane of the same column segment
@@ -878,6 +886,23 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
         if (a.temp) reinterpret_cast<V*>(a.temp)[gi[u]] = keep[r0 + u];
       }
     }
+  }
+  };
+  // the group split is uniform over the launch: dispatch once to a copy of phase A specialised for it
+  if constexpr (NT <= 5) {  // (ARS343 needs up to 5 operands; larger counts keep the run-time split: compile time)
+    bool done = false;
+#define CTS_N1_CASE(K)                                                   \
+    if constexpr (K <= NT) {                                             \
+      if (!done && a.ax.n1 == K) {                                       \
+        phase_a(std::integral_constant<int, K>{});                       \
+        done = true;                                                     \
+      }                                                                  \
+    }
+    CTS_N1_CASE(0) CTS_N1_CASE(1) CTS_N1_CASE(2) CTS_N1_CASE(3) CTS_N1_CASE(4) CTS_N1_CASE(5)
+#undef CTS_N1_CASE
+    if (!done) phase_a(std::integral_constant<int, -1>{});
+  } else {
+    phase_a(std::integral_constant<int, -1>{});
   }
   __syncthreads();
 
