@@ -889,7 +889,9 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
   }
   };
   // the group split is uniform over the launch: dispatch once to a copy of phase A specialised for it
-  if constexpr (NT <= 5) {  // (ARS343 needs up to 5 operands; larger counts keep the run-time split: compile time)
+  // (matrix-free launches only -- the stored-W launches measured 6 % SLOWER with the specialised copies, 1.82 -> 1.96 ms
+  //  and 1.98 -> 2.10 ms per launch, while the matrix-free ones gain 11 %, 1.46 -> 1.30 ms; up to 5 operands: compile time)
+  if constexpr (NT <= 5 && MATRIX_FREE) {
     bool done = false;
 #define CTS_N1_CASE(K)                                                   \
     if constexpr (K <= NT) {                                             \
