@@ -777,7 +777,15 @@ constexpr int kKeep = (CTS_FUSED_TILE_COLS * 32 + kFusedThreads - 1) / kFusedThr
 #ifndef CTS_FUSED_REG_MIN_BLOCKS
 #define CTS_FUSED_REG_MIN_BLOCKS 5
 #endif
-template <typename T, typename C, int NT, bool MATRIX_FREE>
+// N1SPEC: how the kernel learns the split of the NT operands into the explicit group (first n1) and the implicit group:
+// 0 = from the arguments at run time, 1 = all in group 1 (n1 == NT), 2 = n1 == ceil(NT/2) (stage i of an IMEX-ARK tableau
+// with dense lower triangles: i-1 explicit and i-2 implicit tendencies).  A compile-time split needs no selects.
+template <int NT, int N1SPEC>
+struct GroupSplit {
+  static constexpr int value = N1SPEC == 1 ? NT : (N1SPEC == 2 ? (NT + 1) / 2 : -1);
+};
+
+template <typename T, typename C, int NT, bool MATRIX_FREE, int N1SPEC>
 __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) column_fused_stage_reg_kernel(const FusedArgs<NT> a) {
   using V = typename Vec<T>::type;
   constexpr int VN = Vec<T>::N;
@@ -888,24 +896,7 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
     }
   }
   };
-  // the group split is uniform over the launch: dispatch once to a copy of phase A specialised for it
-  // (matrix-free launches only -- the stored-W launches measured 6 % SLOWER with the specialised copies, 1.82 -> 1.96 ms
-  //  and 1.98 -> 2.10 ms per launch, while the matrix-free ones gain 11 %, 1.46 -> 1.30 ms; up to 5 operands: compile time)
-  if constexpr (NT <= 5 && MATRIX_FREE) {
-    bool done = false;
-#define CTS_N1_CASE(K)                                                   \
-    if constexpr (K <= NT) {                                             \
-      if (!done && a.ax.n1 == K) {                                       \
-        phase_a(std::integral_constant<int, K>{});                       \
-        done = true;                                                     \
-      }                                                                  \
-    }
-    CTS_N1_CASE(0) CTS_N1_CASE(1) CTS_N1_CASE(2) CTS_N1_CASE(3) CTS_N1_CASE(4) CTS_N1_CASE(5)
-#undef CTS_N1_CASE
-    if (!done) phase_a(std::integral_constant<int, -1>{});
-  } else {
-    phase_a(std::integral_constant<int, -1>{});
-  }
+  phase_a(std::integral_constant<int, GroupSplit<NT, N1SPEC>::value>{});
   __syncthreads();
 
   // ---- phase B (solver warps): two-sided product-form Thomas, a lane pair per column ---------------------
@@ -1010,14 +1001,31 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
     tiles = (op->ncols + kCols - 1) / kCols;
     size_t smem_reg = (size_t)(mf ? 2 : 4) * kCols * a.pitch + 16 + kCols * sizeof(T);
     a.dbg = nullptr;
-    if (mf) {
-      auto k = column_fused_stage_reg_kernel<T, C, NT, true>;
+    auto launch = [&](auto k) -> int {
       CTS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_reg));
       k<<<(unsigned)tiles, kFusedThreads, smem_reg, ctx->stream>>>(a);
-    } else {
-      auto k = column_fused_stage_reg_kernel<T, C, NT, false>;
-      CTS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_reg));
-      k<<<(unsigned)tiles, kFusedThreads, smem_reg, ctx->stream>>>(a);
+      return CTS_OK;
+    };
+    // kernels specialised for the two usual operand splits exist up to 5 operands (ARS343's largest stage)
+    int spec = 0;
+    if constexpr (NT >= 1 && NT <= 5) {
+      if (a.ax.n1 == NT)
+        spec = 1;
+      else if (a.ax.n1 == (NT + 1) / 2)
+        spec = 2;
+    }
+    if constexpr (NT >= 1 && NT <= 5) {
+      if (spec == 1) {
+        if (mf) CTS_TRY(launch(column_fused_stage_reg_kernel<T, C, NT, true, 1>));
+        else CTS_TRY(launch(column_fused_stage_reg_kernel<T, C, NT, false, 1>));
+      } else if (spec == 2) {
+        if (mf) CTS_TRY(launch(column_fused_stage_reg_kernel<T, C, NT, true, 2>));
+        else CTS_TRY(launch(column_fused_stage_reg_kernel<T, C, NT, false, 2>));
+      }
+    }
+    if (spec == 0) {
+      if (mf) CTS_TRY(launch(column_fused_stage_reg_kernel<T, C, NT, true, 0>));
+      else CTS_TRY(launch(column_fused_stage_reg_kernel<T, C, NT, false, 0>));
     }
     CTS_LAUNCH_CHECK(ctx);
     return CTS_OK;
