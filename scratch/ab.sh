@@ -4,4 +4,4 @@ run() {
 import json; d=json.load(open('/tmp/b.json')); print('$1 $2', round(d['value']/1e9,2), 'G DOF-stage/s', round(d['ms_per_step'],3), 'ms; fused', round(d['kernels']['fused_stage']['ms_per_step'],3), 'roof', round(d['roofline']['frac'],3))"
 }
 run default ""
-run default "--matrix-free"
+for v in $(ls scratch/variants | sed 's/lib_//; s/.so//'); do CTS_LIB_PATH=$PWD/scratch/variants/lib_$v.so run $v ""; done
