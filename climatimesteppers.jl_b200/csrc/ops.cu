@@ -808,6 +808,7 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
   const int nvalid = (int)((a.ncols - col0) < (size_t)kCols ? (a.ncols - col0) : (size_t)kCols);
   const int col_bytes = nlev * (int)sizeof(T);
   const size_t goff = col0 * (size_t)nlev;
+  const size_t gvec0 = goff * sizeof(T) / 16;  // first 16-byte vector of the tile in every operand array
   if (MATRIX_FREE && (int)threadIdx.x < nvalid) sAcol[threadIdx.x] = ((const T*)a.Kcol)[col0 + threadIdx.x];
 
   if (!MATRIX_FREE) {  // W tiles arrive by bulk TMA while U0 is being assembled
@@ -851,7 +852,7 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
       const int col = q >> cshift;
       kk[u] = q & (cpc - 1);
       so[u] = col * pitch + kk[u] * 16;
-      gi[u] = (goff * sizeof(T) + (size_t)col * col_bytes + (size_t)kk[u] * 16) / 16;  // 16-byte vector index
+      gi[u] = gvec0 + (size_t)q;  // 16-byte vector index: the tile's columns are contiguous, so it is simply tile base + q
       acol[u] = T(0);
       if (ok[u]) {
         vb[u] = reinterpret_cast<const V*>(a.ax.base)[gi[u]];
@@ -921,7 +922,7 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
     // warp works: the stores overlap the elimination instead of lengthening the epilogue
     for (int q = (int)threadIdx.x - kSolvers; q < total; q += kFusedThreads - kSolvers) {
       const int c = q >> cshift, k = q & (cpc - 1);
-      const size_t gi = (goff * sizeof(T) + (size_t)c * col_bytes + (size_t)k * 16) / 16;
+      const size_t gi = gvec0 + (size_t)q;
       const double o = __dmul_rn(a.dtg, (double)sAcol[c]);
       T eo[VN], ed[VN];
 #pragma unroll
@@ -944,7 +945,7 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
     const int q = (int)threadIdx.x + r * kFusedThreads;
     if (q >= total) continue;
     const int c = q >> cshift, k = q & (cpc - 1);
-    const size_t gi = (goff * sizeof(T) + (size_t)c * col_bytes + (size_t)k * 16) / 16;
+    const size_t gi = gvec0 + (size_t)q;
     T e0[VN], ex[VN], eU[VN], eT[VN];
     vec_unpack<T>(keep[r], e0);
     vec_unpack<T>(*reinterpret_cast<const V*>(sx + c * pitch + k * 16), ex);
