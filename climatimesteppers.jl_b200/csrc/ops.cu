@@ -802,6 +802,8 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
   char* sdu = smem + 3 * tile_bytes;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (MATRIX_FREE ? 2 : 4) * tile_bytes);
   T* sAcol = reinterpret_cast<T*>(smem + (MATRIX_FREE ? 2 : 4) * tile_bytes + 16);
+  // the solver threads park their U0 vectors here during the solve, so that those registers are free for the sweeps
+  V* sPark = reinterpret_cast<V*>(smem + (MATRIX_FREE ? 2 : 4) * tile_bytes + 16 + ((kCols * (int)sizeof(T) + 15) / 16) * 16);
 
   const int nlev = a.nlev;
   const size_t col0 = (size_t)blockIdx.x * kCols;
@@ -902,6 +904,8 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
 
   // ---- phase B (solver warps): two-sided product-form Thomas, a lane pair per column ---------------------
   if (threadIdx.x < kSolvers) {
+#pragma unroll
+    for (int r = 0; r < kKeep; ++r) sPark[r * kSolvers + threadIdx.x] = keep[r];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int col = warp * 16 + lane_column(lane);
     const bool is_up = lane_is_up(lane);
@@ -917,7 +921,12 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
       StoredRows<T> rows{sdl, sd, sdu};
       babe_solve_lanepair<T, StoredRows<T>, RhsFromTile<T>, CTS_FUSED_PINGPONG>(rows, RhsFromTile<T>{}, sx, col_off, nlev, is_up, valid);
     }
-  } else if (MATRIX_FREE && a.emit_w) {
+    // every warp meets at named barrier 1 (the branches are warp-uniform); the solver threads then take their U0 back
+    asm volatile("bar.sync 1, %0;" ::"n"(kFusedThreads) : "memory");
+#pragma unroll
+    for (int r = 0; r < kKeep; ++r) keep[r] = sPark[r * kSolvers + threadIdx.x];
+  } else {
+    if (MATRIX_FREE && a.emit_w) {
     // the warps that only move data write W = dtγJ - I (same expressions as column_wfact_kernel) while the solver
     // warp works: the stores overlap the elimination instead of lengthening the epilogue
     for (int q = (int)threadIdx.x - kSolvers; q < total; q += kFusedThreads - kSolvers) {
@@ -935,8 +944,9 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
       reinterpret_cast<V*>(const_cast<void*>(a.d))[gi] = vec_pack<T>(ed);
       reinterpret_cast<V*>(const_cast<void*>(a.du))[gi] = vo;
     }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kFusedThreads) : "memory");
   }
-  __syncthreads();
 
   // ---- phase C: U = U0 - dx ; Timp = (U - U0)/dtγ ; coalesced 128-bit stores; U0 from registers ----------
   const DivConst dc = div_const_prepare(a.dtg);
@@ -1000,7 +1010,8 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
   constexpr int kCols = TileShape<T>::kCols;
   if (!timeline && !no_reg && cpc >= 1 && cpc * kCols <= kKeep * kFusedThreads && (cpc & (cpc - 1)) == 0) {
     tiles = (op->ncols + kCols - 1) / kCols;
-    size_t smem_reg = (size_t)(mf ? 2 : 4) * kCols * a.pitch + 16 + kCols * sizeof(T);
+    size_t smem_reg = (size_t)(mf ? 2 : 4) * kCols * a.pitch + 16 + ((kCols * sizeof(T) + 15) / 16) * 16 +
+                      (size_t)TileShape<T>::kThreads * kKeep * 16;  // tiles + mbarrier + K/dz^2 + parked U0 of the solver threads
     a.dbg = nullptr;
     auto launch = [&](auto k) -> int {
       CTS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_reg));
