@@ -771,6 +771,9 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_MIN_BLOCKS) column_fu
 // few loads in flight: 6.7 ms.  So: 128 threads, <= 96 registers, 5 CTAs per SM.)
 constexpr int kKeep = (CTS_FUSED_TILE_COLS * 32 + kFusedThreads - 1) / kFusedThreads;  // U0 vectors per thread (f64: 16 cols x <= 32 vectors, f32: 32 x <= 16)
 
+#ifndef CTS_FUSED_PARK
+#define CTS_FUSED_PARK 1
+#endif
 #ifndef CTS_FUSED_PINGPONG
 #define CTS_FUSED_PINGPONG false
 #endif
@@ -904,8 +907,10 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
 
   // ---- phase B (solver warps): two-sided product-form Thomas, a lane pair per column ---------------------
   if (threadIdx.x < kSolvers) {
+#if CTS_FUSED_PARK
 #pragma unroll
     for (int r = 0; r < kKeep; ++r) sPark[r * kSolvers + threadIdx.x] = keep[r];
+#endif
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int col = warp * 16 + lane_column(lane);
     const bool is_up = lane_is_up(lane);
@@ -923,8 +928,10 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
     }
     // every warp meets at named barrier 1 (the branches are warp-uniform); the solver threads then take their U0 back
     asm volatile("bar.sync 1, %0;" ::"n"(kFusedThreads) : "memory");
+#if CTS_FUSED_PARK
 #pragma unroll
     for (int r = 0; r < kKeep; ++r) keep[r] = sPark[r * kSolvers + threadIdx.x];
+#endif
   } else {
     if (MATRIX_FREE && a.emit_w) {
     // the warps that only move data write W = dtγJ - I (same expressions as column_wfact_kernel) while the solver

@@ -1,7 +1,9 @@
 run() {
-  python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras $2 > /tmp/b.json 2>/tmp/b.err || { tail -3 /tmp/b.err; return; }
+  python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extras $2 > /tmp/b.json 2>/tmp/b.err || { tail -3 /tmp/b.err; return; }
   python -c "
 import json; d=json.load(open('/tmp/b.json')); print('$1 $2', round(d['value']/1e9,2), 'G DOF-stage/s', round(d['ms_per_step'],3), 'ms; fused', round(d['kernels']['fused_stage']['ms_per_step'],3), 'roof', round(d['roofline']['frac'],3))"
 }
+for i in 1 2; do
 run default ""
-for v in $(ls scratch/variants | sed 's/lib_//; s/.so//'); do CTS_LIB_PATH=$PWD/scratch/variants/lib_$v.so run $v ""; done
+CTS_LIB_PATH=$PWD/scratch/variants/lib_nopark.so run nopark ""
+done
