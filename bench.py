@@ -362,7 +362,7 @@ def run_ours(args):
                 "nominal_peak": 8000.0, "frac_of_nominal": achieved / 8000.0,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch (mean of the step's 3 launches) from the
                 # ncu --set full capture summarised in profiles/r1_step_kernels_ncu.txt; same workload, stored W only
-                "traffic": 9.682e9 if (stored_w and ndof_local == (NY + 2) * NX * NLEV) else None,
+                "traffic": 9.666e9 if (stored_w and ndof_local == (NY + 2) * NX * NLEV) else None,
                 "algorithmic_bytes_per_launch": per_step / 3.0,
                 "launches": fs_n, "avg_launch_ms": fs_ms / fs_n,
                 "algorithmic_bytes_per_dof_per_launch": stage_bytes(stored_w),
