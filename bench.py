@@ -5,12 +5,14 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
 
 Workload (BASELINE.json configs[2], the configuration the metric/target is quoted on): ARS343 IMEX on the
-column-stacked vertical-diffusion problem, 2^21 columns x 64 levels = 2^27 DOF per GPU in Float64,
+column-stacked vertical-diffusion problem, 2^21 columns x 64 levels = 2^27 DOF in Float64,
 NewtonsMethod(max_iters = 1, update_j = UpdateEvery(NewTimeStep)), batched tridiagonal Wfact/ldiv!, explicit
-source + 5-point horizontal coupling, dss! = ghost-row halo exchange (NCCL over NVLink when N > 1).
+source + 5-point horizontal coupling, dss! = ghost-row halo exchange.
 A "step" is one `step!` of the integrator; the metric is N_dof * s / t_step with s = 4 stages.
-Multi-GPU: weak scaling, each rank owns a 2^10 x 2^11 slab of columns (the global grid grows with N).
-Prints ONE JSON line on rank 0 (contract in the task statement; extra keys: roofline, cpu_baseline, kernels).
+Multi-GPU (BASELINE.json configs[4]): STRONG scaling -- the same 2^21 columns (a 2^11 x 2^10 horizontal grid) are
+split into N contiguous slabs of 2^10/N rows, one per GPU; dss! = NVLink peer-memory halo kernel (NCCL send/recv if the
+peers cannot be mapped).  The weak-scaling figure (2^27 DOF per GPU) is reported beside it in `extras.weak_scaling`.
+Prints ONE JSON line on rank 0 (contract in the task statement; extra keys: roofline, cpu_baseline, kernels, ...).
 """
 import argparse
 import json
@@ -23,7 +25,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NLEV, NX, NY = 64, 2 ** 11, 2 ** 10          # per-GPU slab: 2^21 columns x 64 levels
+NLEV, NX, NY = 64, 2 ** 11, 2 ** 10          # the GLOBAL problem: 2^21 columns x 64 levels (NY rows of NX columns)
 DT, NU = 0.02, 1.0
 STAGES = 4                                   # ARS343
 METRIC, UNIT = "imex_step_dof_stage_updates_per_s", "DOF-stage/s"
@@ -78,9 +80,20 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+def host_mem_gib():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) / 2 ** 20
+    except Exception:
+        pass
+    return 0.0
+
+
 def cpu_reference(steps, warmup, sample_cols_log2=18, threads=None):
-    """The reference's pass structure (oracle/cts_oracle.c, OpenMP over all host cores) on a bounded sample
-    of the same workload: 2^sample_cols_log2 columns x 64 levels.  `threads = 1` gives the single-core figure: the
+    """The reference's pass structure (oracle/cts_oracle.c, OpenMP over all host cores) on 2^sample_cols_log2 columns x 64
+    levels of the same workload (21 = the full BASELINE configuration).  `threads = 1` gives the single-core figure: the
     reference on `Base.Array` is a single-threaded broadcast loop, the all-cores number is the generous one."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
@@ -89,6 +102,7 @@ def cpu_reference(steps, warmup, sample_cols_log2=18, threads=None):
     lib = CO.load()
     nx = NX
     ny = max(1, (1 << sample_cols_log2) // nx)
+
     # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers: not a property of the box)
     all_threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     lib.oracle_set_num_threads(int(threads) if threads is not None else all_threads)
@@ -120,44 +134,61 @@ def cpu_reference(steps, warmup, sample_cols_log2=18, threads=None):
 
 
 def run_reference(args):
+    """The reference's own pass structure on the host cores, on the SAME configuration as the GPU arm (all 2^21 columns,
+    same --steps/--warmup) when the box has the memory for it (17 arrays of 1 GiB); otherwise a bounded sample whose size
+    is stated in `config`.  ~0.8 s per step on 16 cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 4))
-    warm = max(1, min(args.warmup, 1))
-    cb = cpu_reference(steps, warm)
+    full = host_mem_gib() >= 40 and not args.reference_sample
+    log2cols = 21 if full else 18
+    steps = max(1, min(args.steps, 30 if full else 60))
+    warm = max(1, min(args.warmup, 5))
+    cb = cpu_reference(steps, warm, sample_cols_log2=log2cols)
+    cfg = workload_config(args.gpus, stored_w=True)
+    cfg["reference_arm"] = ("full configuration: 2^21 columns x 64 levels" if full else
+                            f"bounded sample: 2^{log2cols} columns x 64 levels of the same workload (host memory)")
+    cfg["reference_columns"] = 1 << log2cols
+    one = cpu_reference(1, 1, sample_cols_log2=16, threads=1)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus, stored_w=True),
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": cfg,
+            "single_core": {"value": one["value"], "cores": one["cores"], "sample": one["sample"],
+                            "note": "the reference's Base.Array path is single-threaded; `value` above is the generous all-cores OpenMP figure"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def workload_config(n_gpus, stored_w):
+def workload_config(n_gpus, stored_w, ny_local=None):
+    ny_local = NY // n_gpus if ny_local is None else ny_local
+    dof_gpu = NX * ny_local * NLEV
     return {"workload": "ARS343 IMEX + NewtonsMethod(max_iters=1, update_j=NewTimeStep), column vertical diffusion "
-                        f"{NX * NY} columns x {NLEV} levels ({NX * NY * NLEV} DOF{', = 2^27' if NY == 1024 else ''}) per GPU, Float64, batched tridiagonal W "
-                        f"({'stored dl/d/du' if stored_w else 'matrix-free'}), explicit source + 5-point horizontal coupling, "
-                        "dss! = ghost-row halo exchange",
-            "baseline_config": "BASELINE.json configs[2] (single GPU) / configs[4] (sharded)",
-            "columns_per_gpu": NX * NY, "levels": NLEV, "dof_per_gpu": NX * NY * NLEV, "stages_per_step": STAGES, "dt": DT,
-            "global_dof": NX * NY * NLEV * n_gpus, "parallelism": f"column slabs x{n_gpus}",
-            "cache_policy": (f"every operand array is {NX * NY * NLEV * 8 / 2 ** 20:.0f} MiB "
-                             + (">> 126 MB L2, so no L2 flush is needed between steps" if NX * NY * NLEV * 8 > 4 * 126e6
-                                else "(non-default --rows-per-gpu: NOT large against the 126 MB L2, numbers are cache-assisted)"))}
+                        f"{NX * NY} columns x {NLEV} levels ({NX * NY * NLEV} DOF{', = 2^27' if NY == 1024 else ''}) in total, Float64, batched "
+                        f"tridiagonal W ({'stored dl/d/du' if stored_w else 'matrix-free'}), explicit source + 5-point horizontal "
+                        f"coupling, dss! = ghost-row halo exchange; split into {n_gpus} slab(s) of {ny_local} rows x {NX} columns",
+            "baseline_config": "BASELINE.json configs[2] (1 GPU) / configs[4] (the same problem sharded over N GPUs)",
+            "columns_total": NX * NY, "columns_per_gpu": NX * ny_local, "levels": NLEV, "dof_per_gpu": dof_gpu,
+            "stages_per_step": STAGES, "dt": DT, "global_dof": NX * NY * NLEV, "parallelism": f"column slabs x{n_gpus}",
+            "cache_policy": (f"every operand array is {dof_gpu * 8 / 2 ** 20:.0f} MiB per GPU; one step streams "
+                             f"{dof_gpu * 328 / 2 ** 20:.0f} MiB through HBM "
+                             + (">> 126 MB L2, so no L2 flush is needed between steps" if dof_gpu * 328 > 8 * 126e6
+                                else "(NOT large against the 126 MB L2: numbers are cache-assisted)"))}
 
 
 # ------------------------------------------------------------------------------------------------
-def build_problem(cts, ctx, part, matrix_free):
+def build_problem(cts, ctx, part, matrix_free, nx=None, nlev=None, alg=None, nonlinear=False, dt=None):
+    """The column problem on this rank's slab of `part` (hashed inputs keyed by GLOBAL indices, so every sharding sees
+    the same field)."""
     import numpy as np
+    nx = NX if nx is None else nx
+    nlev = NLEV if nlev is None else nlev
     nyl = part.ny_local
-    ncol = (nyl + 2) * NX
-    # hashed inputs keyed by GLOBAL indices so every sharding sees the same field
+    ncol = (nyl + 2) * nx
     K = cts.B200Vector.zeros(ncol, np.float64, ctx)
-    u = cts.B200Vector.zeros(ncol * NLEV, np.float64, ctx)
+    u = cts.B200Vector.zeros(ncol * nlev, np.float64, ctx)
     rows = part.local_rows(1)
-    import torch
     # contiguous runs of global rows (ghost rows wrap around): fill per run
     r = 0
     while r < len(rows):
@@ -165,18 +196,75 @@ def build_problem(cts, ctx, part, matrix_free):
         while e + 1 < len(rows) and rows[e + 1] == rows[e] + 1:
             e += 1
         g0, cnt = int(rows[r]), e - r + 1
-        kv = cts.B200Vector(K.tensor[r * NX:(r + cnt) * NX], ctx)
-        kv.fill_hash(2, g0 * NX, 0.25, 2.0)
-        uv = cts.B200Vector(u.tensor[r * NX * NLEV:(r + cnt) * NX * NLEV], ctx)
-        uv.fill_hash(3, g0 * NX * NLEV)
+        kv = cts.B200Vector(K.tensor[r * nx:(r + cnt) * nx], ctx)
+        kv.fill_hash(2, g0 * nx, 0.25, 2.0)
+        uv = cts.B200Vector(u.tensor[r * nx * nlev:(r + cnt) * nx * nlev], ctx)
+        uv.fill_hash(3, g0 * nx * nlev)
         r = e + 1
-    z = (np.arange(NLEV) + 1) / (NLEV + 1)
+    z = (np.arange(nlev) + 1) / (nlev + 1)
     S = cts.B200Vector.from_host(5.0 * np.exp(-((z - 0.3) ** 2) / 0.01), ctx)
-    op = cts.ColumnOperator(NLEV, NX, nyl, K, S_lev=S, nu=NU, halo=1, ctx=ctx).set_matrix_free(matrix_free)
-    alg = cts.IMEXAlgorithm(cts.ARS343(), cts.NewtonsMethod(max_iters=1, update_j=cts.UpdateEvery(cts.NewTimeStep)))
+    op = cts.ColumnOperator(nlev, nx, nyl, K, S_lev=S, nu=NU, halo=1, nonlinear=nonlinear, ctx=ctx)
+    if matrix_free:
+        op.set_matrix_free(True)
+    if alg is None:
+        alg = cts.IMEXAlgorithm(cts.ARS343(), cts.NewtonsMethod(max_iters=1, update_j=cts.UpdateEvery(cts.NewTimeStep)))
     prob = cts.ODEProblem(op.ode_function(), u, (0.0, 1.0e9), None)
-    integ = cts.init(prob, alg, dt=DT, save=False)
+    integ = cts.init(prob, alg, dt=DT if dt is None else dt, save=False)
     return op, integ, u
+
+
+def sharded_parity(cts, ctx, ctx_single, dist, rank, world, local):
+    """Driver-visible parity of the N-rank path: a miniature of the benchmark problem (same code path: fused stages,
+    overlapped peer-memory halos, CUDA-graph steps) and a sharded Newton-Krylov (SSP333 + JFNK/GMRES) case are stepped on
+    the N slabs and, on rank 0, as ONE slab on a communicator-free context; the owned rows must agree bit for bit."""
+    import torch
+    out = {"vs": "the same global problem stepped as one slab on rank 0 (which tests/ compare with the oracle)", "cases": {}}
+    nx, nlev, nyl = 64, 64, 32
+    cases = (("ars343_fused", None, False, 3, 0.02),
+             ("ssp333_jfnk", cts.IMEXAlgorithm(cts.SSP333(), cts.NewtonsMethod(max_iters=2, krylov_method=cts.KrylovMethod(
+                 jacobian_free_jvp=cts.ForwardDiffJVP(), forcing_term=cts.ConstantForcing(1e-3), itmax=30))), True, 2, 0.002))
+    ok_all = True
+    for name, alg, nonlinear, nsteps, dt in cases:
+        nlev_c = 16 if nonlinear else nlev
+        part = cts.SlabPartition(nyl * world, world, rank)
+        lay = part.reduction_layout(nx, nlev_c)
+        ctx.set_reduction_layout(*lay)
+        op, integ, u = build_problem(cts, ctx, part, False, nx=nx, nlev=nlev_c, alg=alg, nonlinear=nonlinear, dt=dt)
+        op.dss(u, None, 0.0)
+        for _ in range(nsteps):
+            cts.step_(integ)
+        nrm = u.norm()
+        own = u.tensor[lay[0]:lay[0] + lay[1]].contiguous()
+        parts = [torch.empty_like(own) for _ in range(world)] if rank == 0 else None
+        torch.cuda.synchronize()
+        dist.gather(own, parts, dst=0)
+        torch.cuda.synchronize()
+        ctx.set_reduction_window(0, 0)
+        res = None
+        if rank == 0:
+            whole = cts.SlabPartition(nyl * world, 1, 0)
+            lay1 = whole.reduction_layout(nx, nlev_c)
+            ctx_single.set_reduction_layout(*lay1)
+            op1, integ1, u1 = build_problem(cts, ctx_single, whole, False, nx=nx, nlev=nlev_c, alg=alg, nonlinear=nonlinear, dt=dt)
+            op1.dss(u1, None, 0.0)
+            for _ in range(nsteps):
+                cts.step_(integ1)
+            nrm1 = u1.norm()
+            ctx_single.set_reduction_window(0, 0)
+            want = u1.tensor[lay1[0]:lay1[0] + lay1[1]]
+            got = torch.cat(parts)
+            exact = bool(torch.equal(got, want)) and bool(torch.isfinite(got).all())
+            err = float((got - want).abs().max() / want.abs().max())
+            res = {"bit_exact": exact, "max_rel_err": err, "norm_equal": nrm == nrm1, "steps": nsteps,
+                   "global_dof": int(want.numel()), "graph_launches": integ.cache.graph_stats()["graph_launches"],
+                   "krylov_iters": integ.cache.stats()["krylov_iters"]}
+            ok_all = ok_all and exact and nrm == nrm1
+            del op1, integ1, u1
+        out["cases"][name] = res
+        del op, integ, u
+    out["ok"] = ok_all
+    out["halo_path"] = ctx.halo_path()
+    return out
 
 
 def stage_bytes(stored_w):
@@ -189,6 +277,18 @@ def stage_bytes(stored_w):
     return [(r + 2 + (3 if stored_w else 0)) * w for r in reads]
 
 
+def time_steps(cts, stream, integ, steps, barrier):
+    import torch
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        cts.step_(integ)
+    ev1.record(stream)
+    barrier()
+    return ev0.elapsed_time(ev1)
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -199,6 +299,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    if NY % world or NY // world < 32:
+        raise SystemExit(f"bench.py: {NY} rows cannot be split into {world} slabs of >= 32 rows")
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -209,11 +311,16 @@ def run_ours(args):
         ctx = cts.Context(local)           # enqueues on `stream`
         if world > 1:
             cts.attach_communicator(ctx, dist)
-        part = cts.SlabPartition(NY * world, world, rank)
+            ctx.enable_peer_halo(NX * NLEV * 8)   # collective: CUDA IPC mailboxes of the ring neighbours
+        # STRONG scaling: the 2^21-column problem is split into `world` slabs (weak scaling: extras.weak_scaling)
+        part = cts.SlabPartition(NY, world, rank)
         stored_w = not args.matrix_free
         op, integ, u = build_problem(cts, ctx, part, args.matrix_free)
+        if args.no_graph:
+            integ.cache.set_graph(False)
         op.dss(u, None, 0.0)
         n_owned = op.ndof_owned
+        state_bytes = int(u.tensor.numel() * 8)
 
         def barrier():
             torch.cuda.synchronize()
@@ -221,15 +328,21 @@ def run_ours(args):
                 dist.barrier()
             torch.cuda.synchronize()
 
+        def max_over_ranks(x):
+            if dist is None:
+                return x
+            t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()  # started before the warm-up so that nvidia-smi is already streaming when the timing starts
         for _ in range(args.warmup):
             cts.step_(integ)
+        # ---- the timed region: K steps, barrier + synchronize on both sides, CUDA events on the launching stream
         barrier()
         t_wall0 = time.time()
-        ctx.prof_read()
-        ctx.prof_enable(True)
         l0 = ctx.launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
@@ -237,32 +350,34 @@ def run_ours(args):
             cts.step_(integ)
         ev1.record(stream)
         barrier()
-        ms = ev0.elapsed_time(ev1)
+        ms_noprof = max_over_ranks(ev0.elapsed_time(ev1))
         launches = ctx.launch_count() - l0
+        # ---- the same K steps again with CUDA events around every kernel family (external event nodes when the step is a
+        # graph): per-kernel table and the roofline's launch durations
+        ctx.prof_read()
+        ctx.prof_enable(True)
+        ms = max_over_ranks(time_steps(cts, stream, integ, args.steps, barrier))
         prof = ctx.prof_read()
         ctx.prof_enable(False)
         stats = integ.cache.stats()
+        graph_stats = integ.cache.graph_stats()
         # A short timed region (K steps of ~10 ms) can end before nvidia-smi's 100 ms sampler has ticked: keep the
         # same load running (untimed, all ranks in lockstep) until at least 3 samples have been taken under load.
         trailing = 0
         while True:
-            need = torch.tensor([1.0 if (rank == 0 and sampler.proc and sampler.count_since(t_wall0) < 3 and trailing < 400) else 0.0],
+            need = torch.tensor([1.0 if (rank == 0 and sampler.proc and sampler.count_since(t_wall0) < 3 and trailing < 4000) else 0.0],
                                 device=f"cuda:{local}")
             if dist is not None:
                 dist.broadcast(need, 0)
             if need.item() == 0.0:
                 break
-            for _ in range(10):
+            for _ in range(20):
                 cts.step_(integ)
             torch.cuda.synchronize()
-            trailing += 10
+            trailing += 20
         clocks = sampler.stop(t_wall0) if rank == 0 else None
         if clocks is not None:
-            clocks["window"] = f"timed region + {trailing} trailing load steps (untimed)"
-        if dist is not None:
-            t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            clocks["window"] = f"timed region + instrumented pass + {trailing} trailing load steps (untimed)"
         finite = bool(torch.isfinite(u.tensor).all())
 
         # ---- end-to-end through the public API with HOST buffers: H2D of the state, step!, D2H of the result ----
@@ -278,11 +393,7 @@ def run_ours(args):
             ctx.check(ctx.lib.cts_memcpy_d2h_sync(ctx.handle, host.data_ptr(), u.ptr, nbytes), "d2h")
         ev1.record(stream)
         barrier()
-        ms_e2e = ev0.elapsed_time(ev1)
-        if dist is not None:
-            t = torch.tensor([ms_e2e], dtype=torch.float64, device=f"cuda:{local}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_e2e = float(t.item())
+        ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
 
         # ---- the same end-to-end work, software-pipelined: independent problem instances (the upload replaces the whole
         # state every step anyway) alternate between two device buffers, so the H2D of step k+1 and the D2H of step k-1
@@ -326,21 +437,49 @@ def run_ours(args):
             stream.wait_event(ev_out[(pipe_steps - 1) % 2])
             t1.record(stream)
             barrier()
-            ms_pipe = t0.elapsed_time(t1)
+            ms_pipe = max_over_ranks(t0.elapsed_time(t1))
             integ.u = u
-            if dist is not None:
-                t = torch.tensor([ms_pipe], dtype=torch.float64, device=f"cuda:{local}")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms_pipe = float(t.item())
             finite = finite and bool(torch.isfinite(host_out).all())
             del bufs, host_out
         except Exception as e:  # the pipelined variant is an extra; the sequential number above is the contract's e2e
             sys.stderr.write(f"pipelined e2e skipped: {e!r}\n")
             integ.u = u
 
-        # ---- extras (rank 0, N = 1): the other single-GPU workloads and stand-alone kernels --------------
+        # ---- extras ------------------------------------------------------------------------------------------
         extras = {}
-        if world == 1 and not args.no_extras:
+        halo_path = ctx.halo_path()
+        if world > 1:
+            # (a) the same slab stepped WITHOUT a communicator (periodic local ghost copies): what one GPU does on its
+            #     share of the problem when nothing has to be exchanged -> exposed communication = difference
+            ctx1 = cts.Context(local)
+            op1, integ1, u1 = build_problem(cts, ctx1, cts.SlabPartition(NY // world, 1, 0), args.matrix_free)
+            if args.no_graph:
+                integ1.cache.set_graph(False)
+            op1.dss(u1, None, 0.0)
+            for _ in range(args.warmup):
+                cts.step_(integ1)
+            ms_local = max_over_ranks(time_steps(cts, stream, integ1, args.steps, barrier))
+            del op1, integ1, u1
+            extras["local_slab"] = {"ms_per_step": ms_local / args.steps,
+                                    "note": "this rank's slab with periodic local ghost copies instead of the neighbour exchange (max over ranks)"}
+            extras["exposed_comm_ms_per_step"] = (ms_noprof - ms_local) / args.steps
+            # (b) driver-visible parity of the sharded path
+            extras["sharded_parity"] = sharded_parity(cts, ctx, ctx1, dist, rank, world, local)
+            # (c) weak scaling: 2^27 DOF per GPU (the global grid grows with N), as reported in round 1
+            if not args.no_weak:
+                del integ, op, u
+                torch.cuda.empty_cache()
+                opw, integw, uw = build_problem(cts, ctx, cts.SlabPartition(NY * world, world, rank), args.matrix_free)
+                opw.dss(uw, None, 0.0)
+                wsteps = max(3, min(args.steps, 10))
+                for _ in range(3):
+                    cts.step_(integw)
+                ms_w = max_over_ranks(time_steps(cts, stream, integw, wsteps, barrier))
+                extras["weak_scaling"] = {"value": opw.ndof_owned * world * STAGES * wsteps / (ms_w * 1e-3), "unit": UNIT,
+                                          "ms_per_step": ms_w / wsteps, "steps": wsteps, "dof_per_gpu": opw.ndof_owned,
+                                          "global_dof": opw.ndof_owned * world}
+                del opw, integw, uw
+        elif not args.no_extras:
             del integ
             extras = run_extras(cts, ctx, stream, op, u)
 
@@ -349,10 +488,12 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     peak, peak_src = peaks()
-    value = n_owned * world * STAGES * args.steps / (ms * 1e-3)
+    ndof_local = (NY // world + 2) * NX * NLEV
+    # `value`: the K timed steps without the per-kernel event brackets; the instrumented pass of the same K steps (run
+    # immediately before, same state) provides the per-kernel table and the roofline's launch durations
+    value = n_owned * world * STAGES * args.steps / (ms_noprof * 1e-3)
     # roofline of the dominant kernel (fused column stage): algorithmic bytes / measured launch time
     fs_ms, fs_n = prof.get("fused_stage", (0.0, 0))
-    ndof_local = op.ndof
     per_step = sum(stage_bytes(stored_w)) * ndof_local
     roof = None
     if fs_n:
@@ -360,9 +501,7 @@ def run_ours(args):
         roof = {"bound": "hbm", "kernel": "column_fused_stage_reg_kernel (K1+K2+T_imp+K3+K4+K5+K6 of one implicit stage; the first one also writes W)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "nominal_peak": 8000.0, "frac_of_nominal": achieved / 8000.0,
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch (mean of the step's 3 launches) from the
-                # ncu --set full capture summarised in profiles/r1_step_kernels_ncu.txt; same workload, stored W only
-                "traffic": 9.666e9 if (stored_w and ndof_local == (NY + 2) * NX * NLEV) else None,
+                "traffic": ncu_traffic(stored_w, world),
                 "algorithmic_bytes_per_launch": per_step / 3.0,
                 "launches": fs_n, "avg_launch_ms": fs_ms / fs_n,
                 "algorithmic_bytes_per_dof_per_launch": stage_bytes(stored_w),
@@ -370,15 +509,20 @@ def run_ours(args):
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items()}
     step_bytes = step_bytes_per_dof(stored_w) * ndof_local
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_noprof / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(world, stored_w),
             "roofline": roof,
             "step_hbm": {"algorithmic_bytes_per_dof_step": step_bytes_per_dof(stored_w),
-                         "achieved_GBs_per_gpu": step_bytes / (ms / args.steps * 1e-3) / 1e9,
-                         "frac_of_peak": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
+                         "achieved_GBs_per_gpu": step_bytes / (ms_noprof / args.steps * 1e-3) / 1e9,
+                         "frac_of_peak": step_bytes / (ms_noprof / args.steps * 1e-3) / 1e9 / peak},
             "kernels": kernels,
+            "instrumented_pass": {"ms_per_step": ms / args.steps, "steps": args.steps,
+                                  "note": "the same K steps with CUDA events around every kernel family (source of `kernels` and `roofline`)"},
+            "halo": {"path": halo_path, "exchanges_per_step": 4,
+                     "overlap": "both exchanges of every stage and of the step end run on a second stream beside the interior rows"},
+            "cuda_graph": graph_stats,
             "e2e": {"value": n_owned * world * STAGES * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(u.tensor.numel() * 8), "d2h_bytes_per_step": int(u.tensor.numel() * 8),
+                    "h2d_bytes_per_step": state_bytes * world, "d2h_bytes_per_step": state_bytes * world,
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                     "pipelined": None if ms_pipe is None else {
                         "value": n_owned * world * STAGES * pipe_steps / (ms_pipe * 1e-3), "ms_per_step": ms_pipe / pipe_steps,
@@ -386,7 +530,7 @@ def run_ours(args):
                         "on three streams so the copies overlap the kernels"},
                     "api": "C ABI: cts_memcpy_h2d (pinned host state) + cts_imex_step (via cts_b200.step_) + cts_memcpy_d2h_sync, every step"},
             "gpu_launches": launches, "clocks": clocks, "solver_stats": stats, "finite": finite}
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline:   # rank 0, every N (the CPU arm is the same fixed global problem)
         cb = cpu_reference(2, 1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         one = cpu_reference(1, 1, sample_cols_log2=16, threads=1)   # the faithful single-threaded figure, smaller sample
@@ -398,6 +542,19 @@ def run_ours(args):
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def ncu_traffic(stored_w, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused stage (mean of the step's 3 launches), read from
+    the committed summary of the `ncu --set full` capture of this command (profiles/summarize.py traffic -> JSON)."""
+    p = os.path.join(ROOT, "profiles", "fused_stage_traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f)
+        key = f"{'stored' if stored_w else 'matrix_free'}_n{world}"
+        return t.get(key, {}).get("traffic_bytes_per_launch")
+    except Exception:
+        return None
 
 
 def step_bytes_per_dof(stored_w):
@@ -558,14 +715,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--matrix-free", action="store_true", help="regenerate W = dtγJ - I inside the fused stage kernel")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--rows-per-gpu", type=int, default=0,
-                    help="rows of 2048 columns per GPU (default 1024 = BASELINE's 2^27 DOF; e.g. 128 for the 2^24-DOF strong-scaling slab)")
+    ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of the per-step CUDA graph")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling extra (2^27 DOF per GPU)")
+    ap.add_argument("--reference-sample", action="store_true", help="--impl reference: time a 2^18-column sample instead of the full 2^21")
+    ap.add_argument("--rows", type=int, default=0,
+                    help="global rows of 2048 columns (default 1024 = BASELINE's 2^27 DOF; e.g. 128 = one rank's share at N = 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.rows_per_gpu:
+    if args.rows:
         global NY
-        NY = int(args.rows_per_gpu)
+        NY = int(args.rows)
         args.no_extras = True
     if args.impl == "reference":
         run_reference(args)

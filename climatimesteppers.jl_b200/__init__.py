@@ -21,6 +21,7 @@ from .integrators import (CallbackSet, DiscreteCallback, EveryXSimulationSteps, 
                           solve_, step_)
 from .operators import AdvectionOperator, ColumnOperator, ColumnTridiag
 from .parallel import SlabPartition, attach_communicator
-from .solvers import IMEXCache, LSRKCache, RosenbrockCache, init_cache, step_u
+from .solvers import (IMEXCache, LSRKCache, NewtonCache, RosenbrockCache, allocate_cache, init_cache, solve_newton_,
+                      step_u)
 from .tableaus import *  # noqa: F401,F403  (named tableaux: ARS343, SSP333, ...)
 from .tableaus import IMEX_NAMES, EXPLICIT_NAMES, IMEXTableau, RosenbrockTableau, SSPKnoth, is_fsal, tableau

@@ -150,7 +150,13 @@ SIGNATURES = [
     ("cts_nrm2", _I, [_P, _I, _SZ, _P, c_double_p]),
     ("cts_sum1pabs", _I, [_P, _I, _SZ, _P, c_double_p]),
     ("cts_multi_dot", _I, [_P, _I, _SZ, _I, c_void_pp, _P, c_double_p]),
+    ("cts_imex_cache_set_graph", _I, [_P, _I]),
+    ("cts_imex_cache_graph_stats", _I, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("cts_comm_enable_peer_halo", _I, [_P, _SZ]),
+    ("cts_comm_halo_path", _I, [_P, C.POINTER(C.c_int)]),
     ("cts_set_reduction_window", _I, [_P, _SZ, _SZ]),
+    ("cts_set_reduction_layout", _I, [_P, _SZ, _SZ, _SZ, _SZ, _SZ]),
+    ("cts_reduction_global_length", _I, [_P, _SZ, C.POINTER(C.c_size_t)]),
     ("cts_tridiag_solve_batched", _I, [_P, _I, C.POINTER(Tridiag), _P, _P]),
     ("cts_tridiag_matvec", _I, [_P, _I, C.POINTER(Tridiag), _P, _P]),
     ("cts_imex_cache_create", _I, [_P, _I, _SZ, C.POINTER(ImexTableau), _I, C.POINTER(OdeFunction),

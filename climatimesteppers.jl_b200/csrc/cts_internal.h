@@ -9,7 +9,7 @@
 
 #include "../../include/cts.h"
 
-struct cts_nccl_api;  // comm.cpp
+struct cts_peer_halo;  // comm.cu
 
 struct cts_ctx {
   int device = 0;
@@ -18,19 +18,29 @@ struct cts_ctx {
   int num_sms = 148;
   std::string err;
   uint64_t launches = 0;
-  // reduction scratch (reduce.cu)
-  double* d_partials = nullptr;   // [kMaxMulti][kReduceBlocks]
+  // reduction scratch (reduce.cu): per-chunk partial sums, [k][n_chunks_global] (grown on demand)
+  double* d_partials = nullptr;   // this rank's chunk partials (entries of chunks owned by other ranks stay zero)
+  double* d_partials_g = nullptr; // all ranks' chunk partials after the exchange (multi-rank layouts only)
+  size_t partials_cap = 0;        // capacity of each of the two arrays, in doubles
   double* d_result = nullptr;     // [kMaxMulti]
   unsigned int* d_counter = nullptr;
   double* h_result = nullptr;     // pinned [kMaxMulti]
-  bool red_window = false;
+  bool red_window = false;        // reductions cover [red_offset, red_offset + red_count) of every vector
   size_t red_offset = 0, red_count = 0;
+  // shard-invariant layout (cts_set_reduction_layout): the window is the slice [red_g0, red_g0 + red_count) of a
+  // global index space of red_G elements that is cut into fixed chunks of red_chunk elements
+  bool red_layout = false;
+  size_t red_g0 = 0, red_G = 0;
+  unsigned red_chunk = 0;         // 0 -> kReduceChunk
   // device-side pointer table scratch for kernels taking many operands
   // communicator (comm.cpp)
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
+  struct cts_peer_halo* peer = nullptr;        // NVLink peer-memory mailboxes of the halo exchange (comm.cu)
+  int peer_mode = 0;                           // 0: not set up, 1: peer-memory halo kernel, -1: NCCL send/recv
   cudaStream_t comm_stream = nullptr;          // halo exchanges that overlap compute run here (created on first use)
   cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
+  bool capturing = false;  // the context's stream is being captured into a CUDA graph (cts_imex_step)
   // per-kernel timing (cts_prof_*)
   bool prof_on = false;
   struct ProfRec {
@@ -58,16 +68,17 @@ struct cts_prof_scope {
       return e;
     };
     cts_ctx::ProfRec r{cat, get(), get()};
-    cudaEventRecord(r.a, c->stream);
+    cudaEventRecordWithFlags(r.a, c->stream, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
     c->prof_recs.push_back(r);
     idx = (int)c->prof_recs.size() - 1;
   }
   ~cts_prof_scope() {
-    if (idx >= 0) cudaEventRecord(ctx->prof_recs[idx].b, ctx->stream);
+    if (idx >= 0)
+      cudaEventRecordWithFlags(ctx->prof_recs[idx].b, ctx->stream, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
   }
 };
 
-constexpr int kReduceBlocks = 1184;  // 148 SMs x 8: fixed so that reductions are deterministic
+constexpr int kReduceChunk = 8192;   // default elements per reduction chunk (one CTA per chunk): part of the result's definition
 constexpr int kReduceThreads = 256;
 constexpr int kMaxMulti = 8;
 
@@ -102,6 +113,13 @@ inline int cts_fail(cts_ctx* ctx, int code, const std::string& msg) {
     int _r = (expr);         \
     if (_r != 0) return _r;  \
   } while (0)
+
+// length(x) of a distributed vector (newtons_method.jl:135,445): the global domain of the layout, else rank-local * ranks
+inline size_t cts_global_length(const cts_ctx* ctx, size_t n) {
+  if (ctx->red_window && ctx->red_layout) return ctx->red_G;
+  return (ctx->red_window ? ctx->red_count : n) * (size_t)ctx->nranks;
+}
+int cts_allreduce_sum_f64_oop(cts_ctx* ctx, const double* send, double* recv, size_t count);
 
 inline size_t cts_sizeof(cts_dtype ft) { return ft == CTS_F64 ? 8 : 4; }
 inline bool cts_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -147,6 +165,10 @@ int cts_column_dss_T_exp_overlapped(cts_op_column* op, void* du_exp, void* U, do
 int cts_halo_exchange_on(cts_ctx* ctx, cudaStream_t stream, cts_dtype ft, size_t count, const void* send_lo,
                          const void* send_hi, void* recv_lo, void* recv_hi);
 int cts_column_fused_final_update(cts_op_column* op, const cts_final_update_args* a);
+bool cts_column_final_update_supported(const cts_op_column* op, const cts_final_update_args* a);
+// dss!(U_last); final update; dss!(u) with both halo exchanges and the boundary strips on the communication stream
+int cts_column_final_update_overlapped(cts_op_column* op, const cts_final_update_args* a);
+int cts_ctx_ensure_comm_stream(cts_ctx* ctx);
 // Newton residual (dx == NULL) or forward-difference JVP of the stage equation for the column operator in one pass
 bool cts_column_residual_fusable(const cts_op_column* op);
 int cts_column_fused_residual(cts_op_column* op, void* out, const void* x, const void* dx, double eps, const void* U0,

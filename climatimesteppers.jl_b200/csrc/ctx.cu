@@ -32,8 +32,7 @@ int cts_ctx_create(cts_ctx** out, int device, void* cuda_stream) {
   }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
-  bool ok = cudaMalloc(&ctx->d_partials, sizeof(double) * kMaxMulti * kReduceBlocks) == cudaSuccess &&
-            cudaMalloc(&ctx->d_result, sizeof(double) * kMaxMulti) == cudaSuccess &&
+  bool ok = cudaMalloc(&ctx->d_result, sizeof(double) * kMaxMulti) == cudaSuccess &&
             cudaMalloc(&ctx->d_counter, sizeof(unsigned int)) == cudaSuccess &&
             cudaMallocHost(&ctx->h_result, sizeof(double) * kMaxMulti) == cudaSuccess &&
             cudaMemset(ctx->d_counter, 0, sizeof(unsigned int)) == cudaSuccess;
@@ -58,6 +57,7 @@ int cts_ctx_destroy(cts_ctx* ctx) {
   }
   for (auto e : ctx->prof_pool) cudaEventDestroy(e);
   if (ctx->d_partials) cudaFree(ctx->d_partials);
+  if (ctx->d_partials_g) cudaFree(ctx->d_partials_g);
   if (ctx->d_result) cudaFree(ctx->d_result);
   if (ctx->d_counter) cudaFree(ctx->d_counter);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);

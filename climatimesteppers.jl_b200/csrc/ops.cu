@@ -457,6 +457,7 @@ struct FinalArgs {
   unsigned nlev, nx, row_elems;
   size_t ny_local;
   int halo, has_src;
+  size_t jr_begin, jr_end;  // owned rows [jr_begin, jr_end) of this launch
 };
 
 template <typename T, typename C, int NT, int ROWS>
@@ -482,8 +483,8 @@ __global__ void __launch_bounds__(256) column_final_update_kernel(const FinalArg
 #pragma unroll
     for (int e = 0; e < VN; ++e) src[e] = rmul(t[e], g);
   }
-  const size_t jr0 = (size_t)blockIdx.y * ROWS;
-  const size_t jr1 = jr0 + ROWS < a.ny_local ? jr0 + ROWS : a.ny_local;
+  const size_t jr0 = a.jr_begin + (size_t)blockIdx.y * ROWS;
+  const size_t jr1 = jr0 + ROWS < a.jr_end ? jr0 + ROWS : a.jr_end;
   auto local_row = [&](long long jr) -> size_t {
     if (a.halo) return (size_t)(jr + 1);
     return jr < 0 ? rows - 1 : ((size_t)jr == rows ? 0 : (size_t)jr);
@@ -1114,8 +1115,9 @@ int cts_column_fused_stage(cts_op_column* op, const cts_fused_stage_args* s) {
 }
 
 template <typename T, typename C, int NT>
-int launch_final(cts_op_column* op, const cts_final_update_args* s) {
+int launch_final(cts_op_column* op, const cts_final_update_args* s, size_t jr_begin, size_t jr_end) {
   cts_ctx* ctx = op->ctx;
+  if (jr_begin >= jr_end) return CTS_OK;
   const cts_column_desc& d = op->d;
   FinalArgs<NT> a{};
   a.ax.base = s->u;
@@ -1136,20 +1138,22 @@ int launch_final(cts_op_column* op, const cts_final_update_args* s) {
   a.ny_local = d.ny_local;
   a.halo = d.halo;
   a.has_src = d.S_lev != nullptr;
+  a.jr_begin = jr_begin;
+  a.jr_end = jr_end;
   constexpr int ROWS = 8;
   constexpr int VN = Vec<T>::N;
-  dim3 grid((unsigned)((a.row_elems / VN + 255) / 256), (unsigned)((d.ny_local + ROWS - 1) / ROWS));
+  dim3 grid((unsigned)((a.row_elems / VN + 255) / 256), (unsigned)((jr_end - jr_begin + ROWS - 1) / ROWS));
   column_final_update_kernel<T, C, NT, ROWS><<<grid, 256, 0, ctx->stream>>>(a);
   CTS_LAUNCH_CHECK(ctx);
   return CTS_OK;
 }
 
 template <typename T, typename C>
-int dispatch_final(cts_op_column* op, const cts_final_update_args* s) {
+int dispatch_final(cts_op_column* op, const cts_final_update_args* s, size_t jr_begin, size_t jr_end) {
   switch (s->n_grp1 + s->n_grp2) {
 #define CASE(N) \
   case N:       \
-    return launch_final<T, C, N>(op, s);
+    return launch_final<T, C, N>(op, s, jr_begin, jr_end);
     CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
 #undef CASE
     default:
@@ -1165,15 +1169,24 @@ bool cts_column_final_fusable(const cts_op_column* op) {
          (!d.S_lev || cts_aligned16(d.S_lev));
 }
 
-int cts_column_fused_final_update(cts_op_column* op, const cts_final_update_args* s) {
-  if (!op || !s || !s->u || !s->U_last || s->u == s->U_last) return CTS_EINVAL;
-  if (!cts_column_final_fusable(op) || s->n_grp1 + s->n_grp2 > 10) return CTS_EUNSUPPORTED;
+static int final_update_rows(cts_op_column* op, const cts_final_update_args* s, size_t jr_begin, size_t jr_end) {
+  if (op->ft == CTS_F64) return dispatch_final<double, double>(op, s, jr_begin, jr_end);
+  if (s->compute_native) return dispatch_final<float, float>(op, s, jr_begin, jr_end);
+  return dispatch_final<float, double>(op, s, jr_begin, jr_end);
+}
+
+bool cts_column_final_update_supported(const cts_op_column* op, const cts_final_update_args* s) {
+  if (!op || !s || !s->u || !s->U_last || s->u == s->U_last) return false;
+  if (!cts_column_final_fusable(op) || s->n_grp1 + s->n_grp2 > 10) return false;
   bool aligned = cts_aligned16(s->u) && cts_aligned16(s->U_last);
   for (int k = 0; k < s->n_grp1 + s->n_grp2; ++k) aligned = aligned && cts_aligned16(s->terms[k]);
-  if (!aligned) return CTS_EUNSUPPORTED;
-  if (op->ft == CTS_F64) return dispatch_final<double, double>(op, s);
-  if (s->compute_native) return dispatch_final<float, float>(op, s);
-  return dispatch_final<float, double>(op, s);
+  return aligned;
+}
+
+int cts_column_fused_final_update(cts_op_column* op, const cts_final_update_args* s) {
+  if (!op || !s || !s->u || !s->U_last || s->u == s->U_last) return CTS_EINVAL;
+  if (!cts_column_final_update_supported(op, s)) return CTS_EUNSUPPORTED;
+  return final_update_rows(op, s, 0, op->d.ny_local);
 }
 
 bool cts_column_residual_fusable(const cts_op_column* op) {
@@ -1391,10 +1404,9 @@ int cts_op_column_T_exp(void* vop, void* du_exp, void* du_lim, const void* u, do
   return column_T_exp_rows(op, du_exp, u, t, 0, op->d.ny_local);
 }
 
-int cts_op_column_dss(void* vop, void* u, double t) {
-  auto* op = static_cast<cts_op_column*>(vop);
-  if (!op || !u) return CTS_EINVAL;
-  if (!op->d.halo) return CTS_OK;  // nothing is duplicated
+// dss!(u): refresh the ghost rows from their owners, enqueued on `stream` (periodic local copies on one rank, the
+// NVLink peer-memory halo kernel or NCCL send/recv otherwise)
+static int column_halo_on(cts_op_column* op, cudaStream_t stream, void* u) {
   cts_ctx* ctx = op->ctx;
   const size_t row = op->d.nx * (size_t)op->d.nlev;
   const size_t es = cts_sizeof(op->ft);
@@ -1404,52 +1416,114 @@ int cts_op_column_dss(void* vop, void* u, double t) {
   char* last = b + op->d.ny_local * row * es;
   char* ghost_hi = b + (op->d.ny_local + 1) * row * es;
   if (ctx->nranks <= 1) {  // periodic in the slow horizontal axis: the neighbour is this rank
-    CTS_CUDA(ctx, cudaMemcpyAsync(ghost_lo, last, row * es, cudaMemcpyDeviceToDevice, ctx->stream));
-    CTS_CUDA(ctx, cudaMemcpyAsync(ghost_hi, first, row * es, cudaMemcpyDeviceToDevice, ctx->stream));
+    CTS_CUDA(ctx, cudaMemcpyAsync(ghost_lo, last, row * es, cudaMemcpyDeviceToDevice, stream));
+    CTS_CUDA(ctx, cudaMemcpyAsync(ghost_hi, first, row * es, cudaMemcpyDeviceToDevice, stream));
     return CTS_OK;
   }
-  return cts_halo_exchange(ctx, op->ft, row, first, last, ghost_lo, ghost_hi);
+  if (ctx->peer_mode == 0) CTS_TRY(cts_comm_enable_peer_halo(ctx, row * es));  // first dss!: collective set-up
+  return cts_halo_exchange_on(ctx, stream, op->ft, row, first, last, ghost_lo, ghost_hi);
+}
+
+int cts_op_column_dss(void* vop, void* u, double t) {
+  auto* op = static_cast<cts_op_column*>(vop);
+  if (!op || !u) return CTS_EINVAL;
+  if (!op->d.halo) return CTS_OK;  // nothing is duplicated
+  return column_halo_on(op, op->ctx->stream, u);
 }
 
 }  // extern "C"
 
+// ---------------------------------------------------------------------------------------------
+// Halo / compute overlap.  The boundary work of a stencil pass runs on a second (high-priority) stream together with
+// the halo exchange it depends on, the interior rows on the compute stream; the two meet again before the call returns,
+// so callers keep plain stream-ordered semantics.  Captured into a CUDA graph this is a fork/join.
+// ---------------------------------------------------------------------------------------------
+constexpr size_t kEdgeRows = 8;  // one strip of the marching kernels
+
 bool cts_column_overlap_ok(const cts_op_column* op) {
   const cts_column_desc& d = op->d;
   const int vn = op->ft == CTS_F64 ? 2 : 4;
-  return op->ctx->nranks > 1 && d.halo == 1 && d.nu != 0.0 && (d.nlev % vn) == 0 && d.ny_local >= 32 &&
+  static const bool off = getenv("CTS_NO_OVERLAP") != nullptr;  // developer switch
+  return !off && d.halo == 1 && d.nu != 0.0 && (d.nlev % vn) == 0 && d.ny_local >= 4 * kEdgeRows &&
          d.nx * (size_t)d.nlev < (1ull << 31);
 }
 
+int cts_ctx_ensure_comm_stream(cts_ctx* ctx) {
+  if (ctx->comm_stream) return CTS_OK;
+  int lo = 0, hi = 0;
+  CTS_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = greatest priority
+  CTS_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
+  CTS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
+  CTS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
+  return CTS_OK;
+}
+
+namespace {
+struct StreamSwap {  // launches issued through the context go to `s` for the lifetime of the object
+  cts_ctx* ctx;
+  cudaStream_t saved;
+  StreamSwap(cts_ctx* c, cudaStream_t s) : ctx(c), saved(c->stream) { c->stream = s; }
+  ~StreamSwap() { ctx->stream = saved; }
+};
+}  // namespace
+
 int cts_column_dss_T_exp_overlapped(cts_op_column* op, void* du_exp, void* U, double t_dss, double t_exp) {
   if (!op || !du_exp || !U) return CTS_EINVAL;
-  if (!cts_column_overlap_ok(op)) {
+  const cts_column_desc& d = op->d;
+  const int vn = op->ft == CTS_F64 ? 2 : 4;
+  const bool march = cts_aligned16(du_exp) && cts_aligned16(U) && (!d.S_lev || cts_aligned16(d.S_lev)) && (d.nlev % vn) == 0;
+  if (!cts_column_overlap_ok(op) || !march) {
     int r = cts_op_column_dss(op, U, t_dss);
     return r != CTS_OK ? r : cts_op_column_T_exp(op, du_exp, nullptr, U, t_exp);
   }
   cts_ctx* ctx = op->ctx;
-  const cts_column_desc& d = op->d;
-  if (!ctx->comm_stream) {
-    CTS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
-    CTS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
-    CTS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
-  }
-  const size_t row = d.nx * (size_t)d.nlev;
-  const size_t es = cts_sizeof(op->ft);
-  char* b = static_cast<char*>(U);
-  // the stage value is complete on the compute stream -> the exchange may start
+  CTS_TRY(cts_ctx_ensure_comm_stream(ctx));
+  if (ctx->nranks > 1 && ctx->peer_mode == 0)  // collective set-up must not happen between the fork and the join
+    CTS_TRY(cts_comm_enable_peer_halo(ctx, d.nx * (size_t)d.nlev * cts_sizeof(op->ft)));
+  // fork: the stage value is complete on the compute stream
   CTS_CUDA(ctx, cudaEventRecord(ctx->ev_compute, ctx->stream));
   CTS_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_compute, 0));
-  CTS_TRY(cts_halo_exchange_on(ctx, ctx->comm_stream, op->ft, row, b + row * es, b + d.ny_local * row * es, b,
-                               b + (d.ny_local + 1) * row * es));
+  {
+    StreamSwap sw(ctx, ctx->comm_stream);
+    CTS_TRY(column_halo_on(op, ctx->comm_stream, U));
+    // the two strips whose stencil reads a ghost row
+    CTS_TRY(column_T_exp_rows(op, du_exp, U, t_exp, 0, kEdgeRows));
+    CTS_TRY(column_T_exp_rows(op, du_exp, U, t_exp, d.ny_local - kEdgeRows, d.ny_local));
+  }
   CTS_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
   // rows whose 5-point stencil stays inside the owned rows: no ghost row is read, nothing the exchange writes is touched
-  constexpr size_t kEdge = 8;
-  int r = column_T_exp_rows(op, du_exp, U, t_exp, kEdge, d.ny_local - kEdge);
-  // (if the marching kernel is not applicable the whole evaluation waits for the ghosts)
+  CTS_TRY(column_T_exp_rows(op, du_exp, U, t_exp, kEdgeRows, d.ny_local - kEdgeRows));
+  CTS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));  // join
+  return CTS_OK;
+}
+
+// dss!(U_s); final update (with the last T_exp! folded in); dss!(u) -- the tail of an IMEX-ARK step (imex_ark.jl:234,79-101,
+// 98).  Second stream: halo(U_s) -> boundary strips of the final update -> halo(u); compute stream: interior rows.
+int cts_column_final_update_overlapped(cts_op_column* op, const cts_final_update_args* s) {
+  if (!op || !s) return CTS_EINVAL;
+  if (!cts_column_final_update_supported(op, s)) return CTS_EUNSUPPORTED;
+  const cts_column_desc& d = op->d;
+  void* U_last = const_cast<void*>(s->U_last);
+  if (!cts_column_overlap_ok(op)) {
+    CTS_TRY(cts_op_column_dss(op, U_last, s->t_exp_last));
+    CTS_TRY(final_update_rows(op, s, 0, d.ny_local));
+    return cts_op_column_dss(op, s->u, s->t_exp_last);
+  }
+  cts_ctx* ctx = op->ctx;
+  CTS_TRY(cts_ctx_ensure_comm_stream(ctx));
+  if (ctx->nranks > 1 && ctx->peer_mode == 0)
+    CTS_TRY(cts_comm_enable_peer_halo(ctx, d.nx * (size_t)d.nlev * cts_sizeof(op->ft)));
+  CTS_CUDA(ctx, cudaEventRecord(ctx->ev_compute, ctx->stream));
+  CTS_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_compute, 0));
+  {
+    StreamSwap sw(ctx, ctx->comm_stream);
+    CTS_TRY(column_halo_on(op, ctx->comm_stream, U_last));
+    CTS_TRY(final_update_rows(op, s, 0, kEdgeRows));
+    CTS_TRY(final_update_rows(op, s, d.ny_local - kEdgeRows, d.ny_local));
+    CTS_TRY(column_halo_on(op, ctx->comm_stream, s->u));
+  }
+  CTS_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+  CTS_TRY(final_update_rows(op, s, kEdgeRows, d.ny_local - kEdgeRows));
   CTS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
-  if (r == CTS_EUNSUPPORTED) return cts_op_column_T_exp(op, du_exp, nullptr, U, t_exp);
-  if (r != CTS_OK) return r;
-  CTS_TRY(column_T_exp_rows(op, du_exp, U, t_exp, 0, kEdge));
-  CTS_TRY(column_T_exp_rows(op, du_exp, U, t_exp, d.ny_local - kEdge, d.ny_local));
   return CTS_OK;
 }

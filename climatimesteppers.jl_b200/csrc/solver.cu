@@ -128,10 +128,7 @@ void newton_free(cts_newton_cache* c) {
 double eps_of(cts_dtype ft) { return ft == CTS_F64 ? std::numeric_limits<double>::epsilon() : (double)std::numeric_limits<float>::epsilon(); }
 double round_to(cts_dtype ft, double v) { return ft == CTS_F64 ? v : (double)(float)v; }
 
-size_t global_length(const cts_ctx* ctx, size_t n) {
-  size_t local = ctx->red_window ? ctx->red_count : n;
-  return local * (size_t)ctx->nranks;
-}
+size_t global_length(const cts_ctx* ctx, size_t n) { return cts_global_length(ctx, n); }
 
 // Krylov.jl sym_givens (real case): [c s; s -c][a; b] = [rho; 0]
 void sym_givens(double a, double b, double& c, double& s, double& rho) {
@@ -681,6 +678,13 @@ struct cts_imex_cache {
   double beta[CTS_MAX_STAGES] = {};
   int nbuffers = 0;
   cts_solver_stats stats{};
+  // CUDA graph of one step (cts_imex_step): captured every step (the host still runs the stage loop, so times,
+  // coefficients and the Jacobian policy are exact), applied to the instantiated graph with cudaGraphExecUpdate and
+  // launched as ONE graph -- the kernels of a step, the halo exchanges and the fork/join with the communication stream
+  // then run back to back without per-launch gaps.
+  int graph_mode = -1;             // -1: decide on first use (on unless CTS_NO_GRAPH is set), 0: off, 1: on
+  cudaGraphExec_t graph_exec = nullptr;
+  uint64_t graph_launches = 0, graph_reinstantiations = 0;
 };
 
 namespace {
@@ -748,9 +752,11 @@ int assign_with_increments(cts_imex_cache* c, void* out, void* out2, double c0, 
   return cts_axpy_n(c->ctx, c->ft, c->n, out, out2, c0, base, g1.n, g2.n, coef, terms, native_flag(c));
 }
 
-int maybe_update_jacobian(cts_imex_cache* c, const void* u, double t, double dt, bool defer = false) {  // async_utils.jl:11-31
+int maybe_update_jacobian(cts_imex_cache* c, const void* u, double t, double dt, bool defer = false,
+                          bool matrix_free = false) {  // async_utils.jl:11-31
   if (!c->f.T_imp || !c->ncfg.present || !c->nm || !c->nm->W) return CTS_OK;
   if (!needs_update(c->ncfg.update_j, CTS_SIG_NEW_TIMESTEP, t)) return CTS_OK;
+  if (matrix_free) return CTS_OK;  // the handler has seen the signal; W is regenerated inside the stage kernels
   if (defer) {  // the first fused stage of this step regenerates W in registers and stores it: no separate pass
     c->w_pending = true;
     c->w_pending_dtg = dt * c->gamma;
@@ -842,6 +848,9 @@ cts_op_column* fusable_column_op(const cts_imex_cache* c) {
   auto* op = static_cast<cts_op_column*>(f.ud);
   if (!op || !cts_column_fusable(op) || cts_op_column_ctx(op) != c->ctx || cts_op_column_dtype(op) != c->ft) return nullptr;
   if (cts_op_column_ndof(op) != c->n) return nullptr;
+  // a matrix-free stage always uses W(dtγ of the stage); with a host handler (UpdateEveryN/UpdateEveryDt) the policy may ask
+  // for a stale W instead, which only the stored form can honour
+  if (cts_op_column_matrix_free(op) && c->ncfg.update_j.fn) return nullptr;
   return op;
 }
 
@@ -851,7 +860,9 @@ int fused_implicit_stage(cts_imex_cache* c, cts_op_column* op, void* U, double c
   // does not depend on the state, so the stage value is not needed to build it).
   const bool mf = cts_op_column_matrix_free(op);
   bool emit_W = false;
-  if (needs_update(c->ncfg.update_j, CTS_SIG_NEW_NEWTON_SOLVE) || needs_update(c->ncfg.update_j, CTS_SIG_NEW_NEWTON_ITERATION)) {
+  const bool upd_solve = needs_update(c->ncfg.update_j, CTS_SIG_NEW_NEWTON_SOLVE);     // newtons_method.jl:620
+  const bool upd_iter = needs_update(c->ncfg.update_j, CTS_SIG_NEW_NEWTON_ITERATION);  // :626 (both are always sent)
+  if (upd_solve || upd_iter) {
     emit_W = !mf;  // W(dtγ of this stage) is produced and stored by the stage kernel itself
     c->w_pending = false;
     c->stats.wfact_evals++;
@@ -918,12 +929,14 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
   const bool has_T_exp = f.T_exp_T_lim != nullptr;
   const bool has_T_imp = f.T_imp != nullptr;
   cts_op_column* fuse_op = fusable_column_op(c);
+  if (fuse_op && !cts_aligned16(u)) fuse_op = nullptr;  // (cache buffers are cudaMalloc'ed; only the caller's u can be off)
   cts_op_column* final_op = final_fusable_column_op(c);
   bool fold_last_texp = false;
+  bool last_dss_deferred = false;  // dss!(U_s) travels with the overlapped final update
   const void* U_last = nullptr;
-  double t_exp_last = 0.0;
+  double t_exp_last = 0.0, t_imp_last = 0.0;
   // (a matrix-free fused stage regenerates W in the kernel: the stored copy is never read)
-  if (!(fuse_op && cts_op_column_matrix_free(fuse_op))) CTS_TRY(maybe_update_jacobian(c, u, t, dt, fuse_op != nullptr));
+  CTS_TRY(maybe_update_jacobian(c, u, t, dt, fuse_op != nullptr, fuse_op && cts_op_column_matrix_free(fuse_op)));
 
   for (int i = 0; i < s; ++i) {
     const double t_exp = t + dt * tab.c_exp[i];
@@ -945,9 +958,13 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
       CTS_TRY(fused_implicit_stage(c, fuse_op, U, 1.0, u, inc_exp, inc_imp, dtg, t_imp, has_imp_terms ? c->T_imp[i] : nullptr));
       // multi-GPU: when the explicit tendency of this stage follows, its interior rows are evaluated while the halo
       // exchange of dss!(U) is in flight (cts_column_dss_T_exp_overlapped); otherwise dss! runs here
-      overlap_dss = has_exp_terms && f.T_exp_T_lim == cts_op_column_T_exp && f.dss == cts_op_column_dss &&
-                    cts_column_overlap_ok(fuse_op) && !(i == s - 1 && final_op);
-      if (!overlap_dss) CTS_TRY(call_dss(c, U, t_imp));
+      const bool can_overlap = has_exp_terms && f.T_exp_T_lim == cts_op_column_T_exp && f.dss == cts_op_column_dss &&
+                               cts_column_overlap_ok(fuse_op);
+      overlap_dss = can_overlap && !(i == s - 1 && final_op);
+      // last stage with the folded final update: halo(U_s), the boundary strips of the update and halo(u) run beside
+      // the interior rows of the update (cts_column_final_update_overlapped)
+      last_dss_deferred = can_overlap && i == s - 1 && final_op == fuse_op && U != u;
+      if (!overlap_dss && !last_dss_deferred) CTS_TRY(call_dss(c, U, t_imp));
       stage_done = true;
     } else if (fuse_op && no_imp && i == 0 && inc_exp.n == 0 && inc_imp.n == 0) {
       U = u;  // `@. U = u` followed only by tendency evaluations: alias instead of copying
@@ -997,6 +1014,7 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
         fold_last_texp = true;  // evaluated inside the final update kernel (its only reader)
         U_last = U;
         t_exp_last = t_exp;
+        t_imp_last = t_imp;
       } else if (overlap_dss) {
         cts_prof_scope ps(c->ctx, CTS_PROF_T_EXP);
         CTS_TRY(cts_column_dss_T_exp_overlapped(fuse_op, c->T_exp[i], U, t_imp, t_exp));
@@ -1047,6 +1065,13 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
     }
     a.compute_native = native_flag(c);
     int r;
+    if (last_dss_deferred && cts_column_final_update_supported(final_op, &a)) {
+      cts_prof_scope ps(c->ctx, CTS_PROF_FINAL_UPDATE);
+      CTS_TRY(cts_column_final_update_overlapped(final_op, &a));  // dss!(U_s); update; dss!(u)
+      c->stats.dss_calls += 2;
+      return CTS_OK;  // (no constrain_state!/cache! hooks on this path: fusable_column_op)
+    }
+    if (last_dss_deferred) CTS_TRY(call_dss(c, const_cast<void*>(U_last), t_imp_last));
     {
       cts_prof_scope ps(c->ctx, CTS_PROF_FINAL_UPDATE);
       r = cts_column_fused_final_update(final_op, &a);
@@ -1089,8 +1114,9 @@ int ssprk_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
   const bool has_T_imp = f.T_imp != nullptr;
   const int native = native_flag(c);
   cts_op_column* fuse_op = fusable_column_op(c);
+  if (fuse_op && !cts_aligned16(u)) fuse_op = nullptr;
   auto beta_c = [&](double b) { return native ? (double)(float)b : b; };
-  if (!(fuse_op && cts_op_column_matrix_free(fuse_op))) CTS_TRY(maybe_update_jacobian(c, u, t, dt, fuse_op != nullptr));
+  CTS_TRY(maybe_update_jacobian(c, u, t, dt, fuse_op != nullptr, fuse_op && cts_op_column_matrix_free(fuse_op)));
 
   for (int i = 0; i < s; ++i) {
     const double t_exp = t + dt * tab.c_exp[i];
@@ -1336,14 +1362,105 @@ int cts_imex_cache_create(cts_ctx* ctx, cts_dtype ft, size_t n, const cts_imex_t
 
 int cts_imex_cache_destroy(cts_imex_cache* c) {
   if (!c) return CTS_EINVAL;
+  if (c->graph_exec) {
+    cudaStreamSynchronize(c->ctx->stream);
+    cudaGraphExecDestroy(c->graph_exec);
+  }
   imex_free(c);
   delete c;
   return CTS_OK;
 }
 
+// A step may be captured when everything it enqueues is the library's own stream-ordered work: the fused column path
+// (all hooks are library operators, direct Newton with max_iters = 1: no host-visible scalars, no user callbacks).
+static bool graph_capturable(cts_imex_cache* c, const void* u) {
+  if (!cts_aligned16(u)) return false;
+  if (c->graph_mode == -1) c->graph_mode = getenv("CTS_NO_GRAPH") ? 0 : 1;
+  if (c->graph_mode != 1 || c->constraint != 0) return false;
+  if (c->ctx->stream == nullptr || c->ctx->stream == cudaStreamLegacy || c->ctx->stream == cudaStreamPerThread) return false;  // not capturable
+  cts_op_column* op = fusable_column_op(c);
+  if (!op) return false;
+  const cts_ode_function& f = c->f;
+  if (f.T_exp_T_lim && f.T_exp_T_lim != cts_op_column_T_exp) return false;
+  if (f.dss && f.dss != cts_op_column_dss) return false;
+  if (f.lim) return false;
+  const cts_update_handler* hs[3] = {&c->ncfg.update_j, &f.update_cache, &f.update_constrain_state};
+  for (auto* h : hs)
+    if (h->fn) return false;  // host handlers may do anything
+  if (c->ctx->nranks > 1 && c->ctx->peer_mode != 1) return false;  // NCCL send/recv stays outside graphs
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(c->ctx->stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return false;  // the caller captures
+  return true;
+}
+
+static int graphed_ark_step(cts_imex_cache* c, void* u, double t, double dt) {
+  cts_ctx* ctx = c->ctx;
+  CTS_TRY(cts_ctx_ensure_comm_stream(ctx));  // created outside the capture
+  if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    c->graph_mode = 0;  // this stream cannot be captured: plain launches from now on
+    return ark_step(c, u, t, dt);
+  }
+  ctx->capturing = true;
+  const int r = ark_step(c, u, t, dt);
+  ctx->capturing = false;
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+  if (r != CTS_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return r;
+  }
+  if (e != cudaSuccess || !graph) {
+    cudaGetLastError();
+    return cts_fail(ctx, CTS_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+  }
+  if (c->graph_exec) {
+    cudaGraphExecUpdateResultInfo info;
+    if (cudaGraphExecUpdate(c->graph_exec, graph, &info) != cudaSuccess) {  // topology changed (dt, policy, buffers)
+      cudaGetLastError();
+      cudaGraphExecDestroy(c->graph_exec);
+      c->graph_exec = nullptr;
+    }
+  }
+  if (!c->graph_exec) {
+    const cudaError_t ei = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+    if (ei != cudaSuccess) {
+      cudaGraphDestroy(graph);
+      c->graph_exec = nullptr;
+      return cts_fail(ctx, CTS_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei));
+    }
+    c->graph_reinstantiations++;
+  }
+  cudaGraphDestroy(graph);
+  CTS_CUDA(ctx, cudaGraphLaunch(c->graph_exec, ctx->stream));
+  c->graph_launches++;
+  return CTS_OK;
+}
+
 int cts_imex_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
   if (!c || !u) return CTS_EINVAL;
-  return c->constraint == 0 ? ark_step(c, u, t, dt) : ssprk_step(c, u, t, dt, dt_is_f32);
+  if (c->constraint == 0) {
+    if (graph_capturable(c, u)) {
+      // collective set-up (IPC mailboxes) cannot happen inside a capture: do it now if the step will exchange halos
+      return graphed_ark_step(c, u, t, dt);
+    }
+    return ark_step(c, u, t, dt);
+  }
+  return ssprk_step(c, u, t, dt, dt_is_f32);
+}
+
+int cts_imex_cache_set_graph(cts_imex_cache* c, int enabled) {
+  if (!c) return CTS_EINVAL;
+  c->graph_mode = enabled ? 1 : 0;
+  return CTS_OK;
+}
+
+int cts_imex_cache_graph_stats(cts_imex_cache* c, uint64_t* launches, uint64_t* instantiations) {
+  if (!c) return CTS_EINVAL;
+  if (launches) *launches = c->graph_launches;
+  if (instantiations) *instantiations = c->graph_reinstantiations;
+  return CTS_OK;
 }
 
 int cts_imex_cache_buffer(cts_imex_cache* c, const char* name, void** dptr) {

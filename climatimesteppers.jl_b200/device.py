@@ -73,6 +73,22 @@ class Context:
     def set_reduction_window(self, offset: int, count: int):
         self.check(self.lib.cts_set_reduction_window(self.handle, offset, count))
 
+    def set_reduction_layout(self, local_offset: int, count: int, global_offset: int, global_count: int, chunk: int = 0):
+        """Shard-invariant reductions (cts_set_reduction_layout): the owned window is a slice of a global index space cut
+        into fixed chunks; 1, 2, 4 or 8 ranks give bit-identical norms/dots."""
+        self.check(self.lib.cts_set_reduction_layout(self.handle, local_offset, count, global_offset, global_count, chunk),
+                   "cts_set_reduction_layout")
+
+    def halo_path(self) -> str:
+        """How `dss!` halo exchanges travel: local copies (1 rank), NCCL send/recv, or the NVLink peer-memory kernel."""
+        p = C.c_int()
+        self.check(self.lib.cts_comm_halo_path(self.handle, C.byref(p)), "cts_comm_halo_path")
+        return {0: "local", 1: "nccl", 2: "peer"}[p.value]
+
+    def enable_peer_halo(self, max_row_bytes: int):
+        self.check(self.lib.cts_comm_enable_peer_halo(self.handle, int(max_row_bytes)), "cts_comm_enable_peer_halo")
+        return self.halo_path()
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.cts_ctx_destroy(self.handle)

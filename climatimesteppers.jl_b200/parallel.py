@@ -53,6 +53,19 @@ class SlabPartition:
         return halo * nx * nlev, self.ny_local * nx * nlev
 
 
+    def reduction_layout(self, nx: int, nlev: int, halo: int = 1, max_chunk: int = 8192):
+        """(local_offset, count, global_offset, global_count, chunk) for `Context.set_reduction_layout`: the chunk is the
+        largest power of two <= max_chunk that divides a row, so every slab of whole rows owns whole chunks and the
+        reduction tree is the same for every rank count."""
+        row = nx * nlev
+        chunk = 1
+        while chunk * 2 <= max_chunk and row % (chunk * 2) == 0:
+            chunk *= 2
+        if chunk < 4:
+            raise ValueError("row size must be a multiple of 4 elements for the shard-invariant reduction layout")
+        return halo * row, self.ny_local * row, self.row0 * row, self.ny_global * row, chunk
+
+
 def attach_communicator(ctx, dist=None):
     """Create the NCCL communicator of the library context: rank 0 makes the unique id, torch.distributed
     (the plumbing; MPI/ClimaComms in the Julia host) broadcasts it, every rank joins."""

@@ -214,6 +214,16 @@ class IMEXCache:
     def set_fusion(self, enabled: bool):
         self.ctx.check(self.ctx.lib.cts_imex_cache_set_fusion(self.handle, int(enabled)))
 
+    def set_graph(self, enabled: bool):
+        """Step through a CUDA graph (captured every step, applied with cudaGraphExecUpdate) when the step is all library
+        kernels and the context's stream is capturable."""
+        self.ctx.check(self.ctx.lib.cts_imex_cache_set_graph(self.handle, int(enabled)))
+
+    def graph_stats(self) -> dict:
+        a, b = C.c_uint64(), C.c_uint64()
+        self.ctx.check(self.ctx.lib.cts_imex_cache_graph_stats(self.handle, C.byref(a), C.byref(b)))
+        return {"graph_launches": int(a.value), "instantiations": int(b.value)}
+
     def step_u(self, integrator):
         u: B200Vector = integrator.u
         self.views.add(u)
@@ -388,3 +398,93 @@ def init_cache(prob, alg, **kwargs):
 def step_u(integrator):
     """``step_u!(integrator)`` (integrators.jl:442-444)."""
     integrator.cache.step_u(integrator)
+
+
+# ---- NewtonsMethod on its own (newtons_method.jl:583-665) ------------------------------------------------------
+class NewtonCache:
+    """``allocate_cache(alg::NewtonsMethod, x_prototype, j_prototype)`` (newtons_method.jl:583-598) for ``B200Vector``
+    states: Δx, f, the Krylov workspace and the checker cache live in the library (``cts_newton_cache_create``);
+    ``j_prototype`` is any object with ``zero()``, ``ldiv(x, b)`` and, for GMRES without a JVP, ``mul(y, x)`` -- the
+    Jacobian type stays the user's, as in the reference."""
+
+    def __init__(self, alg, x_prototype: B200Vector, j_prototype=None):
+        self.ctx, self.alg = x_prototype.ctx, alg
+        self.n, self.dtype = len(x_prototype), x_prototype.dtype
+        self.views = _Views(self.ctx, self.n, self.dtype)
+        self.jac = j_prototype.zero() if j_prototype is not None else None
+        self.pending_exception: Optional[BaseException] = None
+        self.keep: List[Any] = []
+        cfg = alg.to_c(self.keep)
+
+        def ldiv(ud, x, W, b):
+            try:
+                self.jac.ldiv(self.views.get(x), self.views.get(b))
+                return 0
+            except BaseException as e:  # noqa: BLE001
+                self.pending_exception = e
+                return 1
+
+        def jmul(ud, y, W, x):
+            try:
+                self.jac.mul(self.views.get(y), self.views.get(x))
+                return 0
+            except BaseException as e:  # noqa: BLE001
+                self.pending_exception = e
+                return 1
+
+        null = C.cast(None, L.LDIV_FN)
+        self._ldiv = L.LDIV_FN(ldiv) if self.jac is not None else null
+        self._jmul = L.LDIV_FN(jmul) if (self.jac is not None and hasattr(self.jac, "mul")) else null
+        h = C.c_void_p()
+        token = C.c_void_p(id(self.jac)) if self.jac is not None else None
+        self.ctx.check(self.ctx.lib.cts_newton_cache_create(self.ctx.handle, x_prototype.ft, self.n, C.byref(cfg), token,
+                                                            self._ldiv, self._jmul, None, C.byref(h)), "allocate_cache")
+        self.handle, self._cfg = h, cfg
+        alg.configure_cache(self.ctx, h)
+
+    def stats(self) -> dict:
+        s = L.SolverStats()
+        self.ctx.check(self.ctx.lib.cts_newton_cache_stats(self.handle, C.byref(s)))
+        return s.as_dict()
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.ctx.lib.cts_newton_cache_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def allocate_cache(alg, x_prototype: B200Vector, j_prototype=None) -> NewtonCache:
+    return NewtonCache(alg, x_prototype, j_prototype)
+
+
+def solve_newton_(alg, cache: NewtonCache, x: B200Vector, f_, j_=None, prepare_for_f_=None):
+    """``solve_newton!(alg, cache, x, f!, j!, prepare_for_f!)`` (newtons_method.jl:609-665): the iteration, the linear
+    solves (direct / GMRES / JFNK), forcing terms, line search and convergence checks run in the library
+    (``cts_newton_solve``); ``f!(f, x)``, ``j!(j, x)`` and ``prepare_for_f!(x)`` are the caller's."""
+    views = cache.views
+    views.add(x)
+
+    def guard(fn):
+        def cb(*a):
+            try:
+                fn(*a)
+                return 0
+            except BaseException as e:  # noqa: BLE001
+                cache.pending_exception = e
+                return 1
+        return cb
+
+    fcb = L.RESIDUAL_FN(guard(lambda ud, f, xx: f_(views.get(f), views.get(xx))))
+    jcb = L.JAC_FN(guard(lambda ud, W, xx: j_(cache.jac, views.get(xx)))) if (j_ is not None and cache.jac is not None) \
+        else C.cast(None, L.JAC_FN)
+    pcb = L.PREPARE_FN(guard(lambda ud, xx: prepare_for_f_(views.get(xx)))) if prepare_for_f_ is not None \
+        else C.cast(None, L.PREPARE_FN)
+    r = cache.ctx.lib.cts_newton_solve(cache.handle, x.ptr, fcb, jcb, pcb, None)
+    exc, cache.pending_exception = cache.pending_exception, None
+    if exc is not None:
+        raise exc
+    cache.ctx.check(r, "solve_newton!")
+    return x

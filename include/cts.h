@@ -145,8 +145,9 @@ int cts_lincomb(cts_ctx* ctx, cts_dtype ft, size_t n, void* out, int k, const do
 
 /* ------------------------------------------------------------------ reductions (R1-R4) ------- */
 /* `norm`, `sum(x_i -> 1 + abs(x_i), x)` and Krylov dots (newtons_method.jl:108,120,135,265; convergence_checker.jl:81-82).
- * Deterministic two-stage tree in Float64; if a communicator is attached the partial sums are
- * all-reduced over NCCL before the value is returned.  These synchronise the stream (host scalar). */
+ * Deterministic tree in Float64 defined on fixed chunks of the element index (csrc/reduce.cu): independent of the SM
+ * count, of the operands' alignment and -- with cts_set_reduction_layout -- of the number of ranks.  These synchronise
+ * the stream (host scalar). */
 int cts_dot(cts_ctx* ctx, cts_dtype ft, size_t n, const void* x, const void* y, double* host_out);
 int cts_nrm2(cts_ctx* ctx, cts_dtype ft, size_t n, const void* x, double* host_out);
 int cts_sum1pabs(cts_ctx* ctx, cts_dtype ft, size_t n, const void* x, double* host_out);
@@ -160,6 +161,15 @@ int cts_axpby_dot(cts_ctx* ctx, cts_dtype ft, size_t n, double a, const void* x,
 int cts_div_scalar_nrm2(cts_ctx* ctx, cts_dtype ft, size_t n, void* y, const void* x, double denom, double* host_norm);
 /* restrict reductions to the owned (non-ghost) element range [offset, offset+count) of each vector */
 int cts_set_reduction_window(cts_ctx* ctx, size_t offset, size_t count);
+/* Shard-invariant reductions of a distributed vector: this rank's window [local_offset, local_offset+count) is the slice
+ * [global_offset, global_offset+count) of a global index space of `global_count` elements, cut into chunks of `chunk`
+ * elements (a power of two, 0 = default 8192; every rank must own whole chunks).  The per-chunk partial sums are
+ * exchanged and folded in global chunk order on every rank, so dot/nrm2/sum1pabs -- and everything downstream of them
+ * (JVP step sizes, GMRES, convergence checks) -- are bit-identical for 1, 2, 4 or 8 ranks.  `length(x)` in
+ * ForwardDiffStepSize3 / GMRES itmax (newtons_method.jl:135,445) becomes `global_count`. */
+int cts_set_reduction_layout(cts_ctx* ctx, size_t local_offset, size_t count, size_t global_offset, size_t global_count,
+                             size_t chunk);
+int cts_reduction_global_length(cts_ctx* ctx, size_t n, size_t* out);
 
 /* ------------------------------------------------------------------ batched tridiagonal (K4) -- */
 /* The reference has no tridiagonal type of its own; `ldiv!(Δx, W, f)` (newtons_method.jl:633) dispatches on
@@ -278,6 +288,12 @@ int cts_imex_cache_nbuffers(cts_imex_cache* c, int* n_state_sized);
 int cts_imex_cache_stats(cts_imex_cache* c, cts_solver_stats* out);
 /* 1: let the engine use fused column kernels when it recognises library operators (default 1) */
 int cts_imex_cache_set_fusion(cts_imex_cache* c, int enabled);
+
+/* 1 (default unless the environment variable CTS_NO_GRAPH is set): a step whose hooks are all library operators (the fused
+ * column path) is captured into a CUDA graph every call, applied to the instantiated graph with cudaGraphExecUpdate and
+ * launched as one graph; needs a capturable (non-default) stream, otherwise plain launches are used. */
+int cts_imex_cache_set_graph(cts_imex_cache* c, int enabled);
+int cts_imex_cache_graph_stats(cts_imex_cache* c, uint64_t* graph_launches, uint64_t* instantiations);
 
 /* `init_cache(prob, alg::LowStorageRungeKutta2N)` (lsrk.jl:49-52) + `step_u!` (lsrk.jl:56-67).
  * A, B, C are given in Float64 holding values already rounded to the state eltype (lsrk.jl:51). */
@@ -413,6 +429,13 @@ int cts_comm_rank(cts_ctx* ctx, int* rank, int* nranks);
 /* halo exchange of `count` elements: send `send_lo` to rank-1 (their `recv_hi`), `send_hi` to rank+1 (periodic ring) */
 int cts_halo_exchange(cts_ctx* ctx, cts_dtype ft, size_t count, const void* send_lo, const void* send_hi,
                       void* recv_lo, void* recv_hi);
+/* Collective over the communicator: sets up the NVLink peer-memory path of the halo exchange for rows of up to
+ * `max_row_bytes` (CUDA IPC mailboxes mapped by the two ring neighbours; one kernel per exchange pushes the boundary rows
+ * with 16-byte stores over NVLink and signals with system-scope atomics -- no NCCL call on the data path).  If any rank
+ * cannot map its neighbours every rank keeps the NCCL send/recv path.  cts_comm_halo_path: 0 = single rank (local
+ * copies), 1 = NCCL send/recv, 2 = peer-memory kernel. */
+int cts_comm_enable_peer_halo(cts_ctx* ctx, size_t max_row_bytes);
+int cts_comm_halo_path(cts_ctx* ctx, int* path);
 /* in-stream sum all-reduce of `count` doubles on the device */
 int cts_allreduce_sum_f64(cts_ctx* ctx, double* dev_buf, size_t count);
 int cts_allreduce_max_f64_host(cts_ctx* ctx, double* host_val); /* EveryXWallTimeSeconds' allreduce(max), Callbacks.jl:59,72 */

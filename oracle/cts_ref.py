@@ -254,9 +254,124 @@ def tableau(name: str, **kw) -> IMEXTableau:
             a_exp=[[0, 0, 0, 0], [0, 0, 0, 0], [0, 1, 0, 0], [0, 1 / 4, 1 / 4, 0]], b_exp=[0, 1 / 6, 1 / 6, 2 / 3],
             a_imp=[[al, 0, 0, 0], [-al, al, 0, 0], [0, 1 - al, al, 0], [be, et, 1 / 2 - al - be - et, al]],
             b_imp=[0, 1 / 6, 1 / 6, 2 / 3])
+    if name in _IMKG:  # :399-607 (IMKGTableau :378-389)
+        return _imkg_tableau(*_IMKG[name]())
+    if name == "DBM453":  # :789-822
+        g = 0.32591194130117247
+        bb = [0.87795339639076675, -0.72692641526151547, 0.7520413715737272, -0.22898029400415088, g]
+        return IMEXTableau(
+            a_exp=[[0, 0, 0, 0, 0],
+                   [0.10306208811591838, 0, 0, 0, 0],
+                   [-0.94124866143519894, 1.6626399742527356, 0, 0, 0],
+                   [-1.3670975201437765, 1.3815852911016873, 1.2673234025619065, 0, 0],
+                   [-0.81287582068772448, 0.81223739060505738, 0.90644429603699305, 0.094194134045674111, 0]],
+            b_exp=bb,
+            a_imp=[[0, 0, 0, 0, 0],
+                   [-0.2228498531852541, g, 0, 0, 0],
+                   [-0.46801347074080545, 0.86349284225716961, g, 0, 0],
+                   [-0.46509906651927421, 0.81063103116959553, 0.61036726756832357, g, 0],
+                   bb])
+    if name == "HOMMEM1":  # :831-856
+        ae = np.zeros((6, 6))
+        ai = np.zeros((6, 6))
+        for i, v in enumerate((1 / 5, 1 / 5, 1 / 3, 1 / 2, 1)):
+            ae[i + 1, i] = v
+        for i, v in enumerate((1 / 5, 1 / 5, 1 / 3, 1 / 2)):
+            ai[i + 1, i + 1] = v
+        ai[5, :] = [5 / 18, 5 / 18, 0, 0, 0, 8 / 18]
+        return IMEXTableau(a_exp=ae, a_imp=ai)
+    if name == "ARK2GKC":  # :866-881
+        a32 = (1 / 2 + s2 / 3) if kw.get("paper_version", False) else 1 / 2
+        return IMEXTableau(a_exp=[[0, 0, 0], [2 - s2, 0, 0], [1 - a32, a32, 0]], b_exp=[s2 / 4, s2 / 4, 1 - s2 / 2],
+                           a_imp=[[0, 0, 0], [1 - s2 / 2, 1 - s2 / 2, 0], [s2 / 4, s2 / 4, 1 - s2 / 2]])
+    if name in ("ARK437L2SA1", "ARK548L2SA2"):  # :890-1066: Rational{Int64} tables (oracle/kc2019_tables.json)
+        t = _kc2019()[name]
+        q = lambda p: p[0] / p[1]  # Float64(num // den): both < 2^53, so this is the correctly rounded quotient
+        b = [q(p) for p in t["b"]]
+        c = [q(p) for p in t["c"]]
+        return IMEXTableau(a_exp=[[q(p) for p in r] for r in t["a_exp"]], a_imp=[[q(p) for p in r] for r in t["a_imp"]],
+                           b_exp=b, b_imp=b, c_exp=c, c_imp=c)
+    if name in _EXPLICIT:  # explicit_tableaus.jl:82-124; IMEXTableau((; a, b, c)) = IMEXTableau(a, b, c, a, b, c) (:75)
+        a, b = _EXPLICIT[name]
+        return IMEXTableau(a_exp=a, a_imp=a, b_exp=b, b_imp=b)
     raise KeyError(name)
 
 
+def _imkg_tableau(al, alh, dh, be=None):
+    """IMKGTableau(α, α̂, δ̂, β) (imex_tableaus.jl:375-389): s = length(α̂) + 1;
+    a_exp[i,j] = α[j] on the first sub-diagonal, β[i-2] in the first column of rows i > 2;
+    a_imp likewise with α̂, plus δ̂[i-1] on the diagonal of rows 1 < i <= length(α̂)  (1-based indices)."""
+    s = len(alh) + 1
+    be = (0.0,) * len(dh) if be is None else be
+    ae, ai = np.zeros((s, s)), np.zeros((s, s))
+    for i in range(1, s + 1):
+        for j in range(1, s + 1):
+            if i == j + 1:
+                ae[i - 1, j - 1] = al[j - 1]
+                ai[i - 1, j - 1] = alh[j - 1]
+            elif i > 2 and j == 1:
+                ae[i - 1, j - 1] = be[i - 3]
+                ai[i - 1, j - 1] = be[i - 3]
+            elif 1 < i <= len(alh) and i == j:
+                ai[i - 1, j - 1] = dh[i - 2]
+    return IMEXTableau(a_exp=ae, a_imp=ai)
+
+
+_R2, _R3 = math.sqrt(2.0), math.sqrt(3.0)
+_A5 = (1 / 4, 1 / 6, 3 / 8, 1 / 2, 1)  # α of the five-stage IMKG25x family
+_IMKG = {  # name -> (α, α̂, δ̂[, β]) as written at imex_tableaus.jl:399-607
+    "IMKG232a": lambda: ((1 / 2, 1 / 2, 1), (0, -1 / 2 + _R2 / 2, 1), (1 - _R2 / 2, 1 - _R2 / 2)),
+    "IMKG232b": lambda: ((1 / 2, 1 / 2, 1), (0, -1 / 2 - _R2 / 2, 1), (1 + _R2 / 2, 1 + _R2 / 2)),
+    "IMKG242a": lambda: ((1 / 4, 1 / 3, 1 / 2, 1), (0, 0, -1 / 2 + _R2 / 2, 1), (0, 1 - _R2 / 2, 1 - _R2 / 2)),
+    "IMKG242b": lambda: ((1 / 4, 1 / 3, 1 / 2, 1), (0, 0, -1 / 2 - _R2 / 2, 1), (0, 1 + _R2 / 2, 1 + _R2 / 2)),
+    "IMKG243a": lambda: ((1 / 4, 1 / 3, 1 / 2, 1), (0, 1 / 6, -_R3 / 6, 1), (1 / 2 + _R3 / 6,) * 3),
+    "IMKG252a": lambda: (_A5, (0, 0, 0, -1 / 2 + _R2 / 2, 1), (0, 0, 1 - _R2 / 2, 1 - _R2 / 2)),
+    "IMKG252b": lambda: (_A5, (0, 0, 0, -1 / 2 - _R2 / 2, 1), (0, 0, 1 + _R2 / 2, 1 + _R2 / 2)),
+    "IMKG253a": lambda: (_A5, (0, 0, _R3 / 4 * (1 - _R3 / 3) * ((1 + _R3 / 3) ** 2 - 2), _R3 / 6, 1),
+                         (0, 1 / 2 - _R3 / 6, 1 / 2 - _R3 / 6, 1 / 2 - _R3 / 6)),
+    "IMKG253b": lambda: (_A5, (0, 0, _R3 / 4 * (1 + _R3 / 3) * ((1 - _R3 / 3) ** 2 - 2), -_R3 / 6, 1),
+                         (0, 1 / 2 + _R3 / 6, 1 / 2 + _R3 / 6, 1 / 2 + _R3 / 6)),
+    "IMKG254a": lambda: (_A5, (0, -3 / 10, 5 / 6, -3 / 2, 1), (-1 / 2, 1, 1, 2)),
+    "IMKG254b": lambda: (_A5, (0, -1 / 20, 5 / 4, -1 / 2, 1), (-1 / 2, 1, 1, 1)),
+    "IMKG254c": lambda: (_A5, (0, 1 / 20, 5 / 36, 1 / 3, 1), (1 / 6, 1 / 6, 1 / 6, 1 / 6)),
+    "IMKG342a": lambda: ((1 / 4, 2 / 3, 1 / 3, 3 / 4), (0, 1 / 6 - _R3 / 6, -1 / 6 - _R3 / 6, 3 / 4),
+                         (0, 1 / 2 + _R3 / 6, 1 / 2 + _R3 / 6), (0, 1 / 3, 1 / 4)),
+    "IMKG343a": lambda: ((1 / 4, 2 / 3, 1 / 3, 3 / 4), (0, -1 / 3, -2 / 3, 3 / 4), (-1 / 3, 1, 1), (0, 1 / 3, 1 / 4)),
+}
+_EXPLICIT = {  # name -> (a, b)
+    "SSP22Heuns": ([[0, 0], [1, 0]], [1 / 2, 1 / 2]),
+    "SSP33ShuOsher": ([[0, 0, 0], [1, 0, 0], [1 / 4, 1 / 4, 0]], [1 / 6, 1 / 6, 2 / 3]),
+    "RK4": ([[0, 0, 0, 0], [1 / 2, 0, 0, 0], [0, 1 / 2, 0, 0], [0, 0, 1, 0]], [1 / 6, 1 / 3, 1 / 3, 1 / 6]),
+}
+_KC2019 = None
+
+
+def _kc2019():
+    global _KC2019
+    if _KC2019 is None:
+        import json
+        import os
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "kc2019_tables.json")) as fh:
+            _KC2019 = json.load(fh)
+    return _KC2019
+
+
+IMEX_NAMES = ("ARS111", "ARS121", "ARS122", "ARS232", "ARS222", "IMKG232a", "IMKG232b", "IMKG242a", "IMKG242b", "IMKG243a",
+              "IMKG252a", "IMKG252b", "IMKG253a", "IMKG253b", "IMKG254a", "IMKG254b", "IMKG254c", "HOMMEM1", "ARS233",
+              "ARS343", "ARS443", "IMKG342a", "IMKG343a", "DBM453", "ARK2GKC", "ARK437L2SA1", "ARK548L2SA2", "SSP222",
+              "SSP322", "SSP332", "SSP333", "SSP433")  # test/solvers/imex_ark.jl:11-44
+EXPLICIT_NAMES = ("SSP22Heuns", "SSP33ShuOsher", "RK4")  # test/solvers/explicit_rk.jl:51-55
+# imex_convergence_orders (test/utils/convergence_utils.jl:20-49): (implicit only, explicit only, both)
+CONVERGENCE_ORDERS = {
+    "ARS111": (1, 1, 1), "ARS121": (1, 1, 1), "ARS122": (2, 2, 2), "ARS222": (2, 2, 2), "ARS232": (2, 3, 2),
+    "ARS233": (3, 3, 3), "ARS343": (3, 4, 3), "ARS443": (3, 3, 3), "IMKG232a": (2, 2, 2), "IMKG232b": (2, 2, 2),
+    "IMKG242a": (2, 4, 2), "IMKG242b": (2, 4, 2), "IMKG243a": (2, 4, 2), "IMKG252a": (2, 2, 2), "IMKG252b": (2, 2, 2),
+    "IMKG253a": (2, 2, 2), "IMKG253b": (2, 2, 2), "IMKG254a": (2, 2, 2), "IMKG254b": (2, 2, 2), "IMKG254c": (2, 2, 2),
+    "IMKG342a": (3, 4, 3), "IMKG343a": (3, 4, 3), "SSP222": (2, 2, 2), "SSP322": (2, 2, 2), "SSP332": (2, 3, 2),
+    "SSP333": (3, 3, 3), "SSP433": (3, 3, 3), "DBM453": (3, 3, 3), "HOMMEM1": (2, 3, 2), "ARK2GKC": (2, 2, 2),
+    "ARK437L2SA1": (4, 4, 4), "ARK548L2SA2": (5, 5, 5), "SSP22Heuns": (2, 2, 2), "SSP33ShuOsher": (3, 3, 3),
+    "RK4": (4, 4, 4), "SSPKnoth": (2, 3, 2),
+}
 SSP_NAMES = ("SSP222", "SSP322", "SSP332", "SSP333", "SSP433")  # default_constraint = SSP (:646)
 
 
@@ -330,7 +445,8 @@ def assign_fused_increment(U, u, dt, coeffs, tends, cdtype=np.float64):
 # --------------------------------------------------------------------------------------
 # Newton / Krylov  (src/nl_solvers/newtons_method.jl)
 # --------------------------------------------------------------------------------------
-_RED_BLOCKS, _RED_THREADS = 1184, 256  # csrc/cts_internal.h: kReduceBlocks x kReduceThreads
+_RED_THREADS = 256      # csrc/cts_internal.h: kReduceThreads
+REDUCTION_CHUNK = 8192  # csrc/cts_internal.h: kReduceChunk (cts_set_reduction_layout may choose another power of two)
 
 
 def _warp_tree(a):
@@ -349,31 +465,37 @@ def _block_tree(acc):
     return w[..., 0] + w[..., 1]
 
 
-def tree_sum(terms: np.ndarray, vn: int = 2) -> float:
+def tree_sum(terms: np.ndarray, vn: int = 2, chunk: Optional[int] = None) -> float:
     """The library's deterministic reduction order (csrc/reduce.cu), restated so that norms and dots --
     and everything downstream of them (JVP step sizes, GMRES) -- are bit-identical on both sides.
     LinearAlgebra.norm's own order is implementation defined, so this fixed tree IS the
-    specification: thread t of a fixed 1184x256 grid accumulates the 16-byte vectors t, t+T, t+2T, ...
-    (elements of a vector in order), then a scalar tail, then warp/block trees, then the last block folds
-    the per-block partials (thread t takes partials t, t+256, ...) with the same tree.
+    specification.  It is defined on the GLOBAL element index, hence independent of any sharding: the domain is
+    cut into chunks of `chunk` elements; within a chunk thread t of 256 accumulates (from 0) the 16-byte vectors
+    t, t+256, ... (elements of a vector in order), then warp/block trees give the chunk partial; the chunk
+    partials are folded in order by one block (thread t takes partials t, t+256, ...) with the same tree.
     `terms` are the Float64 summands; `vn` = elements per 16-byte vector (2 for Float64, 4 for Float32)."""
+    chunk = int(chunk or REDUCTION_CHUNK)
     v = np.ascontiguousarray(terms, dtype=np.float64).ravel()
-    T = _RED_BLOCKS * _RED_THREADS
     n = v.size
-    acc = np.zeros(T)
-    nvec = n // vn
-    for r in range(0, nvec, T):
-        chunk = v[r * vn:min(r + T, nvec) * vn].reshape(-1, vn)
+    nc = max(1, -(-n // chunk))
+    rounds = max(1, -(-(chunk // vn) // _RED_THREADS))
+    per = rounds * _RED_THREADS * vn            # padded chunk (absent elements add +0.0, which is exact)
+    buf = np.zeros((nc, per))
+    full = n // chunk
+    if full:
+        buf[:full, :chunk] = v[:full * chunk].reshape(full, chunk)
+    if n - full * chunk:
+        buf[full, :n - full * chunk] = v[full * chunk:]
+    buf = buf.reshape(nc, rounds, _RED_THREADS, vn)
+    acc = np.zeros((nc, _RED_THREADS))
+    for r in range(rounds):
         for e in range(vn):
-            acc[:chunk.shape[0]] = acc[:chunk.shape[0]] + chunk[:, e]
-    for r in range(nvec * vn, n, T):
-        chunk = v[r:min(r + T, n)]
-        acc[:chunk.size] = acc[:chunk.size] + chunk
-    partials = _block_tree(acc.reshape(_RED_BLOCKS, _RED_THREADS))  # [1184]
+            acc = acc + buf[:, r, :, e]
+    partials = _block_tree(acc)  # [nc]
     fin = np.zeros(_RED_THREADS)
-    for b0 in range(0, _RED_BLOCKS, _RED_THREADS):
-        chunk = partials[b0:b0 + _RED_THREADS]
-        fin[:chunk.size] = fin[:chunk.size] + chunk
+    for b0 in range(0, nc, _RED_THREADS):
+        c = partials[b0:b0 + _RED_THREADS]
+        fin[:c.size] = fin[:c.size] + c
     return float(_block_tree(fin))
 
 
@@ -841,9 +963,9 @@ class IMEXAlgorithm:
 
 
 def imex_algorithm(name, newtons_method, constraint=None, **kw):
-    tab = tableau(name, **{k: v for k, v in kw.items() if k == "beta"})
-    if constraint is None:
-        constraint = "SSP" if name in SSP_NAMES else "Unconstrained"
+    tab = tableau(name, **{k: v for k, v in kw.items() if k in ("beta", "paper_version")})
+    if constraint is None:  # default_constraint: SSP for IMEXSSPRK and SSPRK names (imex_tableaus.jl:646, explicit_tableaus.jl:70)
+        constraint = "SSP" if name in SSP_NAMES or name in ("SSP22Heuns", "SSP33ShuOsher") else "Unconstrained"
     return IMEXAlgorithm(tab, newtons_method, constraint, name,
                          kw.get("cast_tableau_to_state_eltype", False))
 

@@ -1,6 +1,8 @@
 """Launched by torchrun (one rank per GPU): config C5 in miniature.  Every rank steps its slab of the column
-problem on its GPU (library dss! = NCCL halo exchange); rank 0 gathers the owned rows and compares them with the
-single-process numpy oracle of the GLOBAL problem.  Also checks the all-reduced reductions and a sharded JFNK step."""
+problem on its GPU (library dss! = NVLink peer-memory halo kernel, or NCCL send/recv with CTS_HALO_NCCL=1); rank 0 gathers
+the owned rows and compares them with the single-process numpy oracle of the GLOBAL problem -- bit for bit, including the
+sharded JFNK step: reductions use the shard-invariant chunk layout (cts_set_reduction_layout), so dots, norms, the JVP step
+size and GMRES see the same bits for any rank count."""
 import os
 import sys
 
@@ -41,7 +43,8 @@ def main():
         u = dev(T0)
         op.dss(u, None, 0.0)
         off, cnt = part.owned_window(nx, nlev)
-        ctx.set_reduction_window(off, cnt)
+        layout = part.reduction_layout(nx, nlev)
+        ctx.set_reduction_layout(*layout)
         nm_kw = dict(newton)
         if krylov:
             nm_kw["krylov_method"] = cts.KrylovMethod(jacobian_free_jvp=cts.ForwardDiffJVP(), forcing_term=cts.ConstantForcing(1e-3), itmax=30)
@@ -67,6 +70,7 @@ def main():
             uo = Tg.copy()
             model.dss(uo, None, 0.0)
             R.REDUCTION_WINDOW = (nx * nlev, ny_g * nx * nlev)  # norms/dots over owned rows only, like the shards
+            chunk_saved, R.REDUCTION_CHUNK = R.REDUCTION_CHUNK, layout[4]
             o_kw = dict(newton)
             if krylov:
                 o_kw["krylov_method"] = R.KrylovMethod(jacobian_free_jvp=R.ForwardDiffJVP(), forcing_term=R.ConstantForcing(1e-3), itmax=30)
@@ -76,19 +80,21 @@ def main():
                 step(uo, None, t, dt)
                 t += dt
             R.REDUCTION_WINDOW = None
+            onorm = None
             want = uo[nx * nlev:-nx * nlev]
             err = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
             exact = bool(np.array_equal(got, want))
-            nerr = abs(nrm - float(np.linalg.norm(want))) / float(np.linalg.norm(want))
-            # the all-reduce changes the summation order of every dot/norm by a few ulp and the finite-difference JVP
-            # amplifies that (its own noise is ~1e-6 of ||Jv|| at this size): Newton-Krylov parity is a tolerance
-            tol = 0.0 if not krylov else 1e-6
-            good = (exact if not krylov else err <= tol) and nerr < (1e-13 if not krylov else tol)
+            R.REDUCTION_WINDOW = (nx * nlev, ny_g * nx * nlev)
+            onorm = R.norm2(uo)   # the oracle's tree over the owned rows == the sharded tree, bit for bit
+            R.REDUCTION_WINDOW = None
+            R.REDUCTION_CHUNK = chunk_saved
+            nerr = abs(nrm - onorm) / onorm
+            good = exact and nrm == onorm
             ok = ok and good
             st = integ.cache.stats()
             good = good and np.isfinite(got).all() and (not krylov or st["krylov_iters"] < 30 * st["newton_iters"])
             ok = ok and good
-            print(f"[{world} ranks] {name} rows/rank={ny_rank} nonlinear={nonlinear} krylov={krylov}: rel err {err:.3e} bit-exact={exact} krylov_iters={st['krylov_iters']} "
+            print(f"[{world} ranks, halo={ctx.halo_path()}, graph_launches={integ.cache.graph_stats()['graph_launches']}] {name} rows/rank={ny_rank} nonlinear={nonlinear} krylov={krylov}: rel err {err:.3e} bit-exact={exact} krylov_iters={st['krylov_iters']} "
                   f"norm rel err {nerr:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
         dist.barrier()
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")

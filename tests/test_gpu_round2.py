@@ -1,0 +1,172 @@
+"""GPU parity for the round-2 machinery: chunked shard-invariant reductions, the CUDA-graph step, the halo/compute
+overlap (fork/join with the communication stream) on one rank, and unaligned states (fallback off the fused stage)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import cts_models as M  # noqa: E402
+from ref_problems import R  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def cts():
+    import cts_b200
+    return cts_b200
+
+
+def _column_problem(cts, ctx, nlev, nx, ny, dtype=np.float64, nu=1.0):
+    K, T0, S = M.column_inputs(nlev, nx, ny, 0, ny, 1)
+    K, T0, S = K.astype(dtype), T0.astype(dtype), S.astype(dtype)
+    dev = lambda a: cts.B200Vector.from_host(a, ctx)
+    op = cts.ColumnOperator(nlev, nx, ny, dev(K), S_lev=dev(S), nu=nu, halo=1, ctx=ctx)
+    u = dev(T0)
+    op.dss(u, None, 0.0)
+    model = M.ColumnModel(nlev, nx, ny, K, S_lev=S, nu=nu, halo=1)
+    uo = T0.copy()
+    model.dss(uo, None, 0.0)
+    return op, u, model, uo
+
+
+# ------------------------------------------------------------------ reductions ------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,chunk", [(1, 0), (7, 0), (8191, 0), (8192, 0), (8193, 0), (100003, 0), (1 << 20, 0), (4096 * 3, 64),
+                                     (5000, 4), (1 << 18, 1 << 14)])
+def test_chunked_reduction_tree_equals_oracle(cts, dtype, n, chunk):
+    # csrc/reduce.cu vs cts_ref.tree_sum: norm / dot / sum(1+|x|) bit for bit, default and explicit chunk sizes
+    ctx = cts.Context.default()
+    x = (M.fill_hash(n, 11) - 0.5).astype(dtype)
+    y = (M.fill_hash(n, 12) - 0.25).astype(dtype)
+    dx, dy = cts.B200Vector.from_host(x), cts.B200Vector.from_host(y)
+    old = R.REDUCTION_CHUNK
+    try:
+        if chunk:
+            ctx.set_reduction_layout(0, n, 0, n, chunk)
+            R.REDUCTION_CHUNK = chunk
+        assert dx.norm() == R.norm2(x)
+        assert dx.dot(dy) == R.dot(x, y)
+        assert dx.sum1pabs() == R.sum1pabs(x)
+    finally:
+        R.REDUCTION_CHUNK = old
+        ctx.set_reduction_window(0, 0)
+
+
+def test_reduction_is_independent_of_alignment(cts):
+    # the accumulation order is defined on element indices, not on 16-byte vectors of the pointer: a view that starts
+    # 8 bytes off gives the same bits as an aligned copy
+    n = 50001
+    x = M.fill_hash(n + 1, 5) - 0.5
+    base = cts.B200Vector.from_host(x)
+    shifted = cts.B200Vector(base.tensor[1:], base.ctx)
+    aligned = cts.B200Vector.from_host(x[1:])
+    assert shifted.ptr % 16 == 8 and aligned.ptr % 16 == 0
+    assert shifted.norm() == aligned.norm() == R.norm2(x[1:])
+    assert shifted.dot(shifted) == aligned.dot(aligned)
+
+
+def test_layout_rejects_partial_chunks(cts):
+    ctx = cts.Context.default()
+    with pytest.raises(Exception):
+        ctx.set_reduction_layout(0, 100, 50, 1000, 64)   # global offset not a multiple of the chunk
+    with pytest.raises(Exception):
+        ctx.set_reduction_layout(0, 100, 0, 1000, 64)    # owned range ends inside a chunk that is not the last
+    ctx.set_reduction_window(0, 0)
+
+
+def test_windowed_layout_matches_oracle_window(cts):
+    # the owned window of a slab (ghost rows excluded) with the chunk a row divides: same bits as the oracle's window
+    ctx = cts.Context.default()
+    nx, nlev, ny = 4, 16, 6
+    part = cts.SlabPartition(ny, 1, 0)
+    lay = part.reduction_layout(nx, nlev)
+    assert lay == (64, 384, 0, 384, 64)
+    x = M.fill_hash((ny + 2) * nx * nlev, 3) - 0.5
+    dx = cts.B200Vector.from_host(x)
+    old = R.REDUCTION_CHUNK
+    try:
+        ctx.set_reduction_layout(*lay)
+        R.REDUCTION_WINDOW, R.REDUCTION_CHUNK = (lay[0], lay[1]), lay[4]
+        assert dx.norm() == R.norm2(x)
+        assert dx.sum1pabs() == R.sum1pabs(x)
+    finally:
+        R.REDUCTION_WINDOW, R.REDUCTION_CHUNK = None, old
+        ctx.set_reduction_window(0, 0)
+
+
+# ------------------------------------------------------------------ CUDA-graph step + overlap ----------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("ny", [8, 40])
+def test_graph_step_on_private_stream_is_bit_exact(cts, dtype, ny):
+    # a capturable (non-default) stream: every step is captured, applied with cudaGraphExecUpdate and launched as one graph;
+    # ny = 40 also takes the fork/join overlap of dss! with the interior rows (T_exp! and the final update)
+    import torch
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        ctx = cts.Context(torch.cuda.current_device())
+        nlev, nx = 16, 8
+        op, u, model, uo = _column_problem(cts, ctx, nlev, nx, ny, dtype)
+        alg = cts.IMEXAlgorithm(cts.ARS343(), cts.NewtonsMethod(max_iters=1, update_j=cts.UpdateEvery(cts.NewTimeStep)))
+        integ = cts.init(cts.ODEProblem(op.ode_function(), u, (0.0, 1e9), None), alg, dt=0.01, save=False)
+        _, step = R.make_stepper(model.ode_function(), R.imex_algorithm("ARS343", R.NewtonsMethod(
+            max_iters=1, update_j=R.UpdateEvery("NewTimeStep"))), uo)
+        t = 0.0
+        try:
+            for k, dt in enumerate((0.01, 0.01, 0.004, 0.01)):   # a changed dt changes kernel arguments, not the topology
+                cts.set_dt_(integ, dt)
+                cts.step_(integ)
+                step(uo, None, t, dt)
+                t += dt
+                np.testing.assert_array_equal(u.to_host(), uo)
+            gs = integ.cache.graph_stats()
+            assert gs["graph_launches"] == 4 and gs["instantiations"] == 1, gs
+            # same results without graphs
+            integ.cache.set_graph(False)
+            cts.step_(integ)
+            step(uo, None, t, 0.01)
+            np.testing.assert_array_equal(u.to_host(), uo)
+            assert integ.cache.graph_stats()["graph_launches"] == 4
+        finally:   # library objects that enqueue on `stream` must go before the stream does
+            ctx.sync()
+            del integ, op, u
+
+
+def test_overlap_on_default_stream_is_bit_exact(cts):
+    # legacy default stream: not capturable -> plain launches, but the overlapped dss!/T_exp!/final-update path still runs
+    ctx = cts.Context.default()
+    op, u, model, uo = _column_problem(cts, ctx, 16, 8, 40)
+    alg = cts.IMEXAlgorithm(cts.ARS343(), cts.NewtonsMethod(max_iters=1))
+    integ = cts.init(cts.ODEProblem(op.ode_function(), u, (0.0, 1e9), None), alg, dt=0.01, save=False)
+    _, step = R.make_stepper(model.ode_function(), R.imex_algorithm("ARS343", R.NewtonsMethod(max_iters=1)), uo)
+    for k in range(3):
+        cts.step_(integ)
+        step(uo, None, 0.01 * k, 0.01)
+    np.testing.assert_array_equal(u.to_host(), uo)
+    assert integ.cache.graph_stats()["graph_launches"] == 0
+    st = integ.cache.stats()
+    assert st["fused_stage_launches"] == 9 and st["dss_calls"] == 12
+
+
+def test_unaligned_state_falls_back_to_the_generic_path(cts):
+    # a state that starts 8 bytes off a 16-byte boundary cannot take the fused stage; the step must still
+    # succeed (pass by pass) and give the oracle's bits
+    ctx = cts.Context.default()
+    nlev, nx, ny = 16, 4, 6
+    K, T0, S = M.column_inputs(nlev, nx, ny, 0, ny, 1)
+    dev = lambda a: cts.B200Vector.from_host(a, ctx)
+    op = cts.ColumnOperator(nlev, nx, ny, dev(K), S_lev=dev(S), nu=1.0, halo=1, ctx=ctx)
+    big = cts.B200Vector.zeros(T0.size + 1, np.float64, ctx)
+    u = cts.B200Vector(big.tensor[1:], ctx)
+    assert u.ptr % 16 == 8
+    u.tensor.copy_(dev(T0).tensor)
+    op.dss(u, None, 0.0)
+    model = M.ColumnModel(nlev, nx, ny, K, S_lev=S, nu=1.0, halo=1)
+    uo = T0.copy()
+    model.dss(uo, None, 0.0)
+    alg = cts.IMEXAlgorithm(cts.ARS343(), cts.NewtonsMethod(max_iters=1, update_j=cts.UpdateEvery(cts.NewTimeStep)))
+    integ = cts.init(cts.ODEProblem(op.ode_function(), u, (0.0, 1e9), None), alg, dt=0.01, save=False)
+    _, step = R.make_stepper(model.ode_function(), R.imex_algorithm("ARS343", R.NewtonsMethod(
+        max_iters=1, update_j=R.UpdateEvery("NewTimeStep"))), uo)
+    for k in range(2):
+        cts.step_(integ)
+        step(uo, None, 0.01 * k, 0.01)
+    np.testing.assert_array_equal(u.to_host(), uo)
