@@ -262,6 +262,7 @@ def sharded_parity(cts, ctx, ctx_single, dist, rank, world, local):
             del op1, integ1, u1
         out["cases"][name] = res
         del op, integ, u
+        dist.barrier()   # rank 0 was busy with the single-slab run: do not let the other ranks run ahead into the next case
     out["ok"] = ok_all
     out["halo_path"] = ctx.halo_path()
     return out

@@ -17,7 +17,7 @@ from .functions import (ClimaODEFunction, EndOfStage, EndOfStep, IncrementingODE
                         NewNewtonSolve, NewTimeStep, ODEFunction, ODEProblem, ODESolution, Returns_nothing,
                         UpdateEvery, UpdateEveryDt, UpdateEveryN, WithDSS, has_T_exp, has_T_lim)
 from .integrators import (CallbackSet, DiscreteCallback, EveryXSimulationSteps, EveryXSimulationTime,
-                          EveryXWallTimeSeconds, add_saveat_, add_tstop_, get_dt, init, reinit_, set_dt_, solve,
+                          EveryXWallTimeSeconds, HostSaver, add_saveat_, add_tstop_, get_dt, init, reinit_, set_dt_, solve,
                           solve_, step_)
 from .operators import AdvectionOperator, ColumnOperator, ColumnTridiag
 from .parallel import SlabPartition, attach_communicator

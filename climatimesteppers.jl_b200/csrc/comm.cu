@@ -80,18 +80,20 @@ NcclApi* nccl_api() {
 // 2 directions x 2 slots x row bytes.  One exchange = one launch of halo_peer_kernel on every rank:
 //   push  : the CTAs store this rank's first owned row into the lower neighbour's mailbox[from_hi][slot] and its last
 //           owned row into the upper neighbour's mailbox[from_lo][slot] with 16-byte stores over NVLink, then
-//           __threadfence_system() and one system-scope atomic add per CTA on the neighbour's arrival counter;
-//   pull  : the same CTAs spin (ld.acquire.sys) until their own counter shows that all chunks of exchange #seq have
-//           arrived and copy mailbox -> ghost row.
+//           __threadfence_system(); the last CTA of a direction to get there adds 1 (red.release.sys) to the neighbour's
+//           arrival counter, which therefore counts exchanges;
+//   pull  : the same CTAs spin (ld.acquire.sys) until their own counter has reached exchange #seq and copy
+//           mailbox -> ghost row.
 // seq lives in device memory (so a captured CUDA graph can be replayed), slot = seq & 1.  Two slots suffice: a rank can
 // only start exchange s+1 after it has received its neighbours' exchange-s rows, which they push at the START of their
 // exchange s, i.e. after they have finished unpacking exchange s-1 (the previous user of slot (s+1)&1).  Exchanges of one
 // context must be ordered with respect to each other (they are: same stream or event chains).  A spin that sees no
-// arrival for ~4 s gives up and raises the error flag (a dead peer must not hang the GPU).
+// arrival for a minute gives up and raises the error flag (a dead peer must not hang the GPU).
 // =============================================================================================
 namespace {
 
 constexpr int kHaloThreads = 512;
+constexpr unsigned long long kHaloTimeoutNs = 60ull * 1000000000ull;
 constexpr size_t kPeerHeaderBytes = 256;  // [0]: arrivals from the lower neighbour, [1]: from the upper neighbour
 
 struct HaloPeerArgs {
@@ -107,6 +109,7 @@ struct HaloPeerArgs {
   int ctas_per_dir;
   unsigned long long* seq;   // local: completed exchanges
   unsigned int* done;        // local: CTA ticket
+  unsigned int* pushed;      // local: [2] CTAs of a direction that have stored their chunk
   unsigned int* error;       // local: set when a wait timed out
 };
 
@@ -144,20 +147,30 @@ __global__ void __launch_bounds__(kHaloThreads) halo_peer_kernel(const HaloPeerA
     for (size_t v = v0 + threadIdx.x; v < v1; v += kHaloThreads) dst[v] = src[v];
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0)
-      red_release_sys_add(reinterpret_cast<unsigned long long*>(peer) + (dir == 0 ? 1 : 0), 1ull);
+    // the last CTA of this direction to finish its chunk signals the neighbour: ONE arrival per exchange and direction,
+    // so the counter is the exchange number whatever the row size (and with it the CTA count) of each exchange is
+    if (threadIdx.x == 0) {
+      const unsigned int t = atomicAdd(a.pushed + dir, 1u);
+      if (t == (unsigned)a.ctas_per_dir - 1) {
+        a.pushed[dir] = 0;
+        __threadfence_system();
+        red_release_sys_add(reinterpret_cast<unsigned long long*>(peer) + (dir == 0 ? 1 : 0), 1ull);
+      }
+    }
   }
   // ---- pull: wait for all chunks of exchange s from the neighbour on this side, then unpack my mailbox
   {
     const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(a.mine) + dir;
-    const unsigned long long want = s * (unsigned long long)a.ctas_per_dir;
+    const unsigned long long want = s;
     __shared__ int ok;
     if (threadIdx.x == 0) {
       ok = 1;
       const unsigned long long t0 = global_timer_ns();
       while (ld_acquire_sys(flag) < want) {
         __nanosleep(64);
-        if (global_timer_ns() - t0 > 4000000000ull) {
+        // a neighbour may legitimately be seconds behind (host-side work between steps); a minute means it is gone.
+        // Once the flag is up every later wait gives up at once, so a dead peer costs one timeout, not one per exchange.
+        if (*reinterpret_cast<volatile unsigned int*>(a.error) != 0u || global_timer_ns() - t0 > kHaloTimeoutNs) {
           ok = 0;
           atomicExch(a.error, 1u);
           break;
@@ -194,6 +207,7 @@ struct cts_peer_halo {
   size_t slot_bytes = 0;
   unsigned long long* seq = nullptr;  // [seq][done|error] local control words
   unsigned int* done = nullptr;
+  unsigned int* pushed = nullptr;
   unsigned int* error = nullptr;
   bool ok = false;
 };
@@ -227,6 +241,7 @@ static int peer_halo_setup(cts_ctx* ctx, size_t row_bytes) {
   if (good) {
     p->done = reinterpret_cast<unsigned int*>(p->seq + 1);
     p->error = p->done + 1;
+    p->pushed = p->done + 2;
   }
   // all-gather the IPC handles (64 bytes each, padded to 128) through the communicator the context already has
   constexpr size_t kSlot = 128;
@@ -292,6 +307,7 @@ static int peer_halo_exchange(cts_ctx* ctx, cudaStream_t stream, size_t bytes, c
   a.ctas_per_dir = per_dir < 1 ? 1 : (per_dir > 32 ? 32 : per_dir);
   a.seq = p->seq;
   a.done = p->done;
+  a.pushed = p->pushed;
   a.error = p->error;
   halo_peer_kernel<<<2 * a.ctas_per_dir, kHaloThreads, 0, stream>>>(a);
   CTS_LAUNCH_CHECK(ctx);

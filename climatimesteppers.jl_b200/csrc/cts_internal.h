@@ -124,6 +124,8 @@ int cts_allreduce_sum_f64_oop(cts_ctx* ctx, const double* send, double* recv, si
 inline size_t cts_sizeof(cts_dtype ft) { return ft == CTS_F64 ? 8 : 4; }
 inline bool cts_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+int cts_newton_residual_ex(cts_ctx* ctx, cts_dtype ft, size_t n, void* r, const void* U0, double dtgamma, const void* Up, int native);
+int cts_timp_from_stage_ex(cts_ctx* ctx, cts_dtype ft, size_t n, void* T, const void* U, const void* temp, double dtgamma, int native);
 // ---- internal entry points used across translation units ------------------------------------
 // fused LSRK stage with the advection stencil (ops.cu); out-of-place in u.
 int cts_advection_fused_stage(cts_op_advection* op, void* u_out, const void* u_in, void* du, double A, double dtB,

@@ -148,9 +148,11 @@ __device__ __forceinline__ void ssp_combine(T xe, T te, T uu, const T (&x)[NT > 
     else
       e1 = (T)op_add((double)xe, op_mul(a.dt, (double)te));
   }
-  C blend = op_add(op_mul((C)a.omb, (C)uu), op_mul((C)a.beta, (C)e1));
+  // β is Float64 (imex_ssprk.jl:48-49), so the blend is a Float64 broadcast for every state type; the implicit increment
+  // is folded in C = promote(typeof(dt), eltype(tableau)) and promoted when it meets the blend
+  double blend = op_add(op_mul(a.omb, (double)uu), op_mul(a.beta, (double)e1));
   o_exp = (T)blend;
-  if (!a.final_update) blend = (C)o_exp;
+  if (!a.final_update) blend = (double)o_exp;
   if (NT > 0) {
     C g = 0;
 #pragma unroll
@@ -158,7 +160,10 @@ __device__ __forceinline__ void ssp_combine(T xe, T te, T uu, const T (&x)[NT > 
       C p = op_mul((C)a.ax.coef[k], (C)x[k]);
       g = (k == 0) ? p : op_add(g, p);
     }
-    o_u = (T)op_add(blend, g);
+    if (!a.final_update && sizeof(C) == 4)
+      o_u = (T)op_add((C)o_exp, g);   // `@. U = U_exp + inc_imp` (:169): both Float32 -> Float32 broadcast
+    else
+      o_u = (T)op_add(blend, (double)g);
   } else {
     o_u = o_exp;
   }
@@ -532,6 +537,16 @@ struct ResidualF {  // K3: (U0 + dtγ*r) - U'   evaluated in Float64 (dtγ is Fl
   }
 };
 template <typename T>
+struct ResidualNativeF {  // K3 with dtγ in the state precision (Float32 dt and a downcast tableau): a native broadcast
+  T dtg;
+  __device__ T operator()(T r, T U0, T Up) const { return op_sub(op_add(U0, op_mul(dtg, r)), Up); }
+};
+template <typename T>
+struct TimpNativeF {  // K6 with dtγ in the state precision
+  T dtg;
+  __device__ T operator()(T U, T temp, T) const { return op_div(op_sub(U, temp), dtg); }
+};
+template <typename T>
 struct SubF {  // K5: x - dx in the state precision
   __device__ T operator()(T x, T dx, T) const { return op_sub(x, dx); }
 };
@@ -645,9 +660,7 @@ int cts_component_update(cts_ctx* ctx, cts_dtype ft, size_t n, const void* val, 
 }
 
 int cts_newton_residual(cts_ctx* ctx, cts_dtype ft, size_t n, void* r, const void* U0, double dtgamma, const void* Up) {
-  CTS_CHECK_CTX(ctx);
-  if (ft == CTS_F64) return launch_ew<double, 3>(ctx, n, r, r, U0, Up, ResidualF<double>{dtgamma});
-  return launch_ew<float, 3>(ctx, n, r, r, U0, Up, ResidualF<float>{dtgamma});
+  return cts_newton_residual_ex(ctx, ft, n, r, U0, dtgamma, Up, 0);
 }
 
 int cts_sub_inplace(cts_ctx* ctx, cts_dtype ft, size_t n, void* x, const void* dx) {
@@ -657,9 +670,7 @@ int cts_sub_inplace(cts_ctx* ctx, cts_dtype ft, size_t n, void* x, const void* d
 }
 
 int cts_timp_from_stage(cts_ctx* ctx, cts_dtype ft, size_t n, void* T, const void* U, const void* temp, double dtgamma) {
-  CTS_CHECK_CTX(ctx);
-  if (ft == CTS_F64) return launch_ew<double, 2>(ctx, n, T, U, temp, nullptr, TimpF<double>{dtgamma});
-  return launch_ew<float, 2>(ctx, n, T, U, temp, nullptr, TimpF<float>{dtgamma});
+  return cts_timp_from_stage_ex(ctx, ft, n, T, U, temp, dtgamma, 0);
 }
 
 int cts_jvp_perturb(cts_ctx* ctx, cts_dtype ft, size_t n, void* x2, const void* x, double eps, const void* dx) {
@@ -692,6 +703,22 @@ int cts_axpby(cts_ctx* ctx, cts_dtype ft, size_t n, double a, const void* x, dou
 }
 
 }  // extern "C"
+
+// K3 / K6 with the type of dtγ made explicit: native != 0 (Float32 state only) evaluates the broadcast in Float32
+int cts_newton_residual_ex(cts_ctx* ctx, cts_dtype ft, size_t n, void* r, const void* U0, double dtgamma, const void* Up,
+                           int native) {
+  CTS_CHECK_CTX(ctx);
+  if (ft == CTS_F64) return launch_ew<double, 3>(ctx, n, r, r, U0, Up, ResidualF<double>{dtgamma});
+  if (native) return launch_ew<float, 3>(ctx, n, r, r, U0, Up, ResidualNativeF<float>{(float)dtgamma});
+  return launch_ew<float, 3>(ctx, n, r, r, U0, Up, ResidualF<float>{dtgamma});
+}
+int cts_timp_from_stage_ex(cts_ctx* ctx, cts_dtype ft, size_t n, void* T, const void* U, const void* temp, double dtgamma,
+                           int native) {
+  CTS_CHECK_CTX(ctx);
+  if (ft == CTS_F64) return launch_ew<double, 2>(ctx, n, T, U, temp, nullptr, TimpF<double>{dtgamma});
+  if (native) return launch_ew<float, 2>(ctx, n, T, U, temp, nullptr, TimpNativeF<float>{(float)dtgamma});
+  return launch_ew<float, 2>(ctx, n, T, U, temp, nullptr, TimpF<float>{dtgamma});
+}
 
 // ---------------------------------------------------------------------------------------------
 // GMRES helpers: y = x / denom, out = sum_j coef[j] V[j]

@@ -682,6 +682,7 @@ struct cts_imex_cache {
   // coefficients and the Jacobian policy are exact), applied to the instantiated graph with cudaGraphExecUpdate and
   // launched as ONE graph -- the kernels of a step, the halo exchanges and the fork/join with the communication stream
   // then run back to back without per-launch gaps.
+  bool dt_f32 = false;             // typeof(dt) of the current step is Float32 (cts_imex_step's dt_is_f32)
   int graph_mode = -1;             // -1: decide on first use (on unless CTS_NO_GRAPH is set), 0: off, 1: on
   cudaGraphExec_t graph_exec = nullptr;
   uint64_t graph_launches = 0, graph_reinstantiations = 0;
@@ -709,12 +710,19 @@ int alloc_state(cts_imex_cache* c, void** p) {
   return CTS_OK;
 }
 
-// coefficient fl(dt * a) in the tableau eltype (fused_increment.jl:58,115-116)
+// Broadcast arithmetic is native Float32 only when the state, the (downcast) tableau AND dt are Float32; a Float64 dt or a
+// Float64 tableau promotes every expression to Float64, rounded on store.
+int native_flag(const cts_imex_cache* c) { return (c->tab.cast_to_state_eltype && c->ft == CTS_F32 && c->dt_f32) ? 1 : 0; }
+// coefficient fl(dt * a) in promote(typeof(dt), eltype(tableau)) (fused_increment.jl:58,115-116)
 double coef_of(const cts_imex_cache* c, double dt, double a) {
-  if (c->tab.cast_to_state_eltype && c->ft == CTS_F32) return (double)((float)dt * (float)a);
-  return dt * a;
+  if (native_flag(c)) return (double)((float)dt * (float)a);
+  return dt * a;  // (a is already Float32-valued when the tableau was downcast)
 }
-int native_flag(const cts_imex_cache* c) { return (c->tab.cast_to_state_eltype && c->ft == CTS_F32) ? 1 : 0; }
+// t + dt*c and float(dt)*a_ii (imex_ark.jl:120-122) in the same promoted type
+double time_of(const cts_imex_cache* c, double t, double dt, double cc) {
+  if (native_flag(c)) return (double)((float)t + (float)dt * (float)cc);
+  return t + dt * cc;
+}
 
 struct Increment {  // a fused_raw_increment: the non-zero (coef, tendency) pairs, NullBroadcasted when n == 0
   int n = 0;
@@ -801,7 +809,7 @@ int solve_implicit_equation(cts_imex_cache* c, void* U, const void* U0, double t
   // library column operator as T_imp! and nothing to run before f! (cache_imp! is the reference's prepare_for_f!):
   // residual and JVP go through the fused kernel
   cts_op_column* rop = nullptr;
-  if (c->fusion && c->f.T_imp == cts_op_column_T_imp && !c->f.cache_imp && c->f.ud) {
+  if (c->fusion && !native_flag(c) && c->f.T_imp == cts_op_column_T_imp && !c->f.cache_imp && c->f.ud) {
     auto* op = static_cast<cts_op_column*>(c->f.ud);
     if (cts_op_column_ctx(op) == ctx && cts_op_column_dtype(op) == c->ft && cts_op_column_ndof(op) == c->n &&
         cts_column_residual_fusable(op) && cts_aligned16(U) && cts_aligned16(U0) && cts_aligned16(c->nm->f) &&
@@ -818,7 +826,7 @@ int solve_implicit_equation(cts_imex_cache* c, void* U, const void* U0, double t
       HOOK(ctx, c->f.T_imp(c->f.ud, res, Up, t_imp));
     }
     cts_prof_scope ps(ctx, CTS_PROF_NEWTON_EW);
-    return cts_newton_residual(ctx, c->ft, c->n, res, U0, dtg, Up);  // K3
+    return cts_newton_residual_ex(ctx, c->ft, c->n, res, U0, dtg, Up, native_flag(c));  // K3
   };
   struct FusedScope {  // the JVP of solve_krylov! sees the operator only for the duration of this solve
     cts_newton_cache* nm;
@@ -840,6 +848,7 @@ int solve_implicit_equation(cts_imex_cache* c, void* U, const void* U0, double t
 cts_op_column* fusable_column_op(const cts_imex_cache* c) {
   const cts_ode_function& f = c->f;
   if (!c->fusion || !c->ncfg.present || c->ncfg.max_iters != 1 || c->ncfg.use_krylov) return nullptr;
+  if (native_flag(c)) return nullptr;  // the column kernels evaluate K3/K6 with a Float64 dtγ
   if (c->nm && (c->nm->has_checker || c->nm->line_search)) return nullptr;  // is_converged! / line_search! must run
   if (f.T_imp != cts_op_column_T_imp || f.Wfact != cts_op_column_Wfact || f.ldiv != cts_op_column_ldiv) return nullptr;
   if (f.has_lim) return nullptr;
@@ -939,9 +948,9 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
   CTS_TRY(maybe_update_jacobian(c, u, t, dt, fuse_op != nullptr, fuse_op && cts_op_column_matrix_free(fuse_op)));
 
   for (int i = 0; i < s; ++i) {
-    const double t_exp = t + dt * tab.c_exp[i];
-    const double t_imp = t + dt * tab.c_imp[i];
-    const double dtg = dt * A(tab.a_imp, s, i, i);
+    const double t_exp = time_of(c, t, dt, tab.c_exp[i]);
+    const double t_imp = time_of(c, t, dt, tab.c_imp[i]);
+    const double dtg = coef_of(c, dt, A(tab.a_imp, s, i, i));
     const bool no_imp = !has_T_imp || dtg == 0;
     const bool has_exp_terms = col_nonzero(tab.a_exp, s, i) || tab.b_exp[i] != 0;
     const bool has_imp_terms = col_nonzero(tab.a_imp, s, i) || tab.b_imp[i] != 0;
@@ -1030,7 +1039,7 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
         HOOK(c->ctx, f.T_imp(f.ud, c->T_imp[i], U, t_imp));
       } else {
         cts_prof_scope ps(c->ctx, CTS_PROF_NEWTON_EW);
-        CTS_TRY(cts_timp_from_stage(c->ctx, c->ft, c->n, c->T_imp[i], U, c->temp, dtg));  // K6 :269
+        CTS_TRY(cts_timp_from_stage_ex(c->ctx, c->ft, c->n, c->T_imp[i], U, c->temp, dtg, native_flag(c)));  // K6 :269
       }
     }
   }
@@ -1115,14 +1124,16 @@ int ssprk_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
   const int native = native_flag(c);
   cts_op_column* fuse_op = fusable_column_op(c);
   if (fuse_op && !cts_aligned16(u)) fuse_op = nullptr;
-  auto beta_c = [&](double b) { return native ? (double)(float)b : b; };
+  // β is formed from the tableau as given (imex_ssprk.jl:48-49: Float64 for the named methods), so the Shu-Osher blends
+  // are Float64 broadcasts whatever the state and dt types are; only the implicit increment can be native Float32
+  auto beta_c = [&](double b) { return b; };
   CTS_TRY(maybe_update_jacobian(c, u, t, dt, fuse_op != nullptr, fuse_op && cts_op_column_matrix_free(fuse_op)));
 
   for (int i = 0; i < s; ++i) {
-    const double t_exp = t + dt * tab.c_exp[i];
-    const double t_imp = t + dt * tab.c_imp[i];
+    const double t_exp = time_of(c, t, dt, tab.c_exp[i]);
+    const double t_imp = time_of(c, t, dt, tab.c_imp[i]);
     const double aii = A(tab.a_imp, s, i, i);
-    const double dtg = dt * aii;
+    const double dtg = coef_of(c, dt, aii);
     Increment inc_imp = has_T_imp ? raw_increment(c, dt, &tab.a_imp[i * s], i, c->T_imp) : Increment{};
     const bool no_imp = !has_T_imp || aii == 0;
     const bool has_imp_terms = col_nonzero(tab.a_imp, s, i) || tab.b_imp[i] != 0;
@@ -1135,7 +1146,7 @@ int ssprk_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
       CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->U_exp, nullptr, 1.0, u, 0, 0, nullptr, nullptr, 0));  // :155
     } else if (c->beta[i - 1] != 0) {
       const double b = beta_c(c->beta[i - 1]);
-      const double omb = native ? (double)(1.0f - (float)b) : 1.0 - b;
+      const double omb = 1.0 - b;
       if (!f.has_lim && c->fusion && inc_imp.n <= 8) {
         // K11: `U_exp += dt*T_exp` :162, `U_exp = (1-β)u + βU_exp` :165, `U = U_exp + inc_imp` :169 (and `temp = U`)
         // in one pass; the fused column stage assembles U itself, so only U_exp is produced for it.
@@ -1156,7 +1167,7 @@ int ssprk_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
         double coef[1] = {b};
         const void* terms[1] = {c->U_exp};
         cts_prof_scope ps(c->ctx, CTS_PROF_STAGE_ASSEMBLY);
-        CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->U_exp, nullptr, omb, u, 1, 0, coef, terms, native));
+        CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->U_exp, nullptr, omb, u, 1, 0, coef, terms, 0));
         // NB: c0 == 1 would skip the multiply; (1-β) == 1 only when β == 0, which this branch excludes.
       }
     }
@@ -1199,7 +1210,7 @@ int ssprk_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
         HOOK(c->ctx, f.T_imp(f.ud, c->T_imp[i], c->U, t_imp));
       } else {
         cts_prof_scope ps(c->ctx, CTS_PROF_NEWTON_EW);
-        CTS_TRY(cts_timp_from_stage(c->ctx, c->ft, c->n, c->T_imp[i], c->U, c->temp, dtg));
+        CTS_TRY(cts_timp_from_stage_ex(c->ctx, c->ft, c->n, c->T_imp[i], c->U, c->temp, dtg, native_flag(c)));
       }
     }
   }
@@ -1210,7 +1221,7 @@ int ssprk_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
   if (c->beta[s - 1] != 0 && !f.has_lim && c->fusion && inc_imp.n <= 8) {
     // K11, final form: `U_exp += dt*T_exp` :117 and `u = (1-β)u + βU_exp + inc_imp` :120-122 in one pass
     const double b = beta_c(c->beta[s - 1]);
-    const double omb = native ? (double)(1.0f - (float)b) : 1.0 - b;
+    const double omb = 1.0 - b;
     cts_prof_scope ps(c->ctx, CTS_PROF_FINAL_UPDATE);
     CTS_TRY(cts_ssprk_stage(c->ctx, c->ft, c->n, nullptr, u, nullptr, c->U_exp, has_T_exp ? c->T_exp1 : nullptr, u, dt,
                             (dt_is_f32 && c->ft == CTS_F32) ? 1 : 0, b, omb, inc_imp.n, inc_imp.coef, inc_imp.term, native, 1));
@@ -1221,14 +1232,13 @@ int ssprk_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
       CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->U_exp, nullptr, 1.0, c->U_lim, 0, 0, nullptr, nullptr, 0));
     }
     if (has_T_exp) CTS_TRY(axpy_dt(c, c->U_exp, c->U_exp, dt, c->T_exp1, dt_is_f32));
-    // `@. u = (1 - β) * u + β * U_exp + inc_imp`  :120-122
+    // `@. u = (1 - β) * u + β * U_exp + inc_imp`  :120-122: the blend in Float64, the increment in its own type -> K11's
+    // final form without the explicit tendency (already added above)
     const double b = beta_c(c->beta[s - 1]);
-    const double omb = native ? (double)(1.0f - (float)b) : 1.0 - b;
-    Increment g1;
-    g1.n = 1;
-    g1.coef[0] = b;
-    g1.term[0] = c->U_exp;
-    CTS_TRY(assign_with_increments(c, u, nullptr, omb, u, g1, inc_imp, CTS_PROF_FINAL_UPDATE));
+    const double omb = 1.0 - b;
+    cts_prof_scope ps(c->ctx, CTS_PROF_FINAL_UPDATE);
+    CTS_TRY(cts_ssprk_stage(c->ctx, c->ft, c->n, nullptr, u, nullptr, c->U_exp, nullptr, u, dt, 0, b, omb, inc_imp.n,
+                            inc_imp.coef, inc_imp.term, native, 1));
   } else if (inc_imp.n > 0) {
     CTS_TRY(assign_with_increments(c, u, nullptr, 1.0, u, inc_imp, Increment{}, CTS_PROF_FINAL_UPDATE));
   }
@@ -1356,6 +1366,19 @@ int cts_imex_cache_create(cts_ctx* ctx, cts_dtype ft, size_t n, const cts_imex_t
     }
     c->nbuffers += 2;  // Δx, f
   }
+  // downcast_tableau (imex_tableaus.jl:127-133, imex_ark.jl:59-61, imex_ssprk.jl:75-78): with cast_tableau_to_state_eltype
+  // and a Float32 state every coefficient is rounded to Float32 -- AFTER γ and β were formed from the tableau as given
+  if (c->tab.cast_to_state_eltype && ft == CTS_F32) {
+    auto rnd = [](double* a, int m) {
+      for (int k = 0; k < m; ++k) a[k] = (double)(float)a[k];
+    };
+    rnd(c->tab.a_exp, CTS_MAX_STAGES * CTS_MAX_STAGES);
+    rnd(c->tab.a_imp, CTS_MAX_STAGES * CTS_MAX_STAGES);
+    rnd(c->tab.b_exp, CTS_MAX_STAGES);
+    rnd(c->tab.b_imp, CTS_MAX_STAGES);
+    rnd(c->tab.c_exp, CTS_MAX_STAGES);
+    rnd(c->tab.c_imp, CTS_MAX_STAGES);
+  }
   *out = c;
   return CTS_OK;
 }
@@ -1440,6 +1463,7 @@ static int graphed_ark_step(cts_imex_cache* c, void* u, double t, double dt) {
 
 int cts_imex_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
   if (!c || !u) return CTS_EINVAL;
+  c->dt_f32 = dt_is_f32 != 0;
   if (c->constraint == 0) {
     if (graph_capturable(c, u)) {
       // collective set-up (IPC mailboxes) cannot happen inside a capture: do it now if the step will exchange halos

@@ -149,7 +149,10 @@ def init(prob: ODEProblem, alg, *, dt, tstops=(), saveat=None, save_everystep=Fa
     return integrator
 
 
-def reinit_(integrator, u0=None, *, t0=None, tf=None, erase_sol=True, tstops=None, saveat="__default__",
+_DEFAULT = object()   # "use what init was given": compared by identity, so arrays are fine as `saveat`
+
+
+def reinit_(integrator, u0=None, *, t0=None, tf=None, erase_sol=True, tstops=None, saveat=_DEFAULT,
             reinit_callbacks=True):
     """integrators.jl:273-303."""
     prob = integrator.sol.prob
@@ -157,7 +160,7 @@ def reinit_(integrator, u0=None, *, t0=None, tf=None, erase_sol=True, tstops=Non
     t0 = prob.tspan[0] if t0 is None else t0
     tf = prob.tspan[1] if tf is None else tf
     tstops = integrator._tstops if tstops is None else tstops
-    saveat = integrator._saveat if saveat == "__default__" else saveat
+    saveat = integrator._saveat if saveat is _DEFAULT else saveat
     if u0 is not integrator.u:
         integrator.u.copyto(u0)
     integrator.t = t0
@@ -269,73 +272,119 @@ def add_saveat_(integrator, t):
 
 
 # ---- Callbacks.jl ----------------------------------------------------------------------------------
-def EveryXSimulationSteps(f, dn: int, atinit=False, call_at_end=False) -> DiscreteCallback:
-    """Callbacks.jl:144-174."""
-    state = {"steps": 0, "steps_since": 0}
+def _ext_initialize(f, integrator):
+    """`Callbacks.initialize!(f!, integrator)` (Callbacks.jl:17-21): an extension point of the affect; default no-op."""
+    h = getattr(f, "initialize", None)
+    if callable(h):
+        h(integrator)
+
+
+def _ext_finalize(f, integrator):
+    """`Callbacks.finalize!(f!, integrator)` (Callbacks.jl:23-28)."""
+    h = getattr(f, "finalize", None)
+    if callable(h):
+        h(integrator)
+
+
+def EveryXSimulationSteps(f, dn: int, atinit=False) -> DiscreteCallback:
+    """Callbacks.jl:144-174: fires when the step counter reaches `steps_next`, which then advances by Δsteps."""
+    state = {"steps": 0, "steps_next": 0}
 
     def condition(u, t, integrator):
         state["steps"] += 1
-        state["steps_since"] += 1
-        if state["steps_since"] >= dn:
-            state["steps_since"] = 0
+        if state["steps"] >= state["steps_next"]:
+            state["steps_next"] += dn
             return True
         return False
 
     def initialize(cb, u, t, integrator):
-        state["steps"], state["steps_since"] = 0, 0
+        state["steps"], state["steps_next"] = 0, dn
+        _ext_initialize(f, integrator)
         if atinit:
             f(integrator)
 
     def finalize(cb, u, t, integrator):
-        if call_at_end and state["steps_since"] > 0:
-            f(integrator)
+        _ext_finalize(f, integrator)
 
     return DiscreteCallback(condition, f, initialize, finalize)
 
 
 def EveryXSimulationTime(f, dt_cb, atinit=False) -> DiscreteCallback:
-    """Callbacks.jl:101-133."""
+    """Callbacks.jl:101-133: `t_next` starts at Δt (an ABSOLUTE time, independent of t0) and advances past t on firing."""
     state = {"t_next": 0.0}
 
     def condition(u, t, integrator):
         if t >= state["t_next"]:
-            while state["t_next"] <= t:
+            while t >= state["t_next"]:
                 state["t_next"] += dt_cb
             return True
         return False
 
     def initialize(cb, u, t, integrator):
-        state["t_next"] = t + dt_cb
+        state["t_next"] = dt_cb
+        _ext_initialize(f, integrator)
         if atinit:
             f(integrator)
 
-    return DiscreteCallback(condition, f, initialize)
+    def finalize(cb, u, t, integrator):
+        _ext_finalize(f, integrator)
+
+    return DiscreteCallback(condition, f, initialize, finalize)
 
 
-def EveryXWallTimeSeconds(f, dt_wall, ctx=None, atinit=False) -> DiscreteCallback:
-    """Callbacks.jl:40-90: the wall clock is all-reduced (max) so every rank fires on the same step (:59,:72)."""
+def EveryXWallTimeSeconds(f, dt_wall, ctx=None, atinit=False, clock=None) -> DiscreteCallback:
+    """Callbacks.jl:40-90: the wall clock is all-reduced (max) so every rank fires on the same step (:59,:72):
+    `ClimaComms.allreduce(comm_ctx, time(), max)` -> `cts_allreduce_max_f64_host` on the context's communicator.
+    `clock` replaces `time.time` (tests)."""
     import ctypes as C
     state = {"next": 0.0}
+    now_fn = clock if clock is not None else time.time
 
     def _now():
-        t = time.time()
+        t = now_fn()
         if ctx is not None and ctx.nranks > 1:
             v = C.c_double(t)
-            ctx.check(ctx.lib.cts_allreduce_max_f64_host(ctx.handle, C.byref(v)))
+            ctx.check(ctx.lib.cts_allreduce_max_f64_host(ctx.handle, C.byref(v)), "allreduce(max)")
             t = v.value
         return t
 
     def condition(u, t, integrator):
         now = _now()
         if now >= state["next"]:
-            while state["next"] <= now:
+            while now >= state["next"]:
                 state["next"] += dt_wall
             return True
         return False
 
     def initialize(cb, u, t, integrator):
         state["next"] = _now() + dt_wall
+        _ext_initialize(f, integrator)
         if atinit:
             f(integrator)
 
-    return DiscreteCallback(condition, f, initialize)
+    def finalize(cb, u, t, integrator):
+        _ext_finalize(f, integrator)
+
+    return DiscreteCallback(condition, f, initialize, finalize)
+
+
+class HostSaver:
+    """A `save_func` for `init(...; save_func)` (integrators.jl:197,495-526) that saves to the HOST without stalling the
+    step loop: every save is a stream-ordered device-to-host copy (`cts_memcpy_d2h`) into its own pinned buffer; the
+    values are valid after `wait()` (or any later synchronisation of the context's stream)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self._bufs = []
+
+    def __call__(self, u, t):
+        import torch
+        host = torch.empty(len(u), dtype=u.tensor.dtype, pin_memory=True)
+        self.ctx.check(self.ctx.lib.cts_memcpy_d2h(self.ctx.handle, host.data_ptr(), u.ptr, host.numel() * host.element_size()),
+                       "cts_memcpy_d2h")
+        self._bufs.append(host)
+        return host
+
+    def wait(self):
+        self.ctx.sync()
+        return [b.numpy() for b in self._bufs]

@@ -396,19 +396,40 @@ def _wide(x):
     return x.astype(np.float64, copy=False)
 
 
-def fused_raw_increment(dt, coeffs: Sequence[float], tends: Sequence[Optional[np.ndarray]], cdtype=np.float64):
+def _jl(x):
+    """A scalar with its Julia type: a Float32 stays Float32, anything else is Float64 (numpy >= 2 promotes typed
+    scalars the way Julia does: Float64*Float32 -> Float64, Float32*Float32 -> Float32)."""
+    return x if isinstance(x, np.float32) else np.float64(x)
+
+
+def _scale(coef, T):
+    """``coef .* T`` with Julia promotion: Float32 only when both are Float32."""
+    if isinstance(coef, np.float32) and T.dtype == np.float32:
+        return coef * T
+    return np.float64(coef) * _wide(T)
+
+
+def downcast_tableau(FT, tab: "IMEXTableau"):
+    """imex_tableaus.jl:127-133: every coefficient array mapped through FT (used when cast_tableau_to_state_eltype)."""
+    import copy
+    t = copy.copy(tab)
+    for k in ("a_exp", "b_exp", "c_exp", "a_imp", "b_imp", "c_imp"):
+        setattr(t, k, getattr(tab, k).astype(FT))
+    return t
+
+
+def fused_raw_increment(dt, coeffs: Sequence[float], tends: Sequence[Optional[np.ndarray]], cdtype=None):
     """fused_increment.jl:115-172.  ``coeffs[j]`` pairs with ``tends[j]``; zero coefficients are dropped
-    (sparse_coeffs.jl:29-35).  Each term is ``(dt*c_j) .* T_j`` with the scalar product rounded first (:58,:79);
-    terms are summed by a left fold (:90-91).  Returns ``None`` for NullBroadcasted (:127-128,:155-156).
-    ``cdtype`` is the tableau eltype (Float64 unless cast_tableau_to_state_eltype)."""
+    (sparse_coeffs.jl:29-35).  Each term is ``(dt*c_j) .* T_j`` with the scalar product rounded first (:58,:79) in
+    ``promote(typeof(dt), eltype(tableau))``; terms are summed by a left fold (:90-91).  Returns ``None`` for
+    NullBroadcasted (:127-128,:155-156).  The tableau eltype is the dtype of ``coeffs`` (Float64 unless
+    cast_tableau_to_state_eltype downcast it, imex_ark.jl:59-61)."""
     acc = None
+    dt = _jl(dt)
     for c, T in zip(coeffs, tends):
         if c == 0:
             continue
-        if cdtype == np.float64:
-            term = (float(dt) * float(c)) * _wide(T)
-        else:  # cast_tableau_to_state_eltype: everything in the state precision
-            term = cdtype(cdtype(dt) * cdtype(c)) * T
+        term = _scale(dt * _jl(c), T)
         acc = term if acc is None else acc + term
     return acc
 
@@ -995,10 +1016,9 @@ def init_cache_ark(u0, f: ClimaODEFunction, alg: IMEXAlgorithm):
     nmc = None
     if T_imp is not None and nm is not None:
         nmc = allocate_newton_cache(nm, u0, T_imp.jac_prototype if has_jac else None)
-    cdtype = u0.dtype if alg.cast_tableau_to_state_eltype else np.float64
+    opt_tb = downcast_tableau(u0.dtype, tab) if alg.cast_tableau_to_state_eltype else tab  # imex_ark.jl:59-61
     return {"U": z(), "T_lim": {i: z() for i in idx_exp}, "T_exp": {i: z() for i in idx_exp},
-            "T_imp": {i: z() for i in idx_imp}, "temp": z(), "gamma": gamma, "nm_cache": nmc,
-            "cdtype": np.dtype(cdtype).type}
+            "T_imp": {i: z() for i in idx_imp}, "temp": z(), "gamma": gamma, "nm_cache": nmc, "tableau": opt_tb}
 
 
 def _maybe_update_jacobian(f, alg, cache, u, p, t, dt):
@@ -1008,35 +1028,46 @@ def _maybe_update_jacobian(f, alg, cache, u, p, t, dt):
         return
     if not nm.update_j.needs_update("NewTimeStep", t):
         return
-    T_imp.Wfact(nmc["j"], u, p, dt * cache["gamma"], t)
+    T_imp.Wfact(nmc["j"], u, p, float(dt) * cache["gamma"], t)  # γ comes from the tableau as given (imex_ark.jl:50-52)
 
 
 def _solve_implicit_equation(U, U0, p, t_imp, dtg, T, nm, nmc, cache_imp):
     """imex_ark.jl:283-308: residual = (U0 + dtγ*T(U')) - U'."""
 
     def residual(res, Up):
-        T(res, Up, p, t_imp)
-        res[...] = (_wide(U0) + dtg * _wide(res)) - _wide(Up)
+        T(res, Up, p, float(t_imp))
+        if isinstance(dtg, np.float32) and res.dtype == np.float32:
+            res[...] = (U0 + dtg * res) - Up  # dtγ in Float32 (Float32 dt and a downcast tableau): Float32 broadcast
+        else:
+            res[...] = (_wide(U0) + float(dtg) * _wide(res)) - _wide(Up)
 
     solve_newton(nm, nmc, U, residual,
-                 (lambda jac, Up: T.Wfact(jac, Up, p, dtg, t_imp)) if getattr(T, "Wfact", None) else None,
-                 lambda Up: cache_imp(Up, p, t_imp))
+                 (lambda jac, Up: T.Wfact(jac, Up, p, float(dtg), float(t_imp))) if getattr(T, "Wfact", None) else None,
+                 lambda Up: cache_imp(Up, p, float(t_imp)))
+
+
+def _timp_from_stage(U, temp, dtg):
+    """``@. T_imp[i] = (U - temp) / dtγ`` (imex_ark.jl:269): the subtraction in the state precision, the division in
+    promote(eltype(U), typeof(dtγ))."""
+    if isinstance(dtg, np.float32) and U.dtype == np.float32:
+        return (U - temp) / dtg
+    return _wide(U - temp) / float(dtg)
 
 
 def imex_ark_step(u, p, t, dt, f: ClimaODEFunction, alg: IMEXAlgorithm, cache):
     """imex_ark.jl:69-104 (step_u!) with the stage loop of :107-272 inlined."""
-    tab = alg.tableau
+    tab = cache["tableau"]
     s = tab.s
     U, T_lim, T_exp, T_imp, temp = cache["U"], cache["T_lim"], cache["T_exp"], cache["T_imp"], cache["temp"]
-    cd = cache["cdtype"]
+    cd = None
     Timp_f = f.T_imp
     nm, nmc = alg.newtons_method, cache["nm_cache"]
     _maybe_update_jacobian(f, alg, cache, u, p, t, dt)
     tend = lambda d, n: [d.get(j) for j in range(n)]
     for i in range(s):
-        t_exp = t + dt * tab.c_exp[i]
-        t_imp = t + dt * tab.c_imp[i]
-        dtg = float(dt) * float(tab.a_imp[i, i])
+        t_exp = float(_jl(t) + _jl(dt) * tab.c_exp[i])
+        t_imp = float(_jl(t) + _jl(dt) * tab.c_imp[i])
+        dtg = _jl(dt) * tab.a_imp[i, i]  # `float(dt) * a_imp[i, i]` :122 in promote(typeof(dt), eltype(tableau))
         # compute_stage_value! :140-165
         inc_exp = fused_raw_increment(dt, tab.a_exp[i, :i], tend(T_exp, i), cd) if f.has_T_exp else None
         inc_imp = None if Timp_f is None else fused_raw_increment(dt, tab.a_imp[i, :i], tend(T_imp, i), cd)
@@ -1083,7 +1114,7 @@ def imex_ark_step(u, p, t, dt, f: ClimaODEFunction, alg: IMEXAlgorithm, cache):
                 if Timp_f is not None:
                     Timp_f(T_imp[i], U, p, t_imp)
             elif Timp_f is not None:
-                T_imp[i][...] = _wide(U - temp) / dtg
+                T_imp[i][...] = _timp_from_stage(U, temp, dtg)
     # final update :79-91
     t_final = t + dt
     inc_exp = fused_raw_increment(dt, tab.b_exp, tend(T_exp, s), cd) if f.has_T_exp else None
@@ -1122,27 +1153,31 @@ def init_cache_ssprk(u0, f: ClimaODEFunction, alg: IMEXAlgorithm):
     nmc = None
     if T_imp is not None and nm is not None:
         nmc = allocate_newton_cache(nm, u0, T_imp.jac_prototype if has_jac else None)
-    cdtype = u0.dtype if alg.cast_tableau_to_state_eltype else np.float64
+    opt_tb = downcast_tableau(u0.dtype, tab) if alg.cast_tableau_to_state_eltype else tab  # imex_ssprk.jl:75-78
     return {"U": z(), "U_exp": z(), "U_lim": z(), "T_lim": z(), "T_exp": z(),
             "T_imp": {i: z() for i in idx_imp}, "temp": z(), "beta": beta, "gamma": gamma,
-            "nm_cache": nmc, "cdtype": np.dtype(cdtype).type}
+            "nm_cache": nmc, "tableau": opt_tb}  # β is formed from the tableau as given (:48-49): Float64 for named methods
 
 
 def imex_ssprk_step(u, p, t, dt, f: ClimaODEFunction, alg: IMEXAlgorithm, cache):
     """imex_ssprk.jl:95-220."""
-    tab = alg.tableau
+    tab = cache["tableau"]
     s = tab.s
     U, U_exp, U_lim, T_lim, T_exp = cache["U"], cache["U_exp"], cache["U_lim"], cache["T_lim"], cache["T_exp"]
-    T_imp, temp, beta, cd = cache["T_imp"], cache["temp"], cache["beta"], cache["cdtype"]
+    T_imp, temp, beta, cd = cache["T_imp"], cache["temp"], cache["beta"], None
     Timp_f, nm, nmc = f.T_imp, alg.newtons_method, cache["nm_cache"]
     _maybe_update_jacobian(f, alg, cache, u, p, t, dt)
     tend = lambda d, n: [d.get(j) for j in range(n)]
-    w = lambda x: _wide(x) if cd == np.float64 else x
-    cdt = (lambda x: float(x)) if cd == np.float64 else (lambda x: cd(x))
+    w = _wide            # β is Float64, so every Shu-Osher blend is a Float64 broadcast (rounded on store)
+    cdt = float
+
+    def plus_inc(x, inc):  # `x + inc_imp`: Float32 only when the increment is (Float32 dt and a downcast tableau)
+        return (x + inc) if (inc.dtype == np.float32 and x.dtype == np.float32) else (_wide(x) + _wide(inc))
+
     for i in range(s):
-        t_exp = t + dt * tab.c_exp[i]
-        t_imp = t + dt * tab.c_imp[i]
-        dtg = float(dt) * float(tab.a_imp[i, i])
+        t_exp = float(_jl(t) + _jl(dt) * tab.c_exp[i])
+        t_imp = float(_jl(t) + _jl(dt) * tab.c_imp[i])
+        dtg = _jl(dt) * tab.a_imp[i, i]
         if i == 0:
             U_exp[...] = u
         elif beta[i - 1] != 0:
@@ -1159,7 +1194,7 @@ def imex_ssprk_step(u, p, t, dt, f: ClimaODEFunction, alg: IMEXAlgorithm, cache)
             # `inc_imp = 0` (:168) when T_imp! === nothing; a NullBroadcasted adds nothing
             U[...] = U_exp
         else:
-            U[...] = w(U_exp) + inc_imp
+            U[...] = plus_inc(U_exp, inc_imp)
         no_imp = Timp_f is None or tab.a_imp[i, i] == 0
         top_sig = "EndOfStage" if no_imp else "WithDSS"
         if i != 0:
@@ -1186,7 +1221,7 @@ def imex_ssprk_step(u, p, t, dt, f: ClimaODEFunction, alg: IMEXAlgorithm, cache)
                 if Timp_f is not None:
                     Timp_f(T_imp[i], U, p, t_imp)
             elif Timp_f is not None:
-                T_imp[i][...] = _wide(U - temp) / dtg
+                T_imp[i][...] = _timp_from_stage(U, temp, dtg)
     t_final = t + dt
     inc_imp = None if Timp_f is None else fused_raw_increment(dt, tab.b_imp, tend(T_imp, s), cd)
     if beta[s - 1] != 0:
@@ -1198,11 +1233,11 @@ def imex_ssprk_step(u, p, t, dt, f: ClimaODEFunction, alg: IMEXAlgorithm, cache)
             U_exp[...] = _axpy_dt(U_exp, dt, T_exp)
         b = cdt(beta[s - 1])
         if inc_imp is not None:
-            u[...] = ((1 - b) * w(u) + b * w(U_exp)) + inc_imp  # :120
+            u[...] = ((1 - b) * w(u) + b * w(U_exp)) + _wide(inc_imp)  # :120
         else:
             u[...] = (1 - b) * w(u) + b * w(U_exp)
     elif inc_imp is not None:
-        u[...] = w(u) + inc_imp
+        u[...] = plus_inc(u, inc_imp)
     f.dss(u, p, t_final)
     if f.update_constrain_state.needs_update("EndOfStep"):
         f.constrain_state(u, p, t_final)

@@ -97,6 +97,37 @@ def main():
             print(f"[{world} ranks, halo={ctx.halo_path()}, graph_launches={integ.cache.graph_stats()['graph_launches']}] {name} rows/rank={ny_rank} nonlinear={nonlinear} krylov={krylov}: rel err {err:.3e} bit-exact={exact} krylov_iters={st['krylov_iters']} "
                   f"norm rel err {nerr:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
         dist.barrier()
+    # ---- EveryXWallTimeSeconds (Callbacks.jl:40-90): every rank has its own (skewed) clock; the max all-reduce
+    # (`cts_allreduce_max_f64_host`) makes all ranks fire on the same steps -- those of the fastest clock
+    part = cts.SlabPartition(8 * world, world, rank)
+    K, T0, S = M.column_inputs(16, nx, 8 * world, part.row0, part.ny_local, 1)
+    op = cts.ColumnOperator(16, nx, part.ny_local, cts.B200Vector.from_host(K, ctx), S_lev=cts.B200Vector.from_host(S, ctx),
+                            nu=1.0, halo=1, ctx=ctx)
+    u = cts.B200Vector.from_host(T0, ctx)
+    op.dss(u, None, 0.0)
+    ticks = iter(np.arange(0.0, 1000.0, 0.1 * (rank + 1)))   # rank r's clock advances 0.1*(r+1) s per query
+    hits = []
+    cb = cts.EveryXWallTimeSeconds(lambda integ: hits.append(integ.step), 1.0, ctx, clock=lambda: float(next(ticks)))
+    integ = cts.init(cts.ODEProblem(op.ode_function(), u, (0.0, 0.2), None),
+                     cts.IMEXAlgorithm(cts.ARS343(), cts.NewtonsMethod(max_iters=1)), dt=0.01, callback=cb)
+    cts.solve_(integ)
+    fast = 0.1 * world                                        # the max over ranks is the fastest clock
+    expect, nxt = [], fast * 0 + 1.0
+    for step in range(1, 21):
+        now = fast * step
+        if now >= nxt:
+            while now >= nxt:
+                nxt += 1.0
+            expect.append(step)
+    got = torch.tensor(hits + [-1] * (32 - len(hits)), device=f"cuda:{local}")
+    allhits = [torch.empty_like(got) for _ in range(world)] if rank == 0 else None
+    dist.gather(got, allhits, dst=0)
+    if rank == 0:
+        same = all(bool(torch.equal(h, allhits[0])) for h in allhits)
+        good = same and hits == expect
+        ok = ok and good
+        print(f"[{world} ranks] EveryXWallTimeSeconds with skewed clocks: hits {hits} expected {expect} identical on all ranks={same} -> {'OK' if good else 'FAIL'}", flush=True)
+    dist.barrier()
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

@@ -287,8 +287,9 @@ def test_K11_ssprk_stage_equals_chained_passes(cts, dtype, native, n_imp, final)
     coef = (C.c_double * max(1, n_imp))(*[0.013 * (k + 1) for k in range(n_imp)])
     terms = (C.c_void_p * max(1, n_imp))(*[t.ptr for t in timp])
     dt, beta = 0.0371, 2.0 / 3.0
-    b = float(np.float32(beta)) if native else beta
-    omb = float(np.float32(1) - np.float32(b)) if native else 1.0 - b
+    # β is Float64 whatever the state/dt types are (imex_ssprk.jl:48-49): the blends are Float64 broadcasts; `native`
+    # (Float32 dt and a downcast tableau) only makes `U_exp + dt*T_exp` and the implicit increment Float32
+    b, omb = beta, 1.0 - beta
     dt_native = 1 if (native and dtype == "f32") else 0
     # chained reference on the device
     e = cts.B200Vector.zeros(n, np_dt)
@@ -296,12 +297,23 @@ def test_K11_ssprk_stage_equals_chained_passes(cts, dtype, native, n_imp, final)
     ctx.check(lib.cts_axpy_n(ctx.handle, ft, n, e.ptr, None, 1.0, xexp.ptr, 1, 0, one_c, one_t, dt_native))
     ref_U, ref_exp = cts.B200Vector.zeros(n, np_dt), cts.B200Vector.zeros(n, np_dt)
     bc, bt = (C.c_double * 1)(b), (C.c_void_p * 1)(e.ptr)
-    if final:
+    if final and not native:
         allc = (C.c_double * (1 + n_imp))(b, *[coef[k] for k in range(n_imp)])
         allt = (C.c_void_p * (1 + n_imp))(e.ptr, *[t.ptr for t in timp])
-        ctx.check(lib.cts_axpy_n(ctx.handle, ft, n, ref_U.ptr, None, omb, u.ptr, 1, n_imp, allc, allt, native))
+        ctx.check(lib.cts_axpy_n(ctx.handle, ft, n, ref_U.ptr, None, omb, u.ptr, 1, n_imp, allc, allt, 0))
+    elif final:
+        # mixed precision: Float64 blend + (Float32 increment promoted), rounded once
+        eh, uh = e.to_host().astype(np.float64), u.to_host().astype(np.float64)
+        acc = omb * uh + b * eh
+        if n_imp:
+            g = None
+            for k in range(n_imp):
+                p = np.float32(coef[k]) * timp[k].to_host()
+                g = p if g is None else g + p
+            acc = acc + g.astype(np.float64)
+        ref_U = dev(cts, acc.astype(np.float32))
     else:
-        ctx.check(lib.cts_axpy_n(ctx.handle, ft, n, ref_exp.ptr, None, omb, u.ptr, 1, 0, bc, bt, native))
+        ctx.check(lib.cts_axpy_n(ctx.handle, ft, n, ref_exp.ptr, None, omb, u.ptr, 1, 0, bc, bt, 0))
         ctx.check(lib.cts_axpy_n(ctx.handle, ft, n, ref_U.ptr, None, 1.0, ref_exp.ptr, n_imp, 0, coef, terms, native))
     got_U, got_exp, got_temp = (cts.B200Vector.zeros(n, np_dt) for _ in range(3))
     ctx.check(lib.cts_ssprk_stage(ctx.handle, ft, n, None if final else got_exp.ptr, got_U.ptr, got_temp.ptr, xexp.ptr, texp.ptr,

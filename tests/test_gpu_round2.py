@@ -170,3 +170,85 @@ def test_unaligned_state_falls_back_to_the_generic_path(cts):
         cts.step_(integ)
         step(uo, None, 0.01 * k, 0.01)
     np.testing.assert_array_equal(u.to_host(), uo)
+
+
+# ------------------------------------------------------------------ cast_tableau_to_state_eltype ------
+@pytest.mark.parametrize("dt32", [False, True])
+@pytest.mark.parametrize("fusion", [False, True])
+@pytest.mark.parametrize("name,constraint", [("ARS343", None), ("ARS222", None), ("SSP333", "SSP"), ("SSP333", "Unconstrained"),
+                                             ("SSP222", "SSP")])
+def test_downcast_tableau_float32_state(cts, name, constraint, fusion, dt32):
+    # imex_tableaus.jl:127-133 + imex_ark.jl:59-61,120-122: with cast_tableau_to_state_eltype the coefficients are rounded to
+    # Float32; with a Float64 dt every product dt*Float32(a) and every broadcast is still Float64 arithmetic, with a
+    # Float32 dt everything is native Float32 -- except the Shu-Osher blends of the SSPRK path, whose β stays Float64
+    import test_gpu_parity as P
+    model, op, T0 = P._column_pair(cts, nlev=16, nx=4, ny=6, dtype=np.float32)
+    dt = np.float32(0.02) if dt32 else 0.02
+    alg_o = R.imex_algorithm(name, R.NewtonsMethod(max_iters=1), constraint, cast_tableau_to_state_eltype=True)
+    alg_c = cts.IMEXAlgorithm(getattr(cts, name)(), cts.NewtonsMethod(max_iters=1), constraint, cast_tableau_to_state_eltype=True)
+    uo = T0.copy()
+    model.dss(uo, None, 0.0)
+    _, step_o = R.make_stepper(model.ode_function(), alg_o, uo)
+    uc = cts.B200Vector.from_host(T0)
+    op.dss(uc, None, 0.0)
+    integ = cts.init(cts.ODEProblem(op.ode_function(), uc, (0.0, 1e6), None), alg_c, dt=dt)
+    integ.cache.set_fusion(fusion)
+    t = 0.0
+    for _ in range(3):
+        step_o(uo, None, t, dt)
+        cts.step_(integ)
+        t = t + dt
+    assert uo.dtype == np.float32
+    np.testing.assert_array_equal(uc.to_host(), uo)
+    assert (integ.cache.stats()["fused_stage_launches"] > 0) == (fusion and not dt32)
+    # and the downcast is not a no-op: the Float64 tableau gives different bits
+    uo2 = T0.copy()
+    model.dss(uo2, None, 0.0)
+    _, step2 = R.make_stepper(model.ode_function(), R.imex_algorithm(name, R.NewtonsMethod(max_iters=1), constraint), uo2)
+    t = 0.0
+    for _ in range(3):
+        step2(uo2, None, t, dt)
+        t = t + dt
+    assert not np.array_equal(uo2, uo)
+
+
+# ------------------------------------------------------------------ saving / callbacks boundary ------
+def test_saveat_async_d2h_host_saver(cts):
+    # integrators.jl:495-526 with a host `save_func`: every save is a stream-ordered cts_memcpy_d2h into its own pinned
+    # buffer (no stall of the step loop); after one synchronisation the saved states equal device-side copies
+    ctx = cts.Context.default()
+    op, u, model, uo = _column_problem(cts, ctx, 16, 8, 8)
+    alg = cts.IMEXAlgorithm(cts.ARS343(), cts.NewtonsMethod(max_iters=1))
+    saver = cts.HostSaver(ctx)
+    integ = cts.init(cts.ODEProblem(op.ode_function(), u, (0.0, 0.1), None), alg, dt=0.01, saveat=(0.0, 0.03, 0.05, 0.1),
+                     save_func=saver)
+    cts.solve_(integ)
+    host = saver.wait()
+    assert integ.sol.t == [0.0, 0.03, 0.05, 0.1] and len(host) == 4
+    # oracle at the same save times
+    _, step = R.make_stepper(model.ode_function(), R.imex_algorithm("ARS343", R.NewtonsMethod(max_iters=1)), uo)
+    want, t = [uo.copy()], 0.0
+    for k in range(10):
+        step(uo, None, t, 0.01)
+        t += 0.01
+        if k + 1 in (3, 5, 10):
+            want.append(uo.copy())
+    for a, b in zip(host, want):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_wall_time_callback_single_rank(cts):
+    # Callbacks.jl:40-90 on one rank: cts_allreduce_max_f64_host is the identity, the callback fires on the fake clock
+    import ctypes as C
+    ctx = cts.Context.default()
+    v = C.c_double(123.5)
+    ctx.check(ctx.lib.cts_allreduce_max_f64_host(ctx.handle, C.byref(v)))
+    assert v.value == 123.5
+    op, u, model, uo = _column_problem(cts, ctx, 16, 4, 6)
+    clock = iter(np.arange(0.0, 100.0, 0.4))          # +0.4 s per query
+    hits = []
+    cb = cts.EveryXWallTimeSeconds(lambda integ: hits.append(integ.step), 1.0, ctx, clock=lambda: float(next(clock)))
+    integ = cts.init(cts.ODEProblem(op.ode_function(), u, (0.0, 0.1), None),
+                     cts.IMEXAlgorithm(cts.ARS343(), cts.NewtonsMethod(max_iters=1)), dt=0.01, callback=cb)
+    cts.solve_(integ)
+    assert hits == [3, 5, 8, 10]   # clock 0.0 at init -> next = 1.0; queries at 0.4, 0.8, 1.2 (step 3) ...
