@@ -178,7 +178,7 @@ def workload_config(n_gpus, stored_w, ny_local=None):
 
 
 # ------------------------------------------------------------------------------------------------
-def build_problem(cts, ctx, part, matrix_free, nx=None, nlev=None, alg=None, nonlinear=False, dt=None):
+def build_problem(cts, ctx, part, matrix_free, nx=None, nlev=None, alg=None, nonlinear=False, dt=None, foreign=False):
     """The column problem on this rank's slab of `part` (hashed inputs keyed by GLOBAL indices, so every sharding sees
     the same field)."""
     import numpy as np
@@ -208,7 +208,7 @@ def build_problem(cts, ctx, part, matrix_free, nx=None, nlev=None, alg=None, non
         op.set_matrix_free(True)
     if alg is None:
         alg = cts.IMEXAlgorithm(cts.ARS343(), cts.NewtonsMethod(max_iters=1, update_j=cts.UpdateEvery(cts.NewTimeStep)))
-    prob = cts.ODEProblem(op.ode_function(), u, (0.0, 1.0e9), None)
+    prob = cts.ODEProblem(op.foreign_ode_function() if foreign else op.ode_function(), u, (0.0, 1.0e9), None)
     integ = cts.init(prob, alg, dt=DT if dt is None else dt, save=False)
     return op, integ, u
 
@@ -344,7 +344,7 @@ def run_ours(args):
         # ---- the timed region: K steps, barrier + synchronize on both sides, CUDA events on the launching stream
         barrier()
         t_wall0 = time.time()
-        l0 = ctx.launch_count()
+        l0, bytes0 = ctx.launch_count(), ctx.bytes_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
         for _ in range(args.steps):
@@ -353,6 +353,7 @@ def run_ours(args):
         barrier()
         ms_noprof = max_over_ranks(ev0.elapsed_time(ev1))
         launches = ctx.launch_count() - l0
+        counted_bytes_per_step = (ctx.bytes_count() - bytes0) / args.steps
         # ---- the same K steps again with CUDA events around every kernel family (external event nodes when the step is a
         # graph): per-kernel table and the roofline's launch durations
         ctx.prof_read()
@@ -514,6 +515,7 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic", "config": workload_config(world, stored_w),
             "roofline": roof,
             "step_hbm": {"algorithmic_bytes_per_dof_step": step_bytes_per_dof(stored_w),
+                         "counted_bytes_per_dof_step": counted_bytes_per_step / ndof_local,
                          "achieved_GBs_per_gpu": step_bytes / (ms_noprof / args.steps * 1e-3) / 1e9,
                          "frac_of_peak": step_bytes / (ms_noprof / args.steps * 1e-3) / 1e9 / peak},
             "kernels": kernels,
@@ -589,6 +591,26 @@ def run_extras(cts, ctx, stream, op, u):
     peak, _ = peaks()
     out = {}
     n = 1 << 27
+    # --- the drop-in (generic-hook) path on the default workload: what a model gets whose T_imp!/Wfact/ldiv! the engine
+    # cannot recognise.  (a) the library's hooks with operator fusion switched off = the reference's pass structure, pass by
+    # pass (K1, K2, T_imp!, K3, K4, K5, K6 per implicit stage; 93w = 744 B/DOF/step); (b) the same hooks as
+    # opaque host closures (Python trampolines -> C ABI): same kernels, plus the host round trip of every callback.
+    part = cts.SlabPartition(NY, 1, 0)
+    for key, foreign in (("C3_generic_hooks", False), ("C3_foreign_hooks", True)):
+        op_g, integ_g, u_g = build_problem(cts, ctx, part, False, foreign=foreign)
+        if not foreign:
+            integ_g.cache.set_fusion(False)
+        op_g.dss(u_g, None, 0.0)
+        l0 = ctx.launch_count()
+        ms = timed(stream, lambda: cts.step_(integ_g), 3, warm=2)
+        launches = (ctx.launch_count() - l0) / 5
+        model = 744
+        out[key] = {"ms_per_step": ms, "dof_stage_per_s": op_g.ndof_owned * STAGES / (ms * 1e-3), "bytes_per_dof_step": model,
+                    "GBs": model * op_g.ndof / (ms * 1e-3) / 1e9, "frac": model * op_g.ndof / (ms * 1e-3) / 1e9 / peak,
+                    "launches_per_step": launches, "fused_stage_launches": integ_g.cache.stats()["fused_stage_launches"],
+                    "passes_per_implicit_stage": 7}
+        del op_g, integ_g, u_g
+        torch.cuda.empty_cache()
     # --- K1 stand-alone: ARS343 final update shape (7 reads + 1 write) and stage-2 shape (2 reads + 1 write)
     vs = [cts.B200Vector.zeros(n, np.float64, ctx).fill_hash(10 + k) for k in range(7)]
     dst = cts.B200Vector.zeros(n, np.float64, ctx)
@@ -667,10 +689,12 @@ def run_c3_f32(cts, ctx, stream):
 
 
 def run_c4(cts, ctx, stream, dtype):
-    """BASELINE configs[3]: IMEXAlgorithm(SSP333(), NewtonsMethod(; max_iters = 2, krylov_method = KrylovMethod(;
-    jacobian_free_jvp = ForwardDiffJVP(), forcing_term = ConstantForcing(rtol)))) on d/dz(K(1+T^2) dT/dz), 2^27 DOF,
-    W (frozen coefficients, batched tridiagonal) as left preconditioner.  Bytes are counted from the executed kernels:
-    per GMRES iteration k (22+5k)w, plus the SSPRK passes."""
+    """BASELINE configs[3] as written: IMEXAlgorithm(SSP333(), NewtonsMethod(; max_iters = 2, krylov_method = KrylovMethod(;
+    jacobian_free_jvp = ForwardDiffJVP(), forcing_term = ConstantForcing(rtol)))) on d/dz(K(1+T^2) dT/dz), 2^27 DOF, the
+    frozen-coefficient W (batched tridiagonal) as left preconditioner, GMRES `memory = 20` and `itmax` at their defaults
+    (newtons_method.jl:433).  The pass count is data dependent, so the algorithmic bytes are those of the kernels that
+    actually ran (`cts_bytes_count`: every launch adds (arrays read + written) x n x w, the per-kernel figures of
+    SURVEY §8d); achieved GB/s = those bytes / step time."""
     import numpy as np
     nlev, nx, ny = NLEV, NX, NY
     K = cts.B200Vector.zeros(nx * ny, dtype, ctx).fill_hash(2, 0, 0.25, 2.0)
@@ -681,8 +705,7 @@ def run_c4(cts, ctx, stream, dtype):
     # ForwardDiffStepSize3 shrinks like 1/sqrt(n): at n = 2^27 the Float32 perturbation eps*v_i falls below eps(Float32)*x_i
     # and the JVP vanishes; `step_adjustment` (ForwardDiffJVP's own knob, newtons_method.jl:152-168) restores it.
     adj = 4096.0 if np.dtype(dtype) == np.float32 else 1.0
-    km = cts.KrylovMethod(jacobian_free_jvp=cts.ForwardDiffJVP(step_adjustment=adj), forcing_term=cts.ConstantForcing(rtol),
-                          itmax=8, memory=8)
+    km = cts.KrylovMethod(jacobian_free_jvp=cts.ForwardDiffJVP(step_adjustment=adj), forcing_term=cts.ConstantForcing(rtol))
     alg = cts.IMEXAlgorithm(cts.SSP333(), cts.NewtonsMethod(max_iters=2, krylov_method=km))
     integ = cts.init(cts.ODEProblem(op.ode_function(explicit=False), u, (0.0, 1e9), None), alg, dt=2e-3, save=False)
     cts.step_(integ)
@@ -690,7 +713,9 @@ def run_c4(cts, ctx, stream, dtype):
     steps = 2
     ctx.prof_read()
     ctx.prof_enable(True)
+    b0, l0 = ctx.bytes_count(), ctx.launch_count()
     ms = timed(stream, lambda: cts.step_(integ), steps, warm=0)
+    nbytes, launches = (ctx.bytes_count() - b0) / steps, (ctx.launch_count() - l0) / steps
     prof = ctx.prof_read()
     ctx.prof_enable(False)
     s1 = integ.cache.stats()
@@ -699,11 +724,15 @@ def run_c4(cts, ctx, stream, dtype):
     n = nx * ny * nlev
     import torch
     finite = bool(torch.isfinite(u.tensor).all())
+    peak = peaks()[0]
+    gbs = nbytes / (ms * 1e-3) / 1e9
     res = {"ms_per_step": ms, "dof_stage_per_s": n * 3 / (ms * 1e-3), "krylov_iters_per_step": kit, "newton_iters_per_step": nit,
-           "rtol": rtol, "dt": 2e-3, "finite": finite, "jvp_step_adjustment": adj,
+           "rtol": rtol, "dt": 2e-3, "gmres_memory": km.memory, "gmres_itmax": "default (2n)", "finite": finite,
+           "jvp_step_adjustment": adj,
+           "algorithmic_bytes_per_step": nbytes, "bytes_per_dof_step": nbytes / n, "GBs": gbs, "frac": gbs / peak,
            "kernels_ms_per_step": {k: round(v[0] / steps, 3) for k, v in prof.items() if v[1]},
-           "launches_per_step": sum(v[1] for v in prof.values()) / steps,
-           "note": "Newton-Krylov work is data dependent; bytes/step = sum over executed kernels, see DESIGN.md"}
+           "launches_per_step": launches,
+           "note": "bytes = sum over the executed kernels (cts_bytes_count); the Newton-Krylov pass count is data dependent"}
     del integ, op, u, K
     return res
 

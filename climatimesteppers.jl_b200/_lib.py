@@ -154,6 +154,7 @@ SIGNATURES = [
     ("cts_imex_cache_graph_stats", _I, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("cts_comm_enable_peer_halo", _I, [_P, _SZ]),
     ("cts_comm_halo_path", _I, [_P, C.POINTER(C.c_int)]),
+    ("cts_bytes_count", _I, [_P, C.POINTER(C.c_uint64)]),
     ("cts_set_reduction_window", _I, [_P, _SZ, _SZ]),
     ("cts_set_reduction_layout", _I, [_P, _SZ, _SZ, _SZ, _SZ, _SZ]),
     ("cts_reduction_global_length", _I, [_P, _SZ, C.POINTER(C.c_size_t)]),

@@ -18,6 +18,7 @@ struct cts_ctx {
   int num_sms = 148;
   std::string err;
   uint64_t launches = 0;
+  uint64_t bytes = 0;  // algorithmic HBM bytes of the kernels launched so far: (arrays read + arrays written) x n x sizeof(FT)
   // reduction scratch (reduce.cu): per-chunk partial sums, [k][n_chunks_global] (grown on demand)
   double* d_partials = nullptr;   // this rank's chunk partials (entries of chunks owned by other ranks stay zero)
   double* d_partials_g = nullptr; // all ranks' chunk partials after the exchange (multi-rank layouts only)
@@ -108,6 +109,9 @@ inline int cts_fail(cts_ctx* ctx, int code, const std::string& msg) {
                                             " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
   } while (0)
 
+// algorithmic bytes of a pass over `arrays` state-sized arrays of n elements of w bytes (SURVEY §8d's per-kernel figures)
+#define CTS_COUNT_BYTES(ctx, arrays, n, w) ((ctx)->bytes += (uint64_t)(arrays) * (uint64_t)(n) * (uint64_t)(w))
+
 #define CTS_TRY(expr)        \
   do {                       \
     int _r = (expr);         \
@@ -126,6 +130,8 @@ inline bool cts_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p
 
 int cts_newton_residual_ex(cts_ctx* ctx, cts_dtype ft, size_t n, void* r, const void* U0, double dtgamma, const void* Up, int native);
 int cts_timp_from_stage_ex(cts_ctx* ctx, cts_dtype ft, size_t n, void* T, const void* U, const void* temp, double dtgamma, int native);
+// K5 + K6 in one pass: U = U - dx ; T_imp = (U_new - U_old)/dtγ  (one-iteration Newton, nothing between K5 and K6)
+int cts_newton_update_timp(cts_ctx* ctx, cts_dtype ft, size_t n, void* U, void* T_imp, const void* dx, double dtgamma, int native);
 // ---- internal entry points used across translation units ------------------------------------
 // fused LSRK stage with the advection stencil (ops.cu); out-of-place in u.
 int cts_advection_fused_stage(cts_op_advection* op, void* u_out, const void* u_in, void* du, double A, double dtB,

@@ -88,6 +88,13 @@ int cts_launch_count(cts_ctx* ctx, uint64_t* out) {
   return CTS_OK;
 }
 
+int cts_bytes_count(cts_ctx* ctx, uint64_t* out) {
+  CTS_CHECK_CTX(ctx);
+  if (!out) return CTS_EINVAL;
+  *out = ctx->bytes;
+  return CTS_OK;
+}
+
 int cts_prof_enable(cts_ctx* ctx, int enabled) {
   CTS_CHECK_CTX(ctx);
   ctx->prof_on = enabled != 0;

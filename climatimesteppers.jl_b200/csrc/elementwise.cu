@@ -87,6 +87,7 @@ int launch_axpy(cts_ctx* ctx, size_t n, void* out, void* out2, double c0, const 
     aligned = aligned && cts_aligned16(terms[k]);
   }
   constexpr int VN = Vec<T>::N;
+  CTS_COUNT_BYTES(ctx, 1 + NT + 1 + (out2 ? 1 : 0), n, sizeof(T));  // K1/K2: base + terms in, out (+ out2)
   // more independent requests per thread when there are few operands
   constexpr int UNROLL = (NT <= 1) ? 4 : (NT <= 4 ? 2 : 1);
   size_t nvec = aligned ? n / VN : 0;
@@ -243,6 +244,7 @@ int launch_ssprk(cts_ctx* ctx, size_t n, SspArgs<NT> a, const double* coef, cons
   }
   constexpr int VN = Vec<T>::N;
   constexpr int UNROLL = (NT <= 2) ? 2 : 1;
+  CTS_COUNT_BYTES(ctx, 2 + (a.texp ? 1 : 0) + NT + (a.out_exp ? 1 : 0) + (a.ax.out ? 1 : 0) + (a.ax.out2 ? 1 : 0), n, sizeof(T));  // K11
   size_t nvec = aligned ? n / VN : 0;
   if (nvec > 0) {
     size_t per_block = (size_t)256 * UNROLL;
@@ -354,6 +356,7 @@ int launch_chain(cts_ctx* ctx, size_t n, void* out, const void* base, const doub
   }
   constexpr int VN = Vec<T>::N;
   constexpr int UNROLL = (NT <= 1) ? 4 : (NT <= 4 ? 2 : 1);
+  CTS_COUNT_BYTES(ctx, (base ? 1 : 0) + NT + 1, n, sizeof(T));
   const int round_each = sizeof(T) == 4;
   size_t nvec = aligned ? n / VN : 0;
   if (nvec > 0) {
@@ -511,6 +514,7 @@ template <typename T, int NIN, typename F>
 int launch_ew(cts_ctx* ctx, size_t n, void* out, const void* a, const void* b, const void* c, F f) {
   if (n == 0) return CTS_OK;
   constexpr int VN = Vec<T>::N;
+  CTS_COUNT_BYTES(ctx, NIN + 1, n, sizeof(T));  // K3 4w, K5/K6/K7/K8/K10 3w, ...
   bool aligned = cts_aligned16(out) && cts_aligned16(a) && (NIN < 2 || cts_aligned16(b)) && (NIN < 3 || cts_aligned16(c));
   size_t nvec = aligned ? n / VN : 0;
   if (nvec > 0) {
@@ -526,6 +530,40 @@ int launch_ew(cts_ctx* ctx, size_t n, void* out, const void* a, const void* b, c
     CTS_LAUNCH_CHECK(ctx);
   }
   return CTS_OK;
+}
+
+// K5 + K6 of a one-iteration Newton solve in one pass (newtons_method.jl:651 and imex_ark.jl:269):
+//   U = x - Δx ;  T_imp = (U - x) / dtγ          (x == temp bit for bit: nothing has touched U since `temp = U`)
+// 4w B/DOF instead of 3w + 3w.  NATIVE: dtγ has the state precision (Float32 dt and a downcast tableau).
+template <typename T, bool NATIVE>
+__global__ void __launch_bounds__(256) newton_update_timp_kernel(T* __restrict__ U, T* __restrict__ Timp,
+                                                                 const T* __restrict__ dx, double dtg, size_t nvec,
+                                                                 size_t n) {
+  using V = typename Vec<T>::type;
+  constexpr int VN = Vec<T>::N;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  auto one = [&](T x, T d, T& u, T& t) {
+    u = op_sub(x, d);
+    const T diff = op_sub(u, x);
+    t = NATIVE ? op_div(diff, (T)dtg) : (T)__ddiv_rn((double)diff, dtg);
+  };
+  if (i < nvec) {
+    T ex[VN], ed[VN], eu[VN], et[VN];
+    vec_unpack<T>(reinterpret_cast<const V*>(U)[i], ex);
+    vec_unpack<T>(reinterpret_cast<const V*>(dx)[i], ed);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) one(ex[e], ed[e], eu[e], et[e]);
+    reinterpret_cast<V*>(U)[i] = vec_pack<T>(eu);
+    reinterpret_cast<V*>(Timp)[i] = vec_pack<T>(et);
+  }
+  // scalar tail (and the whole range when the operands are not 16-byte aligned: nvec == 0)
+  const size_t j = nvec * VN + i;
+  if (j < n) {
+    T u, t;
+    one(U[j], dx[j], u, t);
+    U[j] = u;
+    Timp[j] = t;
+  }
 }
 
 // functors ------------------------------------------------------------------------------------
@@ -704,6 +742,28 @@ int cts_axpby(cts_ctx* ctx, cts_dtype ft, size_t n, double a, const void* x, dou
 
 }  // extern "C"
 
+int cts_newton_update_timp(cts_ctx* ctx, cts_dtype ft, size_t n, void* U, void* T_imp, const void* dx, double dtgamma,
+                           int native) {
+  CTS_CHECK_CTX(ctx);
+  if (!U || !T_imp || !dx || U == T_imp) return cts_fail(ctx, CTS_EINVAL, "cts_newton_update_timp: bad argument");
+  const bool aligned = cts_aligned16(U) && cts_aligned16(T_imp) && cts_aligned16(dx);
+  CTS_COUNT_BYTES(ctx, 4, n, cts_sizeof(ft));
+  if (ft == CTS_F64) {
+    const size_t nvec = aligned ? n / 2 : 0;
+    const size_t work = nvec > n - nvec * 2 ? nvec : n - nvec * 2;
+    newton_update_timp_kernel<double, false><<<(unsigned)((work + 255) / 256), 256, 0, ctx->stream>>>((double*)U, (double*)T_imp, (const double*)dx, dtgamma, nvec, n);
+  } else {
+    const size_t nvec = aligned ? n / 4 : 0;
+    const size_t work = nvec > n - nvec * 4 ? nvec : n - nvec * 4;
+    if (native)
+      newton_update_timp_kernel<float, true><<<(unsigned)((work + 255) / 256), 256, 0, ctx->stream>>>((float*)U, (float*)T_imp, (const float*)dx, dtgamma, nvec, n);
+    else
+      newton_update_timp_kernel<float, false><<<(unsigned)((work + 255) / 256), 256, 0, ctx->stream>>>((float*)U, (float*)T_imp, (const float*)dx, dtgamma, nvec, n);
+  }
+  CTS_LAUNCH_CHECK(ctx);
+  return CTS_OK;
+}
+
 // K3 / K6 with the type of dtγ made explicit: native != 0 (Float32 state only) evaluates the broadcast in Float32
 int cts_newton_residual_ex(cts_ctx* ctx, cts_dtype ft, size_t n, void* r, const void* U0, double dtgamma, const void* Up,
                            int native) {
@@ -764,6 +824,7 @@ extern "C" int cts_lincomb(cts_ctx* ctx, cts_dtype ft, size_t n, void* out, int 
     LincombArgs a;
     a.k = (k - j0 < kLincombMax) ? k - j0 : kLincombMax;
     a.accumulate = (j0 > 0) || accumulate;
+    CTS_COUNT_BYTES(ctx, a.k + 1 + (a.accumulate ? 1 : 0), n, cts_sizeof(ft));
     for (int j = 0; j < a.k; ++j) {
       a.V[j] = V[j0 + j];
       a.coef[j] = coef[j0 + j];

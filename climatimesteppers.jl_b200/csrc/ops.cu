@@ -97,6 +97,7 @@ int launch_advection(cts_op_advection* op, void* du, const void* u, void* u_out,
   const size_t n = op->n;
   constexpr int VN = Vec<T>::N;
   bool vec = (n % VN) == 0 && cts_aligned16(du) && cts_aligned16(u) && (!FUSED || cts_aligned16(u_out));
+  CTS_COUNT_BYTES(ctx, FUSED ? 4 : 3, n, sizeof(T));  // K10f (+ K10): u, du in; du (, u) out
   T negc = (T)(-op->c), dx = (T)op->dx;
   if (vec) {
     size_t blocks = (n / VN + 255) / 256;
@@ -977,6 +978,279 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pipelined, warp-specialised, persistent variant of the fused stage (one CTA per SM loops over its tiles).
+//
+// The kernels above give every 16-column tile to its own short-lived CTA whose load -> solve -> store phases are serial;
+// five such CTAs per SM are the only overlap, three of four warps idle during a solve, and the loads in flight come in
+// bursts (ncu: 30 % issue utilisation, DRAM at 67-80 %).  Here the phases of DIFFERENT tiles run concurrently in
+// dedicated warps of one resident CTA, coupled by mbarriers over shared-memory rings:
+//
+//   producer  (1 warp)   bulk-TMA (cp.async.bulk + mbarrier complete_tx) of ALL operands of tile t+1, t+2: base and the NT
+//                        tendencies as one contiguous 8 KiB copy each into a 2-deep staging ring, dl/d/du column by column
+//                        into the padded tiles of a slot ring.  No registers, whole tiles in flight (~150 KiB per SM).
+//   assemblers (4 warps) phase A of tile t: staging -> U0 = K1(base, terms) (LDS.128, conflict free) -> Newton residual via
+//                        warp shuffles -> slot {U0, r};  frees the staging buffer.
+//   solvers   (4 warps)  phase B: two-sided product-form Thomas on 16 columns per warp, in place in the slot.
+//   epilogue  (4 warps)  phase C of tile t-1..t-2: U = U0 - dx, T_imp = (U - U0)/dtγ (and W when the stage folds Wfact in),
+//                        128-bit coalesced stores;  frees the slot.
+//
+// Arithmetic, operation order and rounding are those of the kernels above (same device functions), so results are
+// bit-identical; only the schedule differs.  A tile is always 512 16-byte vectors (16 columns of 64 Float64 levels,
+// 32 columns of 64 Float32 levels, ...), so one 128-thread group covers it with 4 vectors per thread and a column is a
+// power-of-two lane group of one warp.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPipeAsm = 128;
+constexpr int kPipeSolverWarps = 4;
+constexpr int kPipeStore = 128;
+constexpr int kPipeThreads = 32 + kPipeAsm + 32 * kPipeSolverWarps + kPipeStore;  // 416
+constexpr int kPipeTileVecs = 512;
+constexpr int kPipeOpStages = 2;
+constexpr int kPipeMaxSlots = 8;
+constexpr int kPipeBarBytes = 512;
+constexpr int kPipeOpBytes = kPipeTileVecs * 16;  // one operand tile in the staging ring
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <typename T, typename C, int NT, bool MATRIX_FREE, int N1SPEC>
+__global__ void __launch_bounds__(kPipeThreads, 1) column_fused_stage_pipe_kernel(const FusedArgs<NT> a, int nslots) {
+  using V = typename Vec<T>::type;
+  constexpr int VN = Vec<T>::N;
+  constexpr int NTS = NT > 0 ? NT : 1;
+  constexpr int kRounds = kPipeTileVecs / kPipeAsm;  // vectors per thread and tile
+  extern __shared__ __align__(128) char smem[];
+  const int nlev = a.nlev;
+  const int pitch = a.pitch;
+  const int col_bytes = nlev * (int)sizeof(T);
+  const int cpc = col_bytes / 16;               // vectors per column: a power of two <= 32
+  const int cshift = 31 - __clz(cpc);
+  const int kCols = kPipeTileVecs / cpc;        // columns per tile
+  const int jobs = kCols / 16;                  // solver jobs (16 columns each) per tile
+  const int tile_bytes = kCols * pitch;         // a padded tile (conflict-free column pitch)
+  const int slot_bytes = tile_bytes + kPipeOpBytes + (MATRIX_FREE ? 1 : 3) * tile_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* op_full = bars;                     // [2]  staging buffer b holds tile i's operands (TMA complete_tx)
+  uint64_t* op_empty = bars + 2;                // [2]  the assemblers are done with staging buffer b
+  uint64_t* w_full = bars + 4;                  // [8]  slot s holds tile i's dl/d/du (TMA complete_tx)
+  uint64_t* s_full = bars + 4 + kPipeMaxSlots;  // [8]  slot s holds U0 and the residual
+  uint64_t* s_solved = bars + 4 + 2 * kPipeMaxSlots;
+  uint64_t* s_empty = bars + 4 + 3 * kPipeMaxSlots;
+  char* stage = smem + kPipeBarBytes;           // [2][1 + NT][8 KiB]
+  char* slots = stage + kPipeOpStages * (1 + NT) * kPipeOpBytes;
+
+  const size_t ntiles = (a.ncols + kCols - 1) / kCols;
+  const int count = ntiles > blockIdx.x ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < kPipeOpStages; ++b) {
+      mbar_init(op_full + b, 1);
+      mbar_init(op_empty + b, kPipeAsm);
+    }
+    for (int s = 0; s < nslots; ++s) {
+      mbar_init(w_full + s, 1);
+      mbar_init(s_full + s, kPipeAsm);
+      mbar_init(s_solved + s, 32 * jobs);
+      mbar_init(s_empty + s, kPipeStore);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto tile_of = [&](int i, size_t& col0, int& nvalid) {
+    const size_t tile = blockIdx.x + (size_t)i * gridDim.x;
+    col0 = tile * kCols;
+    nvalid = (int)((a.ncols - col0) < (size_t)kCols ? (a.ncols - col0) : (size_t)kCols);
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer ---------------------------------
+    for (int i = 0; i < count; ++i) {
+      size_t col0;
+      int nvalid;
+      tile_of(i, col0, nvalid);
+      const size_t goff = col0 * (size_t)nlev;
+      const uint32_t flat = (uint32_t)(nvalid * col_bytes);
+      const int b = i % kPipeOpStages, s = i % nslots;
+      char* st = stage + (size_t)b * (1 + NT) * kPipeOpBytes;
+      if (lane == 0) {
+        mbar_wait(op_empty + b, ((i / kPipeOpStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(op_full + b, (uint32_t)(1 + NT) * flat);
+        bulk_g2s(st, (const T*)a.ax.base + goff, flat, op_full + b);
+#pragma unroll
+        for (int k = 0; k < NT; ++k) bulk_g2s(st + (k + 1) * kPipeOpBytes, (const T*)a.ax.terms[k] + goff, flat, op_full + b);
+      }
+      if (!MATRIX_FREE) {
+        char* sl = slots + (size_t)s * slot_bytes + tile_bytes + kPipeOpBytes;  // dl | d | du tiles of the slot
+        if (lane == 0) {
+          mbar_wait(s_empty + s, ((i / nslots) & 1) ^ 1);
+          mbar_arrive_expect_tx(w_full + s, 3u * flat);
+        }
+        __syncwarp();
+        for (int c = lane; c < nvalid; c += 32) {
+          const size_t g = goff + (size_t)c * nlev;
+          bulk_g2s(sl + c * pitch, (const T*)a.dl + g, col_bytes, w_full + s);
+          bulk_g2s(sl + tile_bytes + c * pitch, (const T*)a.d + g, col_bytes, w_full + s);
+          bulk_g2s(sl + 2 * tile_bytes + c * pitch, (const T*)a.du + g, col_bytes, w_full + s);
+        }
+      }
+    }
+  } else if (warp < 1 + kPipeAsm / 32) {
+    // ------------------------------------------------------------------ assemblers (phase A) ----------------------
+    const int at = threadIdx.x - 32;
+    for (int i = 0; i < count; ++i) {
+      size_t col0;
+      int nvalid;
+      tile_of(i, col0, nvalid);
+      const int total = nvalid * cpc;
+      const size_t gvec0 = col0 * (size_t)nlev * sizeof(T) / 16;
+      const int b = i % kPipeOpStages, s = i % nslots;
+      const char* st = stage + (size_t)b * (1 + NT) * kPipeOpBytes;
+      char* sx = slots + (size_t)s * slot_bytes;
+      V* sU0 = reinterpret_cast<V*>(sx + tile_bytes);
+      mbar_wait(op_full + b, (i / kPipeOpStages) & 1);
+      mbar_wait(s_empty + s, ((i / nslots) & 1) ^ 1);
+      // (the operands sit in shared memory: every round loads what it needs, no register staging across rounds)
+#pragma unroll 2
+      for (int r = 0; r < kRounds; ++r) {
+        const int q = at + r * kPipeAsm;
+        const bool ok = q < total;
+        const int col = q >> cshift, kk = q & (cpc - 1);
+        V vb, vt[NTS];
+        T acol = T(0);
+        if (ok) {
+          vb = reinterpret_cast<const V*>(st)[q];
+#pragma unroll
+          for (int t = 0; t < NT; ++t) vt[t] = reinterpret_cast<const V*>(st + (t + 1) * kPipeOpBytes)[q];
+          acol = ((const T*)a.Kcol)[col0 + col];
+        }
+        T eb[VN], uu[VN], rr[VN], et[NTS][VN];
+        vec_unpack<T>(vb, eb);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) vec_unpack<T>(vt[t], et[t]);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+          T x[NTS];
+#pragma unroll
+          for (int t = 0; t < NT; ++t) x[t] = et[t][e];
+          constexpr int N1 = GroupSplit<NT, N1SPEC>::value;
+          if constexpr (N1 >= 0)
+            uu[e] = axpy_combine_n1<T, C, NT, (N1 >= 0 ? N1 : 0)>(eb[e], x, a.ax);
+          else
+            uu[e] = axpy_combine<T, C, NT>(eb[e], x, a.ax);
+        }
+        const V vu = vec_pack<T>(uu);
+        T below = __shfl_up_sync(0xffffffffu, uu[VN - 1], 1, cpc);
+        T above = __shfl_down_sync(0xffffffffu, uu[0], 1, cpc);
+        if (kk == 0) below = T(0);
+        if (kk == cpc - 1) above = T(0);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+          const T um = e > 0 ? uu[e > 0 ? e - 1 : 0] : below;
+          const T up = e + 1 < VN ? uu[e + 1 < VN ? e + 1 : e] : above;
+          const T ti = timp_linear<T>(acol, um, uu[e], up);
+          rr[e] = (T)__dsub_rn(__dadd_rn((double)uu[e], __dmul_rn(a.dtg, (double)ti)), (double)uu[e]);
+        }
+        if (ok) {
+          sU0[q] = vu;
+          *reinterpret_cast<V*>(sx + col * pitch + kk * 16) = vec_pack<T>(rr);
+          if (a.temp) reinterpret_cast<V*>(a.temp)[gvec0 + q] = vu;
+        }
+      }
+      mbar_arrive(s_full + s);
+      mbar_arrive(op_empty + b);
+    }
+  } else if (warp < 1 + kPipeAsm / 32 + kPipeSolverWarps) {
+    // ------------------------------------------------------------------ solvers (phase B) -------------------------
+    const int w = warp - 1 - kPipeAsm / 32;
+    for (int i = 0; i < count; ++i) {
+      size_t col0;
+      int nvalid;
+      tile_of(i, col0, nvalid);
+      const int s = i % nslots;
+      char* sx = slots + (size_t)s * slot_bytes;
+      char* sw = sx + tile_bytes + kPipeOpBytes;
+      bool waited = false;
+      for (int j = 0; j < jobs; ++j) {
+        if (((i * jobs + j) % kPipeSolverWarps) != w) continue;
+        if (!waited) {
+          mbar_wait(s_full + s, (i / nslots) & 1);
+          if (!MATRIX_FREE) mbar_wait(w_full + s, (i / nslots) & 1);
+          waited = true;
+        }
+        const int col = j * 16 + lane_column(lane);
+        const bool is_up = lane_is_up(lane);
+        const bool valid = col < nvalid;
+        const int col_off = col * pitch;
+        if (MATRIX_FREE) {
+          const T ac = valid ? ((const T*)a.Kcol)[col0 + col] : T(0);
+          const double o = __dmul_rn(a.dtg, (double)ac);
+          ConstRows<T> rows{(T)o, (T)__dsub_rn(__dmul_rn(-2.0, o), 1.0), sw};
+          babe_solve_lanepair<T, ConstRows<T>, RhsFromTile<T>, true>(rows, RhsFromTile<T>{}, sx, col_off, nlev, is_up, valid);
+        } else {
+          StoredRows<T> rows{sw, sw + tile_bytes, sw + 2 * tile_bytes};
+          babe_solve_lanepair<T, StoredRows<T>, RhsFromTile<T>, true>(rows, RhsFromTile<T>{}, sx, col_off, nlev, is_up, valid);
+        }
+        fence_proxy_async_smem();  // the factors overwrote dl/du in place; the next user of these bytes is a bulk copy
+        mbar_arrive(s_solved + s);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (phase C) ------------------------
+    const int et_ = threadIdx.x - 32 - kPipeAsm - 32 * kPipeSolverWarps;
+    const DivConst dc = div_const_prepare(a.dtg);
+    for (int i = 0; i < count; ++i) {
+      size_t col0;
+      int nvalid;
+      tile_of(i, col0, nvalid);
+      const int total = nvalid * cpc;
+      const size_t gvec0 = col0 * (size_t)nlev * sizeof(T) / 16;
+      const int s = i % nslots;
+      const char* sx = slots + (size_t)s * slot_bytes;
+      const V* sU0 = reinterpret_cast<const V*>(sx + tile_bytes);
+      mbar_wait(s_solved + s, (i / nslots) & 1);
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        const int q = et_ + r * kPipeStore;
+        if (q >= total) continue;
+        const int col = q >> cshift, kk = q & (cpc - 1);
+        T e0[VN], ex[VN], eU[VN], eT[VN];
+        vec_unpack<T>(sU0[q], e0);
+        vec_unpack<T>(*reinterpret_cast<const V*>(sx + col * pitch + kk * 16), ex);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+          eU[e] = rsub(e0[e], ex[e]);
+          eT[e] = (T)div_const((double)rsub(eU[e], e0[e]), dc);
+        }
+        reinterpret_cast<V*>(a.U)[gvec0 + q] = vec_pack<T>(eU);
+        if (a.Timp) reinterpret_cast<V*>(a.Timp)[gvec0 + q] = vec_pack<T>(eT);
+        if (MATRIX_FREE && a.emit_w) {  // same expressions as column_wfact_kernel
+          const double o = __dmul_rn(a.dtg, (double)((const T*)a.Kcol)[col0 + col]);
+          T eo[VN], ed[VN];
+#pragma unroll
+          for (int e = 0; e < VN; ++e) {
+            eo[e] = (T)o;
+            ed[e] = (T)__dsub_rn(__dmul_rn(-2.0, o), 1.0);
+          }
+          const V vo = vec_pack<T>(eo);
+          reinterpret_cast<V*>(const_cast<void*>(a.dl))[gvec0 + q] = vo;
+          reinterpret_cast<V*>(const_cast<void*>(a.d))[gvec0 + q] = vec_pack<T>(ed);
+          reinterpret_cast<V*>(const_cast<void*>(a.du))[gvec0 + q] = vo;
+        }
+      }
+      mbar_arrive(s_empty + s);
+    }
+  }
+}
+
+// smem of the pipelined kernel for `nslots` slots; 0 slots = does not fit
+static size_t pipe_smem_bytes(int nt, int tile_bytes, bool mf, int nslots) {
+  return (size_t)kPipeBarBytes + (size_t)kPipeOpStages * (1 + nt) * kPipeOpBytes +
+         (size_t)nslots * ((size_t)tile_bytes + kPipeOpBytes + (size_t)(mf ? 1 : 3) * tile_bytes);
+}
+
 template <typename T, typename C, int NT>
 int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
   cts_ctx* ctx = op->ctx;
@@ -1002,6 +1276,8 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
   a.pitch = pitch_bytes(op->d.nlev, sizeof(T));
   const bool mf = op->matrix_free || s->emit_W;
   a.emit_w = s->emit_W;
+  // base + terms in, U (+ T_imp, temp) out, dl/d/du read -- or written by the stage that folds Wfact in
+  CTS_COUNT_BYTES(ctx, 1 + NT + 1 + (s->T_imp ? 1 : 0) + (s->temp ? 1 : 0) + ((!op->matrix_free) ? 3 : 0), cts_op_column_ndof(op), sizeof(T));
   if (!op->matrix_free) {
     if (!s->W) return cts_fail(ctx, CTS_EINVAL, "fused stage: stored W required");
     a.dl = s->W->dl;
@@ -1016,6 +1292,46 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
   static const bool no_reg = getenv("CTS_FUSED_NO_REG") != nullptr;      // developer aid: force the 5-tile kernel
   const int cpc = op->d.nlev * (int)sizeof(T) / 16;
   constexpr int kCols = TileShape<T>::kCols;
+  // pipelined persistent kernel: a tile is 512 vectors, a column 8..32 of them (a power of two)
+  static const bool no_pipe = getenv("CTS_FUSED_NO_PIPE") != nullptr;  // developer aid: the one-tile-per-CTA kernels
+  if constexpr (NT <= 5) {
+  if (!timeline && !no_reg && !no_pipe && (cpc == 8 || cpc == 16 || cpc == 32)) {
+    const int pcols = kPipeTileVecs / cpc;
+    const int ptile = pcols * a.pitch;
+    int nslots = kPipeMaxSlots;
+    while (nslots > 0 && pipe_smem_bytes(NT, ptile, mf, nslots) > (size_t)227 * 1024) --nslots;
+    const size_t ptiles = (op->ncols + pcols - 1) / pcols;
+    if (nslots >= 3 && ptiles >= 1) {
+      const size_t psmem = pipe_smem_bytes(NT, ptile, mf, nslots);
+      const unsigned grid = (unsigned)std::min<size_t>(ptiles, (size_t)ctx->num_sms);
+      a.dbg = nullptr;
+      auto launchp = [&](auto k) -> int {
+        CTS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        k<<<grid, kPipeThreads, psmem, ctx->stream>>>(a, nslots);
+        return CTS_OK;
+      };
+      int spec = 0;
+      if constexpr (NT >= 1) {
+        if (a.ax.n1 == NT)
+          spec = 1;
+        else if (a.ax.n1 == (NT + 1) / 2)
+          spec = 2;
+      }
+      if (spec == 1) {
+        if (mf) CTS_TRY(launchp(column_fused_stage_pipe_kernel<T, C, NT, true, 1>));
+        else CTS_TRY(launchp(column_fused_stage_pipe_kernel<T, C, NT, false, 1>));
+      } else if (spec == 2) {
+        if (mf) CTS_TRY(launchp(column_fused_stage_pipe_kernel<T, C, NT, true, 2>));
+        else CTS_TRY(launchp(column_fused_stage_pipe_kernel<T, C, NT, false, 2>));
+      } else {
+        if (mf) CTS_TRY(launchp(column_fused_stage_pipe_kernel<T, C, NT, true, 0>));
+        else CTS_TRY(launchp(column_fused_stage_pipe_kernel<T, C, NT, false, 0>));
+      }
+      CTS_LAUNCH_CHECK(ctx);
+      return CTS_OK;
+    }
+  }
+  }
   if (!timeline && !no_reg && cpc >= 1 && cpc * kCols <= kKeep * kFusedThreads && (cpc & (cpc - 1)) == 0) {
     tiles = (op->ncols + kCols - 1) / kCols;
     size_t smem_reg = (size_t)(mf ? 2 : 4) * kCols * a.pitch + 16 + ((kCols * sizeof(T) + 15) / 16) * 16 +
@@ -1140,6 +1456,7 @@ int launch_final(cts_op_column* op, const cts_final_update_args* s, size_t jr_be
   a.has_src = d.S_lev != nullptr;
   a.jr_begin = jr_begin;
   a.jr_end = jr_end;
+  CTS_COUNT_BYTES(ctx, 3 + NT, (jr_end - jr_begin) * a.row_elems, sizeof(T));  // u, U_s, terms in; u out
   constexpr int ROWS = 8;
   constexpr int VN = Vec<T>::N;
   dim3 grid((unsigned)((a.row_elems / VN + 255) / 256), (unsigned)((jr_end - jr_begin + ROWS - 1) / ROWS));
@@ -1207,6 +1524,7 @@ int cts_column_fused_residual(cts_op_column* op, void* out, const void* x, const
   column_residual_kernel<T, NONLIN, JVP><<<(unsigned)((n / Vec<T>::N + 255) / 256), 256, 0, ctx->stream>>>(            \
       (T*)out, (const T*)x, (const T*)dx, (const T*)U0, (const T*)f, (const T*)op->a_col, (T)eps, dtg, nl, n / Vec<T>::N)
   const bool nonlin = op->d.nonlinear, jvp = dx != nullptr;
+  CTS_COUNT_BYTES(ctx, jvp ? 5 : 3, n, cts_sizeof(op->ft));
   if (op->ft == CTS_F64) {
     if (nonlin) { if (jvp) LAUNCH(double, true, true); else LAUNCH(double, true, false); }
     else        { if (jvp) LAUNCH(double, false, true); else LAUNCH(double, false, false); }
@@ -1305,6 +1623,7 @@ int cts_op_column_T_imp(void* vop, void* du, const void* u, double t) {
   size_t n = cts_op_column_ndof(op);
   size_t blocks = (n + 255) / 256;
   const int nl = op->d.nlev;
+  CTS_COUNT_BYTES(ctx, 2, n, cts_sizeof(op->ft));
   if (op->ft == CTS_F64) {
     if (op->d.nonlinear)
       column_timp_kernel<double, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)du, (const double*)u, (const double*)op->a_col, nl, n);
@@ -1328,6 +1647,7 @@ int cts_op_column_Wfact(void* vop, void* vW, const void* u, double dtgamma, doub
   size_t n = cts_op_column_ndof(op);
   size_t blocks = (n + 255) / 256;
   const int nl = op->d.nlev;
+  CTS_COUNT_BYTES(ctx, op->d.nonlinear ? 4 : 3, n, cts_sizeof(op->ft));
   if (op->ft == CTS_F64) {
     if (op->d.nonlinear)
       column_wfact_kernel<double, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)W->dl, (double*)W->d, (double*)W->du, (const double*)u, (const double*)op->a_col, dtgamma, nl, n);
@@ -1368,6 +1688,7 @@ static int column_T_exp_rows(cts_op_column* op, void* du_exp, const void* u, dou
   const bool vec = (d.nlev % vn) == 0 && cts_aligned16(du_exp) && cts_aligned16(u) && (!has_src || cts_aligned16(d.S_lev));
   const size_t row_elems = d.nx * (size_t)d.nlev;
   const size_t nrows = jr_end - jr_begin;
+  CTS_COUNT_BYTES(ctx, 2, nrows * row_elems, cts_sizeof(op->ft));
   if (vec && row_elems < (1ull << 31) && d.nu != 0.0 && (nrows + 7) / 8 <= 65535) {
     // strips of 8 rows (25 % of the rows are fetched twice, from L2): measured best of 8/16/32/64/128 on B200
     constexpr int ROWS = 8;

@@ -360,6 +360,7 @@ int launch_reduce(cts_ctx* ctx, size_t n, const void* const* xs, const void* y) 
   a.y = y ? static_cast<const char*>(y) + p.off * sizeof(T) : nullptr;
   if (y) aligned = aligned && cts_aligned16(a.y);
   a.n = p.n;
+  CTS_COUNT_BYTES(ctx, K + (y ? 1 : 0), p.n, sizeof(T));  // R1-R4: dot 2w, nrm2 / sum 1w, k-way multi-dot (k+1)w
   if (aligned)
     reduce_kernel<T, K, OP, true><<<(unsigned)p.nchunks, kReduceThreads, 0, ctx->stream>>>(a, p.f);
   else
@@ -413,6 +414,7 @@ int launch_reduce_ew(cts_ctx* ctx, size_t n, void* y, const void* x, const void*
   Plan p;
   CTS_TRY(make_plan(ctx, n, 1, &p));
   const size_t off = p.off;
+  CTS_COUNT_BYTES(ctx, 2 + (EW == EW_AXPBY ? 1 : 0) + (z ? 1 : 0), n, sizeof(T));  // producer + reduction in one pass
   const bool aligned = cts_aligned16((const T*)y + off) && cts_aligned16((const T*)x + off) && (!z || cts_aligned16((const T*)z + off));
   if (aligned)
     reduce_ew_kernel<T, EW, OP, true><<<(unsigned)p.nchunks, kReduceThreads, 0, ctx->stream>>>((T*)y, (const T*)x, (const T*)z, a, b, n, off, p.n, p.f);

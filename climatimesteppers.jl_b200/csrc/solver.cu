@@ -86,6 +86,9 @@ struct cts_newton_cache {
   bool fuse_reductions = true;           // cleared together with the engine's fusion switch (reference pass structure)
   bool xstat_valid = false;              // sum(1+|x|) (or norm(x)) of the current solve_krylov! call
   double xstat = 0.0;
+  // one-iteration direct solve whose `x .-= Δx` (K5) the caller fuses with what follows (K6): solve_newton leaves Δx
+  // in `dx` and x untouched
+  bool defer_update = false;
 };
 
 namespace {
@@ -524,6 +527,7 @@ int solve_newton(cts_newton_cache* c, void* x, const ResidualFn& f_, const JacFn
     } else {
       CTS_TRY(solve_krylov(c, c->dx, x, f_, c->f, n - 1, prepare));
     }
+    if (c->defer_update && cfg.max_iters == 1 && !c->line_search && !c->has_checker) return CTS_OK;  // K5 fused by the caller
     {
       cts_prof_scope ps(ctx, CTS_PROF_NEWTON_EW);
       CTS_TRY(cts_sub_inplace(ctx, c->ft, c->n, x, c->dx));  // K5
@@ -960,7 +964,7 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
     Increment inc_exp = has_T_exp ? raw_increment(c, dt, &tab.a_exp[i * s], i, c->T_exp) : Increment{};
     Increment inc_imp = has_T_imp ? raw_increment(c, dt, &tab.a_imp[i * s], i, c->T_imp) : Increment{};
 
-    bool stage_done = false, overlap_dss = false;
+    bool stage_done = false, overlap_dss = false, temp_done = false, timp_done = false;
     if (fuse_op && !no_imp) {
       // K1 + Newton + K6 in one kernel; the pre-Newton dss! calls only rewrite ghost rows that the column
       // solve never reads, so one post-Newton dss! leaves every owned DOF bit-identical.
@@ -983,7 +987,9 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
       if (i != 0 && f.lim) HOOK(c->ctx, f.lim(f.ud, U, t_exp, u));
       CTS_TRY(assign_with_increments(c, U, nullptr, 1.0, U, inc_exp, inc_imp));
     } else {
-      CTS_TRY(assign_with_increments(c, U, nullptr, 1.0, u, inc_exp, inc_imp));
+      // `temp = U` (:209) rides along when no hook may touch U between the assembly and the copy
+      temp_done = c->fusion && !no_imp && !f.dss && !f.constrain_state && !f.cache_imp && !f.initialize_imp && c->nm != nullptr;
+      CTS_TRY(assign_with_increments(c, U, temp_done ? c->temp : nullptr, 1.0, u, inc_exp, inc_imp));
     }
 
     // solve_stage_implicit!  :174-242
@@ -996,7 +1002,7 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
       }
       if (!no_imp) {
         if (!c->ncfg.present || !c->nm) return cts_fail(c->ctx, CTS_EINVAL, "implicit stage without a NewtonsMethod");
-        {
+        if (!temp_done) {
           cts_prof_scope ps(c->ctx, CTS_PROF_NEWTON_EW);
           CTS_TRY(cts_axpy_n(c->ctx, c->ft, c->n, c->temp, nullptr, 1.0, U, 0, 0, nullptr, nullptr, 0));  // K2 :209
         }
@@ -1008,7 +1014,19 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
         } else if (i != 0) {
           CTS_TRY(call_state(c, f.cache_imp, U, t_imp));
         }
-        CTS_TRY(solve_implicit_equation(c, U, c->temp, t_imp, dtg));
+        // K5 + K6 in one pass: a one-iteration direct solve, no dss!/constrain_state!/cache! between `x .-= Δx` (:651) and
+        // `T_imp[i] = (U - temp)/dtγ` (:269), and temp == the pre-update U bit for bit
+        const bool fuse56 = c->fusion && has_imp_terms && c->ncfg.max_iters == 1 && !c->ncfg.use_krylov && !c->nm->has_checker &&
+                            !c->nm->line_search && !f.dss && !f.constrain_state && !f.cache && !f.initialize_imp && U != c->T_imp[i];
+        c->nm->defer_update = fuse56;
+        const int rsolve = solve_implicit_equation(c, U, c->temp, t_imp, dtg);
+        c->nm->defer_update = false;
+        CTS_TRY(rsolve);
+        if (fuse56) {
+          cts_prof_scope ps(c->ctx, CTS_PROF_NEWTON_EW);
+          CTS_TRY(cts_newton_update_timp(c->ctx, c->ft, c->n, U, c->T_imp[i], c->nm->dx, dtg, native_flag(c)));
+          timp_done = true;
+        }
         CTS_TRY(call_dss(c, U, t_imp));
         if (!(i == s - 1 && is_fsal(tab))) {
           if (needs_update(f.update_constrain_state, CTS_SIG_END_OF_STAGE)) CTS_TRY(call_state(c, f.constrain_state, U, t_imp));
@@ -1033,7 +1051,7 @@ int ark_step(cts_imex_cache* c, void* u, double t, double dt) {
         HOOK(c->ctx, f.T_exp_T_lim(f.ud, c->T_exp[i], c->T_lim[i], U, t_exp));
       }
     }
-    if (has_imp_terms && has_T_imp && !stage_done) {
+    if (has_imp_terms && has_T_imp && !stage_done && !timp_done) {
       if (dtg == 0) {
         cts_prof_scope ps(c->ctx, CTS_PROF_T_IMP);
         HOOK(c->ctx, f.T_imp(f.ud, c->T_imp[i], U, t_imp));

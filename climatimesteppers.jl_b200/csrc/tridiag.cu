@@ -212,6 +212,7 @@ int cts_tridiag_solve_batched(cts_ctx* ctx, cts_dtype ft, const cts_tridiag* W, 
   if (!W || !rhs || !x || W->nlev <= 0 || !W->dl || !W->d || !W->du)
     return cts_fail(ctx, CTS_EINVAL, "cts_tridiag_solve_batched: bad argument");
   if (W->ncols == 0) return CTS_OK;
+  CTS_COUNT_BYTES(ctx, 5, W->ncols * (size_t)W->nlev, cts_sizeof(ft));  // K4: dl, d, du, rhs in; x out
   return ft == CTS_F64 ? solve_t<double>(ctx, W, rhs, x) : solve_t<float>(ctx, W, rhs, x);
 }
 
@@ -220,6 +221,7 @@ int cts_tridiag_matvec(cts_ctx* ctx, cts_dtype ft, const cts_tridiag* W, const v
   if (!W || !x || !y || x == y) return cts_fail(ctx, CTS_EINVAL, "cts_tridiag_matvec: bad argument");
   size_t n = W->ncols * (size_t)W->nlev;
   if (n == 0) return CTS_OK;
+  CTS_COUNT_BYTES(ctx, 5, n, cts_sizeof(ft));
   size_t blocks = (n + 255) / 256;
   if (ft == CTS_F64)
     tridiag_matvec_kernel<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>((const double*)W->dl, (const double*)W->d,

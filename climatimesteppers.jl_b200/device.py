@@ -60,6 +60,12 @@ class Context:
         self.check(self.lib.cts_launch_count(self.handle, C.byref(out)))
         return int(out.value)
 
+    def bytes_count(self) -> int:
+        """Algorithmic HBM bytes of all kernels launched so far (cts_bytes_count)."""
+        out = C.c_uint64()
+        self.check(self.lib.cts_bytes_count(self.handle, C.byref(out)))
+        return int(out.value)
+
     def prof_enable(self, enabled: bool = True):
         self.check(self.lib.cts_prof_enable(self.handle, int(enabled)))
 

@@ -184,6 +184,28 @@ class ColumnOperator:
         args.update(kw)
         return ClimaODEFunction(**args)
 
+    def foreign_ode_function(self, *, explicit: bool = True, dss: Optional[bool] = None, **kw) -> ClimaODEFunction:
+        """The same model handed to the solver as OPAQUE user closures (Python callables around the library kernels), the
+        way a ClimaAtmos-style model supplies `T_imp!`/`Wfact`/`ldiv!`: the engine cannot recognise the operator, so every
+        step runs the generic pass-by-pass path through host callbacks (used to measure and test that path)."""
+        op = self
+
+        class _ForeignTridiag(ColumnTridiag):   # a user Jacobian type: `zero`, `ldiv!`, `mul!`
+            def zero(self_inner):
+                z = _ForeignTridiag(op, allocate=True)
+                return z
+
+        T_imp = ODEFunction(lambda du, u, p, t: op.T_imp(du, u, p, t), jac_prototype=_ForeignTridiag(self),
+                            Wfact=lambda W, u, p, dtg, t: op.Wfact(W, u, p, dtg, t))
+        use_dss = self.halo > 0 if dss is None else dss
+        args = dict(T_imp=T_imp)
+        if explicit:
+            args["T_exp"] = lambda du, u, p, t: op.T_exp(du, u, p, t)
+        if use_dss:
+            args["dss"] = lambda u, p, t: op.dss(u, p, t)
+        args.update(kw)
+        return ClimaODEFunction(**args)
+
     def __del__(self):
         try:
             if self.handle:

@@ -59,6 +59,10 @@ const char* cts_last_error(cts_ctx* ctx);
 void* cts_ctx_stream(cts_ctx* ctx);
 /* number of kernels this context has launched so far (evidence for bench.py's gpu_launches) */
 int cts_launch_count(cts_ctx* ctx, uint64_t* out);
+/* algorithmic HBM bytes of the kernels this context has launched so far: (arrays read + arrays written) x elements x
+ * sizeof(FT) per pass, the per-kernel figures of the design document -- the numerator of bench.py's achieved GB/s for
+ * workloads whose pass count is data dependent (Newton-Krylov) */
+int cts_bytes_count(cts_ctx* ctx, uint64_t* out);
 /* `zero(u0)` in init_cache (imex_ark.jl:44-48): zero-filled device allocation */
 int cts_alloc(cts_ctx* ctx, size_t bytes, void** dptr);
 int cts_free(cts_ctx* ctx, void* dptr);

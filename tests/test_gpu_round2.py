@@ -252,3 +252,35 @@ def test_wall_time_callback_single_rank(cts):
                      cts.IMEXAlgorithm(cts.ARS343(), cts.NewtonsMethod(max_iters=1)), dt=0.01, callback=cb)
     cts.solve_(integ)
     assert hits == [3, 5, 8, 10]   # clock 0.0 at init -> next = 1.0; queries at 0.4, 0.8, 1.2 (step 3) ...
+
+
+# ------------------------------------------------------------------ generic (foreign-hook) path -------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("halo", [0, 1])
+def test_foreign_hooks_generic_path_bit_exact(cts, dtype, halo):
+    # user closures the engine cannot recognise: pass-by-pass path through host callbacks.  Without a dss! hook (halo = 0)
+    # `temp = U` rides with the stage assembly and `x .-= Δx` + `T_imp = (U - temp)/dtγ` are one pass (5 passes per
+    # implicit stage instead of 7); results are the oracle's bits either way
+    import test_gpu_parity as P
+    model, op, T0 = P._column_pair(cts, nlev=16, nx=4, ny=6, halo=halo, dtype=dtype, nu=0.7 if halo else 0.0)
+    alg = cts.IMEXAlgorithm(cts.ARS343(), cts.NewtonsMethod(max_iters=1))
+    uo = T0.copy()
+    fo = model.ode_function()
+    if halo:
+        model.dss(uo, None, 0.0)
+    _, step = R.make_stepper(fo, R.imex_algorithm("ARS343", R.NewtonsMethod(max_iters=1)), uo)
+    res = []
+    for fusion in (True, False):
+        uc = cts.B200Vector.from_host(T0)
+        if halo:
+            op.dss(uc, None, 0.0)
+        integ = cts.init(cts.ODEProblem(op.foreign_ode_function(), uc, (0.0, 1e9), None), alg, dt=0.01, save=False)
+        integ.cache.set_fusion(fusion)
+        for k in range(2):
+            cts.step_(integ)
+        assert integ.cache.stats()["fused_stage_launches"] == 0     # never the recognised-operator kernel
+        res.append(uc.to_host())
+    for k in range(2):
+        step(uo, None, 0.01 * k, 0.01)
+    np.testing.assert_array_equal(res[0], uo)
+    np.testing.assert_array_equal(res[1], uo)
