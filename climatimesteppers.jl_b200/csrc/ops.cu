@@ -1000,22 +1000,62 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
 // 32 columns of 64 Float32 levels, ...), so one 128-thread group covers it with 4 vectors per thread and a column is a
 // power-of-two lane group of one warp.
 // ---------------------------------------------------------------------------------------------
-constexpr int kPipeAsm = 128;
-constexpr int kPipeSolverWarps = 4;
-constexpr int kPipeStore = 128;
-constexpr int kPipeThreads = 32 + kPipeAsm + 32 * kPipeSolverWarps + kPipeStore;  // 416
+constexpr int kPipeAsm = 128;            // assembler threads (phase A)
+constexpr int kPipeMaxSolverWarps = 6;   // solver warps (phase B): teams of `jobs` warps, one team per tile in flight
+constexpr int kPipeStore = 128;          // epilogue threads (phase C)
+constexpr int kPipeThreads = 64 + kPipeAsm + 32 * kPipeMaxSolverWarps + kPipeStore;  // 512
 constexpr int kPipeTileVecs = 512;
-constexpr int kPipeOpStages = 2;
-constexpr int kPipeMaxSlots = 8;
-constexpr int kPipeBarBytes = 512;
-constexpr int kPipeOpBytes = kPipeTileVecs * 16;  // one operand tile in the staging ring
+constexpr int kPipeMaxDepth = 8;         // upper bound of every ring depth
+constexpr int kPipeBarBytes = 512;       // 7 barrier arrays x 8 x 8 B = 448 B
+constexpr int kPipeOpBytes = kPipeTileVecs * 16;  // one operand tile (8 KiB) of the operand ring
 
+struct PipeCfg {
+  int n_op;     // depth of the operand ring   (base + NT tendencies per stage, flat 8 KiB tiles, bulk TMA)
+  int n_w;      // depth of the W ring         (stored W: dl|d|du padded tiles by bulk TMA; matrix-free: one factor tile per team)
+  int n_x;      // depth of the x ring         (U0 flat + residual/x padded)
+  int n_teams;  // solver teams (a team = `jobs` warps = one tile); stored W: == n_w
+};
+
+// mbarrier wait of the pipelined kernel with a watchdog: a protocol error must surface as a launch failure (trap), never
+// as a hung GPU.  ~2 s at 2 GHz; the check only runs while the barrier is NOT ready.
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, int tag) {
+  uint32_t ok;
+  long long t0 = 0;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!ok) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) {
+        printf("cts: fused-stage pipeline watchdog: block %d thread %d barrier tag %d parity %u\n", (int)blockIdx.x, (int)threadIdx.x, tag, parity);
+        __trap();
+      }
+    }
+  } while (!ok);
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Rings and their barriers (tile i uses buffer i % depth in phase i / depth of that buffer's barriers):
+//   operand ring  op_full  (TMA complete_tx)        -> assemblers;   op_empty (128 assembler arrivals)  -> operand producer
+//   W ring        w_full   (TMA complete_tx)        -> solver team;  w_empty  (32*jobs solver arrivals) -> W producer
+//   x ring        x_full   (128 assembler arrivals) -> solver team;  x_solved (32*jobs)                 -> epilogue;
+//                 x_empty  (128 epilogue arrivals)  -> assemblers
+// A parity wait is only meaningful for the current or the immediately preceding phase of a barrier, so every waiter must
+// meet the phases of a buffer in sequence: producers, assemblers and the epilogue walk ALL tiles in order; solver team k
+// takes tiles k, k + n_teams, ... with n_teams <= n_x (x_full completes in tile order) and n_teams == n_w for stored W
+// (a team always meets the same W buffer, whatever order the bulk copies complete in).
 template <typename T, typename C, int NT, bool MATRIX_FREE, int N1SPEC>
-__global__ void __launch_bounds__(kPipeThreads, 1) column_fused_stage_pipe_kernel(const FusedArgs<NT> a, int nslots) {
+__global__ void __launch_bounds__(kPipeThreads, 1) column_fused_stage_pipe_kernel(const FusedArgs<NT> a, const PipeCfg cfg) {
   using V = typename Vec<T>::type;
   constexpr int VN = Vec<T>::N;
   constexpr int NTS = NT > 0 ? NT : 1;
@@ -1027,33 +1067,40 @@ __global__ void __launch_bounds__(kPipeThreads, 1) column_fused_stage_pipe_kerne
   const int cpc = col_bytes / 16;               // vectors per column: a power of two <= 32
   const int cshift = 31 - __clz(cpc);
   const int kCols = kPipeTileVecs / cpc;        // columns per tile
-  const int jobs = kCols / 16;                  // solver jobs (16 columns each) per tile
+  const int jobs = kCols / 16;                  // solver warps per tile (16 columns each)
   const int tile_bytes = kCols * pitch;         // a padded tile (conflict-free column pitch)
-  const int slot_bytes = tile_bytes + kPipeOpBytes + (MATRIX_FREE ? 1 : 3) * tile_bytes;
+  const int op_bytes = (1 + NT) * kPipeOpBytes;
+  const int w_bytes = (MATRIX_FREE ? 1 : 3) * tile_bytes;
+  const int x_bytes = kPipeOpBytes + tile_bytes;  // U0 (flat) | residual -> x (padded)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* op_full = bars;                     // [2]  staging buffer b holds tile i's operands (TMA complete_tx)
-  uint64_t* op_empty = bars + 2;                // [2]  the assemblers are done with staging buffer b
-  uint64_t* w_full = bars + 4;                  // [8]  slot s holds tile i's dl/d/du (TMA complete_tx)
-  uint64_t* s_full = bars + 4 + kPipeMaxSlots;  // [8]  slot s holds U0 and the residual
-  uint64_t* s_solved = bars + 4 + 2 * kPipeMaxSlots;
-  uint64_t* s_empty = bars + 4 + 3 * kPipeMaxSlots;
-  char* stage = smem + kPipeBarBytes;           // [2][1 + NT][8 KiB]
-  char* slots = stage + kPipeOpStages * (1 + NT) * kPipeOpBytes;
+  uint64_t* op_full = bars;
+  uint64_t* op_empty = bars + kPipeMaxDepth;
+  uint64_t* w_full = bars + 2 * kPipeMaxDepth;
+  uint64_t* w_empty = bars + 3 * kPipeMaxDepth;
+  uint64_t* x_full = bars + 4 * kPipeMaxDepth;
+  uint64_t* x_solved = bars + 5 * kPipeMaxDepth;
+  uint64_t* x_empty = bars + 6 * kPipeMaxDepth;
+  char* op_ring = smem + kPipeBarBytes;
+  char* w_ring = op_ring + (size_t)cfg.n_op * op_bytes;
+  char* x_ring = w_ring + (size_t)cfg.n_w * w_bytes;
 
   const size_t ntiles = (a.ncols + kCols - 1) / kCols;
   const int count = ntiles > blockIdx.x ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int b = 0; b < kPipeOpStages; ++b) {
+    for (int b = 0; b < cfg.n_op; ++b) {
       mbar_init(op_full + b, 1);
       mbar_init(op_empty + b, kPipeAsm);
     }
-    for (int s = 0; s < nslots; ++s) {
-      mbar_init(w_full + s, 1);
-      mbar_init(s_full + s, kPipeAsm);
-      mbar_init(s_solved + s, 32 * jobs);
-      mbar_init(s_empty + s, kPipeStore);
+    for (int b = 0; b < cfg.n_w; ++b) {
+      mbar_init(w_full + b, 1);
+      mbar_init(w_empty + b, 32 * jobs);
+    }
+    for (int s = 0; s < cfg.n_x; ++s) {
+      mbar_init(x_full + s, kPipeAsm);
+      mbar_init(x_solved + s, 32 * jobs);
+      mbar_init(x_empty + s, kPipeStore);
     }
     fence_mbar_init();
   }
@@ -1064,67 +1111,111 @@ __global__ void __launch_bounds__(kPipeThreads, 1) column_fused_stage_pipe_kerne
     col0 = tile * kCols;
     nvalid = (int)((a.ncols - col0) < (size_t)kCols ? (a.ncols - col0) : (size_t)kCols);
   };
+  // optional wait-time profile (CTS_FUSED_TIMELINE): lane 0 of each role's first warp sums the cycles it spends in each wait
+  long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_begin = a.dbg ? clock64() : 0;
+  auto wait = [&](uint64_t* bar, uint32_t parity, int tag) {
+    if (a.dbg) {
+      const long long t0 = clock64();
+      mbar_wait_wd(bar, parity, tag);
+      acc[tag] += clock64() - t0;
+    } else {
+      mbar_wait_wd(bar, parity, tag);
+    }
+  };
+  int role = -1;  // profile row of this thread (only one thread per role reports)
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ producer ---------------------------------
-    for (int i = 0; i < count; ++i) {
-      size_t col0;
-      int nvalid;
-      tile_of(i, col0, nvalid);
-      const size_t goff = col0 * (size_t)nlev;
-      const uint32_t flat = (uint32_t)(nvalid * col_bytes);
-      const int b = i % kPipeOpStages, s = i % nslots;
-      char* st = stage + (size_t)b * (1 + NT) * kPipeOpBytes;
-      if (lane == 0) {
-        mbar_wait(op_empty + b, ((i / kPipeOpStages) & 1) ^ 1);
+    // ------------------------------------------------------------------ operand producer -------------------------
+    if (lane == 0) {
+      role = 0;
+      for (int i = 0; i < count; ++i) {
+        size_t col0;
+        int nvalid;
+        tile_of(i, col0, nvalid);
+        const size_t goff = col0 * (size_t)nlev;
+        const uint32_t flat = (uint32_t)(nvalid * col_bytes);
+        const int b = i % cfg.n_op;
+        char* st = op_ring + (size_t)b * op_bytes;
+        wait(op_empty + b, ((i / cfg.n_op) & 1) ^ 1, 1);
         mbar_arrive_expect_tx(op_full + b, (uint32_t)(1 + NT) * flat);
         bulk_g2s(st, (const T*)a.ax.base + goff, flat, op_full + b);
 #pragma unroll
         for (int k = 0; k < NT; ++k) bulk_g2s(st + (k + 1) * kPipeOpBytes, (const T*)a.ax.terms[k] + goff, flat, op_full + b);
       }
-      if (!MATRIX_FREE) {
-        char* sl = slots + (size_t)s * slot_bytes + tile_bytes + kPipeOpBytes;  // dl | d | du tiles of the slot
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ W producer (stored W) --------------------
+    if (!MATRIX_FREE) {
+      if (lane == 0) role = 1;
+      for (int i = 0; i < count; ++i) {
+        size_t col0;
+        int nvalid;
+        tile_of(i, col0, nvalid);
+        const size_t goff = col0 * (size_t)nlev;
+        const uint32_t flat = (uint32_t)(nvalid * col_bytes);
+        const int b = i % cfg.n_w;
+        char* sl = w_ring + (size_t)b * w_bytes;  // dl | d | du padded tiles
         if (lane == 0) {
-          mbar_wait(s_empty + s, ((i / nslots) & 1) ^ 1);
-          mbar_arrive_expect_tx(w_full + s, 3u * flat);
+          wait(w_empty + b, ((i / cfg.n_w) & 1) ^ 1, 3);
+          mbar_arrive_expect_tx(w_full + b, 3u * flat);
         }
         __syncwarp();
         for (int c = lane; c < nvalid; c += 32) {
           const size_t g = goff + (size_t)c * nlev;
-          bulk_g2s(sl + c * pitch, (const T*)a.dl + g, col_bytes, w_full + s);
-          bulk_g2s(sl + tile_bytes + c * pitch, (const T*)a.d + g, col_bytes, w_full + s);
-          bulk_g2s(sl + 2 * tile_bytes + c * pitch, (const T*)a.du + g, col_bytes, w_full + s);
+          bulk_g2s(sl + c * pitch, (const T*)a.dl + g, col_bytes, w_full + b);
+          bulk_g2s(sl + tile_bytes + c * pitch, (const T*)a.d + g, col_bytes, w_full + b);
+          bulk_g2s(sl + 2 * tile_bytes + c * pitch, (const T*)a.du + g, col_bytes, w_full + b);
         }
       }
     }
-  } else if (warp < 1 + kPipeAsm / 32) {
+  } else if (warp < 2 + kPipeAsm / 32) {
     // ------------------------------------------------------------------ assemblers (phase A) ----------------------
-    const int at = threadIdx.x - 32;
+    const int at = threadIdx.x - 64;
+    if (at == 0) role = 2;
+    // K/dz^2 of this thread's columns, fetched one tile ahead: under a saturated memory system a dependent global load
+    // inside the tile loop costs microseconds (it queues behind the bulk copies)
+    T acol_next[kRounds];
+    auto fetch_acol = [&](int i) {
+      size_t c0;
+      int nv;
+      tile_of(i, c0, nv);
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        const int col = (at + r * kPipeAsm) >> cshift;
+        acol_next[r] = (i < count && col < nv) ? ((const T*)a.Kcol)[c0 + col] : T(0);
+      }
+    };
+    fetch_acol(0);
     for (int i = 0; i < count; ++i) {
       size_t col0;
       int nvalid;
       tile_of(i, col0, nvalid);
       const int total = nvalid * cpc;
+      T acol_cur[kRounds];
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) acol_cur[r] = acol_next[r];
+      fetch_acol(i + 1);
       const size_t gvec0 = col0 * (size_t)nlev * sizeof(T) / 16;
-      const int b = i % kPipeOpStages, s = i % nslots;
-      const char* st = stage + (size_t)b * (1 + NT) * kPipeOpBytes;
-      char* sx = slots + (size_t)s * slot_bytes;
-      V* sU0 = reinterpret_cast<V*>(sx + tile_bytes);
-      mbar_wait(op_full + b, (i / kPipeOpStages) & 1);
-      mbar_wait(s_empty + s, ((i / nslots) & 1) ^ 1);
+      const int b = i % cfg.n_op, s = i % cfg.n_x;
+      const char* st = op_ring + (size_t)b * op_bytes;
+      char* xs = x_ring + (size_t)s * x_bytes;
+      V* sU0 = reinterpret_cast<V*>(xs);
+      char* sx = xs + kPipeOpBytes;
+      wait(x_empty + s, ((i / cfg.n_x) & 1) ^ 1, 5);
+      wait(op_full + b, (i / cfg.n_op) & 1, 2);
       // (the operands sit in shared memory: every round loads what it needs, no register staging across rounds)
-#pragma unroll 2
+#pragma unroll
       for (int r = 0; r < kRounds; ++r) {
         const int q = at + r * kPipeAsm;
         const bool ok = q < total;
         const int col = q >> cshift, kk = q & (cpc - 1);
         V vb, vt[NTS];
-        T acol = T(0);
+        const T acol = acol_cur[r];
         if (ok) {
           vb = reinterpret_cast<const V*>(st)[q];
 #pragma unroll
           for (int t = 0; t < NT; ++t) vt[t] = reinterpret_cast<const V*>(st + (t + 1) * kPipeOpBytes)[q];
-          acol = ((const T*)a.Kcol)[col0 + col];
         }
         T eb[VN], uu[VN], rr[VN], et[NTS][VN];
         vec_unpack<T>(vb, eb);
@@ -1159,58 +1250,86 @@ __global__ void __launch_bounds__(kPipeThreads, 1) column_fused_stage_pipe_kerne
           if (a.temp) reinterpret_cast<V*>(a.temp)[gvec0 + q] = vu;
         }
       }
-      mbar_arrive(s_full + s);
+      mbar_arrive(x_full + s);
       mbar_arrive(op_empty + b);
     }
-  } else if (warp < 1 + kPipeAsm / 32 + kPipeSolverWarps) {
+  } else if (warp < 2 + kPipeAsm / 32 + kPipeMaxSolverWarps) {
     // ------------------------------------------------------------------ solvers (phase B) -------------------------
-    const int w = warp - 1 - kPipeAsm / 32;
-    for (int i = 0; i < count; ++i) {
-      size_t col0;
-      int nvalid;
-      tile_of(i, col0, nvalid);
-      const int s = i % nslots;
-      char* sx = slots + (size_t)s * slot_bytes;
-      char* sw = sx + tile_bytes + kPipeOpBytes;
-      bool waited = false;
-      for (int j = 0; j < jobs; ++j) {
-        if (((i * jobs + j) % kPipeSolverWarps) != w) continue;
-        if (!waited) {
-          mbar_wait(s_full + s, (i / nslots) & 1);
-          if (!MATRIX_FREE) mbar_wait(w_full + s, (i / nslots) & 1);
-          waited = true;
-        }
+    const int w = warp - 2 - kPipeAsm / 32;
+    const int team = w / jobs, j = w - team * jobs;
+    if (team < cfg.n_teams) {
+      if (w == 0 && lane == 0) role = 3;
+      T ac_next = T(0);
+      auto fetch_ac = [&](int i) {
+        size_t c0;
+        int nv;
+        tile_of(i, c0, nv);
+        const int col = j * 16 + lane_column(lane);
+        ac_next = (MATRIX_FREE && i < count && col < nv) ? ((const T*)a.Kcol)[c0 + col] : T(0);
+      };
+      fetch_ac(team);
+      for (int i = team; i < count; i += cfg.n_teams) {
+        size_t col0;
+        int nvalid;
+        tile_of(i, col0, nvalid);
+        const T ac = ac_next;
+        fetch_ac(i + cfg.n_teams);
+        const int s = i % cfg.n_x;
+        const int b = MATRIX_FREE ? team : i % cfg.n_w;
+        char* sx = x_ring + (size_t)s * x_bytes + kPipeOpBytes;
+        char* sw = w_ring + (size_t)b * w_bytes;
+        wait(x_full + s, (i / cfg.n_x) & 1, 4);
+        if (!MATRIX_FREE) wait(w_full + b, (i / cfg.n_w) & 1, 6);
         const int col = j * 16 + lane_column(lane);
         const bool is_up = lane_is_up(lane);
         const bool valid = col < nvalid;
         const int col_off = col * pitch;
         if (MATRIX_FREE) {
-          const T ac = valid ? ((const T*)a.Kcol)[col0 + col] : T(0);
           const double o = __dmul_rn(a.dtg, (double)ac);
           ConstRows<T> rows{(T)o, (T)__dsub_rn(__dmul_rn(-2.0, o), 1.0), sw};
           babe_solve_lanepair<T, ConstRows<T>, RhsFromTile<T>, true>(rows, RhsFromTile<T>{}, sx, col_off, nlev, is_up, valid);
         } else {
           StoredRows<T> rows{sw, sw + tile_bytes, sw + 2 * tile_bytes};
           babe_solve_lanepair<T, StoredRows<T>, RhsFromTile<T>, true>(rows, RhsFromTile<T>{}, sx, col_off, nlev, is_up, valid);
+          fence_proxy_async_smem();  // the factors overwrote dl/du in place; the next writer of these bytes is a bulk copy
+          mbar_arrive(w_empty + b);
         }
-        fence_proxy_async_smem();  // the factors overwrote dl/du in place; the next user of these bytes is a bulk copy
-        mbar_arrive(s_solved + s);
+        mbar_arrive(x_solved + s);
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (phase C) ------------------------
-    const int et_ = threadIdx.x - 32 - kPipeAsm - 32 * kPipeSolverWarps;
+    const int et_ = threadIdx.x - 64 - kPipeAsm - 32 * kPipeMaxSolverWarps;
+    if (et_ == 0) role = 4;
     const DivConst dc = div_const_prepare(a.dtg);
+    const bool emit = MATRIX_FREE && a.emit_w;
+    T kc_next[kRounds];
+    auto fetch_kc = [&](int i) {
+      size_t c0;
+      int nv;
+      tile_of(i, c0, nv);
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        const int col = (et_ + r * kPipeStore) >> cshift;
+        kc_next[r] = (emit && i < count && col < nv) ? ((const T*)a.Kcol)[c0 + col] : T(0);
+      }
+    };
+    fetch_kc(0);
     for (int i = 0; i < count; ++i) {
       size_t col0;
       int nvalid;
       tile_of(i, col0, nvalid);
       const int total = nvalid * cpc;
       const size_t gvec0 = col0 * (size_t)nlev * sizeof(T) / 16;
-      const int s = i % nslots;
-      const char* sx = slots + (size_t)s * slot_bytes;
-      const V* sU0 = reinterpret_cast<const V*>(sx + tile_bytes);
-      mbar_wait(s_solved + s, (i / nslots) & 1);
+      const int s = i % cfg.n_x;
+      const char* xs = x_ring + (size_t)s * x_bytes;
+      T kc_cur[kRounds];
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) kc_cur[r] = kc_next[r];
+      fetch_kc(i + 1);
+      const V* sU0 = reinterpret_cast<const V*>(xs);
+      const char* sx = xs + kPipeOpBytes;
+      wait(x_solved + s, (i / cfg.n_x) & 1, 7);
 #pragma unroll
       for (int r = 0; r < kRounds; ++r) {
         const int q = et_ + r * kPipeStore;
@@ -1226,8 +1345,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) column_fused_stage_pipe_kerne
         }
         reinterpret_cast<V*>(a.U)[gvec0 + q] = vec_pack<T>(eU);
         if (a.Timp) reinterpret_cast<V*>(a.Timp)[gvec0 + q] = vec_pack<T>(eT);
-        if (MATRIX_FREE && a.emit_w) {  // same expressions as column_wfact_kernel
-          const double o = __dmul_rn(a.dtg, (double)((const T*)a.Kcol)[col0 + col]);
+        if (emit) {  // same expressions as column_wfact_kernel
+          const double o = __dmul_rn(a.dtg, (double)kc_cur[r]);
           T eo[VN], ed[VN];
 #pragma unroll
           for (int e = 0; e < VN; ++e) {
@@ -1240,15 +1359,48 @@ __global__ void __launch_bounds__(kPipeThreads, 1) column_fused_stage_pipe_kerne
           reinterpret_cast<V*>(const_cast<void*>(a.du))[gvec0 + q] = vo;
         }
       }
-      mbar_arrive(s_empty + s);
+      mbar_arrive(x_empty + s);
     }
+  }
+  if (a.dbg && role >= 0) {
+    acc[0] = clock64() - t_begin;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a.dbg[((size_t)blockIdx.x * 5 + role) * 8 + k] = acc[k];
   }
 }
 
-// smem of the pipelined kernel for `nslots` slots; 0 slots = does not fit
-static size_t pipe_smem_bytes(int nt, int tile_bytes, bool mf, int nslots) {
-  return (size_t)kPipeBarBytes + (size_t)kPipeOpStages * (1 + nt) * kPipeOpBytes +
-         (size_t)nslots * ((size_t)tile_bytes + kPipeOpBytes + (size_t)(mf ? 1 : 3) * tile_bytes);
+// ring depths of the pipelined kernel for this launch (n_op == 0: does not fit).  CTS_PIPE_OP / CTS_PIPE_X / CTS_PIPE_TEAMS
+// override the defaults (developer aid for tuning).
+static PipeCfg pipe_config(int nt, int tile_bytes, bool mf, int jobs) {
+  const long budget = 227 * 1024 - kPipeBarBytes;
+  const long op_b = (long)(1 + nt) * kPipeOpBytes, w_b = (long)(mf ? 1 : 3) * tile_bytes, x_b = kPipeOpBytes + tile_bytes;
+  static const int env_op = getenv("CTS_PIPE_OP") ? atoi(getenv("CTS_PIPE_OP")) : 0;
+  static const int env_x = getenv("CTS_PIPE_X") ? atoi(getenv("CTS_PIPE_X")) : 0;
+  static const int env_teams = getenv("CTS_PIPE_TEAMS") ? atoi(getenv("CTS_PIPE_TEAMS")) : 0;
+  PipeCfg c{0, 0, 0, 0};
+  const int max_teams = kPipeMaxSolverWarps / jobs;
+  int teams = std::min(max_teams, mf ? 4 : 3);
+  if (env_teams > 0) teams = std::min(env_teams, max_teams);
+  if (teams < 1) return c;
+  const int n_w = teams;
+  int n_x = env_x > 0 ? std::max(env_x, teams) : teams;
+  int n_op = env_op > 0 ? env_op : 2;
+  n_x = std::min(n_x, kPipeMaxDepth);
+  n_op = std::min(n_op, kPipeMaxDepth);
+  if (n_op * op_b + n_w * w_b + n_x * x_b > budget) return c;
+  if (env_op <= 0)  // operands first: they are the bulk of the bytes in flight
+    while (n_op < 4 && (n_op + 1) * op_b + n_w * w_b + n_x * x_b <= budget) ++n_op;
+  if (env_x <= 0)
+    while (n_x < kPipeMaxDepth && n_op * op_b + n_w * w_b + (n_x + 1) * x_b <= budget) ++n_x;
+  c.n_op = n_op;
+  c.n_w = n_w;
+  c.n_x = n_x;
+  c.n_teams = teams;
+  return c;
+}
+static size_t pipe_smem_bytes(int nt, int tile_bytes, bool mf, const PipeCfg& c) {
+  return (size_t)kPipeBarBytes + (size_t)c.n_op * (1 + nt) * kPipeOpBytes + (size_t)c.n_w * (mf ? 1 : 3) * tile_bytes +
+         (size_t)c.n_x * (kPipeOpBytes + tile_bytes);
 }
 
 template <typename T, typename C, int NT>
@@ -1293,21 +1445,25 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
   const int cpc = op->d.nlev * (int)sizeof(T) / 16;
   constexpr int kCols = TileShape<T>::kCols;
   // pipelined persistent kernel: a tile is 512 vectors, a column 8..32 of them (a power of two)
-  static const bool no_pipe = getenv("CTS_FUSED_NO_PIPE") != nullptr;  // developer aid: the one-tile-per-CTA kernels
+  // The pipelined kernel is opt-in (CTS_FUSED_PIPE=1): bit-identical, but measured slower on B200
+  static const bool no_pipe = getenv("CTS_FUSED_PIPE") == nullptr || getenv("CTS_FUSED_PIPE")[0] == '0';
   if constexpr (NT <= 5) {
-  if (!timeline && !no_reg && !no_pipe && (cpc == 8 || cpc == 16 || cpc == 32)) {
+  if (!no_reg && !no_pipe && (cpc == 16 || cpc == 32)) {
     const int pcols = kPipeTileVecs / cpc;
     const int ptile = pcols * a.pitch;
-    int nslots = kPipeMaxSlots;
-    while (nslots > 0 && pipe_smem_bytes(NT, ptile, mf, nslots) > (size_t)227 * 1024) --nslots;
+    const PipeCfg cfg = pipe_config(NT, ptile, mf, pcols / 16);
     const size_t ptiles = (op->ncols + pcols - 1) / pcols;
-    if (nslots >= 3 && ptiles >= 1) {
-      const size_t psmem = pipe_smem_bytes(NT, ptile, mf, nslots);
+    if (cfg.n_op >= 2 && ptiles >= 1) {
+      const size_t psmem = pipe_smem_bytes(NT, ptile, mf, cfg);
       const unsigned grid = (unsigned)std::min<size_t>(ptiles, (size_t)ctx->num_sms);
       a.dbg = nullptr;
+      if (timeline) {
+        CTS_CUDA(ctx, cudaMalloc(&a.dbg, (size_t)grid * 40 * sizeof(long long)));
+        CTS_CUDA(ctx, cudaMemsetAsync(a.dbg, 0, (size_t)grid * 40 * sizeof(long long), ctx->stream));
+      }
       auto launchp = [&](auto k) -> int {
         CTS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-        k<<<grid, kPipeThreads, psmem, ctx->stream>>>(a, nslots);
+        k<<<grid, kPipeThreads, psmem, ctx->stream>>>(a, cfg);
         return CTS_OK;
       };
       int spec = 0;
@@ -1328,6 +1484,26 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
         else CTS_TRY(launchp(column_fused_stage_pipe_kernel<T, C, NT, false, 0>));
       }
       CTS_LAUNCH_CHECK(ctx);
+      if (timeline) {
+        std::vector<long long> h((size_t)grid * 40);
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(h.data(), a.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaFree(a.dbg);
+        static const char* roles[5] = {"op-producer", "W-producer", "assemblers", "solver0", "epilogue"};
+        static const char* tags[8] = {"total", "op_empty", "op_full", "w_empty", "x_full", "x_empty", "w_full", "x_solved"};
+        fprintf(stderr, "[cts pipe timeline] NT=%d mf=%d tiles=%zu grid=%u n_op=%d n_w=%d n_x=%d teams=%d smem=%zu\n", NT, (int)mf, ptiles, grid,
+                cfg.n_op, cfg.n_w, cfg.n_x, cfg.n_teams, psmem);
+        for (int r = 0; r < 5; ++r) {
+          double sum[8] = {0};
+          for (unsigned bk = 0; bk < grid; ++bk)
+            for (int k = 0; k < 8; ++k) sum[k] += (double)h[((size_t)bk * 5 + r) * 8 + k];
+          if (sum[0] == 0) continue;
+          fprintf(stderr, "  %-12s total %.0f cycles/CTA; wait share:", roles[r], sum[0] / grid);
+          for (int k = 1; k < 8; ++k)
+            if (sum[k] > 0) fprintf(stderr, " %s %.1f%%", tags[k], 100.0 * sum[k] / sum[0]);
+          fprintf(stderr, "\n");
+        }
+      }
       return CTS_OK;
     }
   }

@@ -1,5 +1,7 @@
 """GPU parity for the round-2 machinery: chunked shard-invariant reductions, the CUDA-graph step, the halo/compute
 overlap (fork/join with the communication stream) on one rank, and unaligned states (fallback off the fused stage)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -284,3 +286,83 @@ def test_foreign_hooks_generic_path_bit_exact(cts, dtype, halo):
         step(uo, None, 0.01 * k, 0.01)
     np.testing.assert_array_equal(res[0], uo)
     np.testing.assert_array_equal(res[1], uo)
+
+
+# ------------------------------------------------------------------ pipelined fused-stage kernel (opt-in) ----------
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_pipelined_fused_stage_kernel_is_bit_identical(dtype):
+    """`CTS_FUSED_PIPE=1` selects the persistent, warp-specialised variant of the fused column stage (operand / W / x
+    rings over mbarriers, csrc/ops.cu).  Same device functions, same roundings: two ARS343 steps on several waves of tiles
+    (stored W with the Wfact-emitting first stage, and matrix-free) must equal the default kernel's result bit for bit."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, hashlib, numpy as np
+sys.path.insert(0, %r)
+import cts_b200 as cts
+dtype = np.dtype(%r)
+out = []
+for mf in (False, True):
+    nlev, nx, ny = 64, 256, 150          # 152 x 256 = 38912 columns: > 148 tiles per CTA wave, partial last wave
+    K = cts.B200Vector.zeros((ny + 2) * nx, dtype).fill_hash(2, 0, 0.25, 2.0)
+    z = (np.arange(nlev) + 1) / (nlev + 1)
+    S = cts.B200Vector.from_host((5.0 * np.exp(-((z - 0.3) ** 2) / 0.01)).astype(dtype))
+    op = cts.ColumnOperator(nlev, nx, ny, K, S_lev=S, nu=1.0, halo=1).set_matrix_free(mf)
+    u = cts.B200Vector.zeros(op.ndof, dtype).fill_hash(3)
+    op.dss(u, None, 0.0)
+    integ = cts.init(cts.ODEProblem(op.ode_function(), u, (0.0, 1e9), None),
+                     cts.IMEXAlgorithm(cts.ARS343(), cts.NewtonsMethod(max_iters=1, update_j=cts.UpdateEvery(cts.NewTimeStep))),
+                     dt=0.02, save=False)
+    for _ in range(2):
+        cts.step_(integ)
+    h = u.to_host()
+    assert np.isfinite(h).all()
+    assert integ.cache.stats()["fused_stage_launches"] == 6
+    out.append(hashlib.sha256(h.tobytes()).hexdigest())
+print("HASH", *out)
+""" % (root, dtype)
+    hashes = {}
+    for pipe in ("0", "1"):
+        env = dict(os.environ, CTS_FUSED_PIPE=pipe)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        hashes[pipe] = [ln for ln in r.stdout.splitlines() if ln.startswith("HASH")][-1]
+    assert hashes["0"] == hashes["1"]
+
+
+# ------------------------------------------------------------------ config C4 at size ------------------------------
+@pytest.mark.parametrize("dtype,tol,adj", [(np.float64, 1e-12, 1.0), (np.float32, 1e-5, 64.0)])
+def test_c4_ssp333_jfnk_at_2pow20_dof(cts, dtype, tol, adj):
+    """BASELINE configs[3] in the exact set-up bench.py times (`run_c4`): SSP333 (SSPRK path) + NewtonsMethod(max_iters = 2,
+    KrylovMethod(ForwardDiffJVP, ConstantForcing(1e-2))), nonlinear column diffusion, frozen-coefficient W as left
+    preconditioner, smooth state with a 2 % hashed perturbation -- on 2^14 columns x 64 levels = 2^20 DOF instead of 2^27,
+    against the numpy oracle (imex_ssprk.jl:95-220, newtons_method.jl:465-509,609-665; GMRES per Krylov.jl v0.10.6).
+    Float64 is bit-exact (one reduction tree on both sides), Float32 within the north-star tolerance."""
+    nlev, nx, ny = 64, 128, 128
+    K = M.fill_hash(nx * ny, 2, 0, 0.25, 2.0, dtype=dtype)
+    T0 = M.fill_hash(nx * ny * nlev, 3, 0, 0.02, 25.0, dtype=dtype)
+    model = M.ColumnModel(nlev, nx, ny, K, S_lev=None, nu=0.0, halo=0, nonlinear=True)
+    km_o = R.KrylovMethod(jacobian_free_jvp=R.ForwardDiffJVP(step_adjustment=adj), forcing_term=R.ConstantForcing(1e-2))
+    alg_o = R.imex_algorithm("SSP333", R.NewtonsMethod(max_iters=2, krylov_method=km_o), None)
+    uo = T0.copy()
+    cache_o, step_o = R.make_stepper(model.ode_function(explicit=False), alg_o, uo)
+
+    op = cts.ColumnOperator(nlev, nx, ny, cts.B200Vector.from_host(K), nu=0.0, halo=0, nonlinear=True)
+    km = cts.KrylovMethod(jacobian_free_jvp=cts.ForwardDiffJVP(step_adjustment=adj), forcing_term=cts.ConstantForcing(1e-2))
+    alg = cts.IMEXAlgorithm(cts.SSP333(), cts.NewtonsMethod(max_iters=2, krylov_method=km))
+    u = cts.B200Vector.from_host(T0)
+    integ = cts.init(cts.ODEProblem(op.ode_function(explicit=False), u, (0.0, 1e9), None), alg, dt=2e-3, save=False)
+    t = 0.0
+    for _ in range(2):
+        step_o(uo, None, t, 2e-3)
+        cts.step_(integ)
+        t += 2e-3
+    got = u.to_host()
+    assert np.isfinite(got).all()
+    st = integ.cache.stats()
+    assert st["krylov_iters"] == sum(s["niter"] for s in cache_o["nm_cache"]["stats"]) > 0
+    err = float(np.max(np.abs(got.astype(np.float64) - uo.astype(np.float64))) / np.max(np.abs(uo)))
+    assert err <= 2 * tol
+    if dtype == np.float64:
+        np.testing.assert_array_equal(got, uo)
