@@ -638,7 +638,7 @@ def run_extras(cts, ctx, stream, op, u):
     for fused in (True, False):
         integ.cache.set_fusion(fused)
         ms = timed(stream, lambda: cts.step_(integ), 5)
-        model = (4 * 4 + 6) * 8 if fused else 30 * 8   # bytes/DOF/step: 4 fused stages (4w) + 1 two-pass stage (6w) | 5 x 6w
+        model = 5 * 4 * 8 if fused else 30 * 8   # bytes/DOF/step: 5 fused stages of 4w (the last one in place) | 5 x 6w
         out[f"C2_lsrk54_advection_{'fused' if fused else 'unfused'}"] = {
             "ms_per_step": ms, "dof_stage_per_s": n * 5 / (ms * 1e-3), "GBs": model * n / (ms * 1e-3) / 1e9,
             "frac": model * n / (ms * 1e-3) / 1e9 / peak, "bytes_per_dof_step": model}
@@ -650,6 +650,9 @@ def run_extras(cts, ctx, stream, op, u):
         torch.cuda.empty_cache()
     out["C3_ars343_column_f32"] = run_c3_f32(cts, ctx, stream)
     torch.cuda.empty_cache()
+    for fused in (True, False):
+        out[f"F2_rosenbrock_sspknoth_column_{'fused' if fused else 'unfused'}"] = run_rosenbrock(cts, ctx, stream, fused)
+        torch.cuda.empty_cache()
     # --- the default workload with W regenerated in the stage kernel from K_col instead of stored (bit-identical results,
     # 3w B/DOF less per implicit stage; `--matrix-free` runs the whole bench line this way)
     part = cts.SlabPartition(NY, 1, 0)
@@ -685,6 +688,34 @@ def run_c3_f32(cts, ctx, stream):
            "GBs": model * op.ndof / (ms * 1e-3) / 1e9, "frac": model * op.ndof / (ms * 1e-3) / 1e9 / peaks()[0],
            "finite": bool(torch.isfinite(u.tensor).all())}
     del integ, op, u, K
+    return res
+
+
+def run_rosenbrock(cts, ctx, stream, fused):
+    """RosenbrockAlgorithm(tableau(SSPKnoth())) (rosenbrock.jl:136-239) on the default column workload
+    (2^21 columns x 64 levels, Float64, explicit source + horizontal coupling, halo dss!).  `fused`: T_imp! + the `.+=` chain of
+    the stage right-hand side + ldiv! run as one tile kernel per stage (cts_column_rosenbrock_stage); otherwise the reference's
+    pass structure.  Bytes = those of the kernels that ran (cts_bytes_count)."""
+    import numpy as np
+    import torch
+    part = cts.SlabPartition(NY, 1, 0)
+    op, _, u = build_problem(cts, ctx, part, False)
+    integ = cts.init(cts.ODEProblem(op.ode_function(), u, (0.0, 1.0e9), None), cts.RosenbrockAlgorithm(cts.tableau(cts.SSPKnoth())),
+                     dt=DT, save=False)
+    integ.cache.set_fusion(fused)
+    op.dss(u, None, 0.0)
+    cts.step_(integ)
+    steps = 3
+    b0, l0 = ctx.bytes_count(), ctx.launch_count()
+    ms = timed(stream, lambda: cts.step_(integ), steps, warm=0)
+    nbytes, launches = (ctx.bytes_count() - b0) / steps, (ctx.launch_count() - l0) / steps
+    peak = peaks()[0]
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    res = {"ms_per_step": ms, "dof_stage_per_s": op.ndof_owned * 3 / (ms * 1e-3), "stages_per_step": 3,
+           "bytes_per_dof_step": nbytes / op.ndof, "GBs": gbs, "frac": gbs / peak, "launches_per_step": launches,
+           "fused_stage_launches_per_step": integ.cache.stats()["fused_stage_launches"] / (steps + 1),
+           "finite": bool(torch.isfinite(u.tensor).all())}
+    del integ, op, u
     return res
 
 

@@ -136,6 +136,7 @@ SIGNATURES = [
     ("cts_rosenbrock_step", _I, [_P, _P, _D, _D]),
     ("cts_rosenbrock_cache_buffer", _I, [_P, C.c_char_p, _P]),
     ("cts_rosenbrock_cache_stats", _I, [_P, _P]),
+    ("cts_rosenbrock_cache_set_fusion", _I, [_P, _I]),
     ("cts_ssprk_stage", _I, [_P, _I, _SZ, _P, _P, _P, _P, _P, _P, _D, _I, _D, _D, _I, c_double_p, c_void_pp, _I, _I]),
     ("cts_newton_residual", _I, [_P, _I, _SZ, _P, _P, _D, _P]),
     ("cts_sub_inplace", _I, [_P, _I, _SZ, _P, _P]),

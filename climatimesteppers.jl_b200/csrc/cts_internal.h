@@ -88,6 +88,8 @@ constexpr int kMaxMulti = 8;
     if (!(ctx)) return CTS_EINVAL; \
   } while (0)
 
+bool cts_ctx_alive(const cts_ctx* ctx);  // false once cts_ctx_destroy has run (ctx.cu: live-context registry)
+
 inline int cts_fail(cts_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->err = msg;
   return code;
@@ -181,6 +183,13 @@ int cts_ctx_ensure_comm_stream(cts_ctx* ctx);
 bool cts_column_residual_fusable(const cts_op_column* op);
 int cts_column_fused_residual(cts_op_column* op, void* out, const void* x, const void* dx, double eps, const void* U0,
                               const void* f, double dtgamma);
+// right-hand side + column solve in one pass (ops.cu): the left-preconditioned Jacobian-free GMRES matvec
+//   q = W \ ((f(x + eps v) - f(x))/eps)   and the Rosenbrock stage   k_i = W \ (-dtγ (T_imp(U) [+ fU_exp] + sum_j coef_j terms_j))
+bool cts_column_rhs_solve_fusable(const cts_op_column* op);
+int cts_column_jvp_precond(cts_op_column* op, void* q, const void* x, const void* v, double eps, const void* U0, const void* f,
+                           double dtgamma, const cts_tridiag* W);
+int cts_column_rosenbrock_stage(cts_op_column* op, void* k_out, const void* U, const void* fU_exp, int nt, const double* coef,
+                                const void* const* terms, double dtgamma, const cts_tridiag* W);
 bool cts_op_column_is_linear(const cts_op_column* op);
 bool cts_op_column_matrix_free(const cts_op_column* op);
 cts_ctx* cts_op_column_ctx(const cts_op_column* op);
@@ -188,3 +197,4 @@ cts_ctx* cts_op_advection_ctx(const cts_op_advection* op);
 cts_dtype cts_op_column_dtype(const cts_op_column* op);
 cts_dtype cts_op_advection_dtype(const cts_op_advection* op);
 size_t cts_op_advection_n(const cts_op_advection* op);
+bool cts_advection_inplace_supported(const cts_op_advection* op, const void* u, const void* du);  // u_out == u_in allowed

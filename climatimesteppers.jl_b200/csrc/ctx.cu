@@ -1,5 +1,24 @@
 // Context, memory and synthetic-input helpers of libcts_sm100a.so.
+#include <mutex>
+#include <unordered_set>
+
 #include "cts_internal.h"
+
+// Live-context registry.  Caches, vectors and operators keep a plain pointer to their context, and garbage-collected hosts
+// (Julia finalizers, Python __del__) release objects in no particular order: releasing something whose context is already
+// gone must not touch the dead context (cts_free then degrades to a plain cudaFree; *_destroy skip the stream work).
+namespace {
+std::mutex g_ctx_mu;
+std::unordered_set<const cts_ctx*>& live_ctxs() {
+  static std::unordered_set<const cts_ctx*> s;
+  return s;
+}
+}  // namespace
+bool cts_ctx_alive(const cts_ctx* ctx) {
+  if (!ctx) return false;
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  return live_ctxs().count(ctx) != 0;
+}
 
 extern "C" {
 
@@ -30,6 +49,10 @@ int cts_ctx_create(cts_ctx** out, int device, void* cuda_stream) {
     }
     ctx->own_stream = true;
   }
+  {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    live_ctxs().insert(ctx);
+  }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
   bool ok = cudaMalloc(&ctx->d_result, sizeof(double) * kMaxMulti) == cudaSuccess &&
@@ -48,6 +71,10 @@ int cts_comm_destroy(cts_ctx* ctx);
 
 int cts_ctx_destroy(cts_ctx* ctx) {
   if (!ctx) return CTS_EINVAL;
+  {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (!live_ctxs().erase(ctx)) return CTS_EINVAL;  // already destroyed (or never created here)
+  }
   cudaSetDevice(ctx->device);
   if (ctx->nccl_comm) cts_comm_destroy(ctx);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -136,6 +163,11 @@ int cts_alloc(cts_ctx* ctx, size_t bytes, void** dptr) {
 int cts_free(cts_ctx* ctx, void* dptr) {
   CTS_CHECK_CTX(ctx);
   if (!dptr) return CTS_OK;
+  if (!cts_ctx_alive(ctx)) {  // released after its context (finalizer order): cudaFree synchronises the device itself
+    cudaFree(dptr);
+    cudaGetLastError();
+    return CTS_OK;
+  }
   CTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   CTS_CUDA(ctx, cudaFree(dptr));
   return CTS_OK;

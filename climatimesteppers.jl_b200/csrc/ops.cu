@@ -34,6 +34,7 @@ struct cts_op_advection {
   cts_dtype ft;
   size_t n;
   double c, dx;
+  void* edge = nullptr;  // in-place fused stage: the upwind neighbour of every CTA's first element (lazy, n/(256*VN) values)
 };
 
 namespace {
@@ -91,6 +92,66 @@ __global__ void __launch_bounds__(256) advection_kernel(T* du, const T* u, T* u_
   }
 }
 
+// In-place fused stage (u_out == u): the stencil reads u[i-1], which another thread overwrites.  Inside a CTA every load is
+// issued before the barrier and every store after it; across CTAs the one value that crosses the boundary (the upwind
+// neighbour of the CTA's first element) is gathered into `edge` by a tiny kernel before the stage runs.  Same arithmetic
+// as advection_kernel<FUSED>: bit-identical.  With it an odd stage count (LSRK54: 5) needs no two-pass stage to end in
+// the caller's array: 5 x 4w = 160 B/DOF per step instead of 176.
+template <typename T>
+__global__ void __launch_bounds__(256) advection_edges_kernel(T* __restrict__ edge, const T* __restrict__ u, size_t n, size_t chunk,
+                                                              size_t nblocks) {
+  const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  const size_t first = b * chunk;
+  edge[b] = u[first == 0 ? n - 1 : first - 1];
+}
+
+template <typename T, typename C>
+__global__ void __launch_bounds__(256) advection_inplace_kernel(T* du, T* u, const T* __restrict__ edge, size_t n, T negc, T dx,
+                                                                T alpha, T beta, C dtB) {
+  using V = typename Vec<T>::type;
+  constexpr int VN = Vec<T>::N;
+  const size_t nv = n / VN;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = i < nv;
+  T eu[VN], ed[VN];
+  T left = T(0);
+  if (ok) {
+    vec_unpack<T>(reinterpret_cast<const V*>(u)[i], eu);
+    vec_unpack<T>(reinterpret_cast<const V*>(du)[i], ed);
+    left = threadIdx.x == 0 ? edge[blockIdx.x] : u[i * VN - 1];
+  }
+  __syncthreads();  // every load of this CTA precedes every store
+  if (!ok) return;
+  T od[VN], ou[VN];
+#pragma unroll
+  for (int e = 0; e < VN; ++e) {
+    T rhs = adv_rhs<T>(eu[e], left, negc, dx);
+    od[e] = radd(rmul(alpha, rhs), rmul(beta, ed[e]));
+    ou[e] = (T)cts_ew::op_add((C)eu[e], cts_ew::op_mul(dtB, (C)od[e]));
+    left = eu[e];
+  }
+  reinterpret_cast<V*>(du)[i] = vec_pack<T>(od);
+  reinterpret_cast<V*>(u)[i] = vec_pack<T>(ou);
+}
+
+template <typename T, typename C>
+int launch_advection_inplace(cts_op_advection* op, void* du, void* u, double A, double dtB) {
+  cts_ctx* ctx = op->ctx;
+  const size_t n = op->n;
+  constexpr int VN = Vec<T>::N;
+  const size_t chunk = (size_t)256 * VN;
+  const size_t blocks = (n / VN + 255) / 256;
+  if (!op->edge) CTS_TRY(cts_alloc(ctx, blocks * sizeof(T), &op->edge));
+  CTS_COUNT_BYTES(ctx, 4, n, sizeof(T));  // u, du in; du, u out (the edge gather moves n/(256 VN) elements)
+  advection_edges_kernel<T><<<(unsigned)((blocks + 255) / 256), 256, 0, ctx->stream>>>((T*)op->edge, (const T*)u, n, chunk, blocks);
+  CTS_LAUNCH_CHECK(ctx);
+  advection_inplace_kernel<T, C><<<(unsigned)blocks, 256, 0, ctx->stream>>>((T*)du, (T*)u, (const T*)op->edge, n, (T)(-op->c),
+                                                                           (T)op->dx, (T)1.0, (T)A, (C)dtB);
+  CTS_LAUNCH_CHECK(ctx);
+  return CTS_OK;
+}
+
 template <typename T, typename C, bool FUSED>
 int launch_advection(cts_op_advection* op, void* du, const void* u, void* u_out, double alpha, double beta, double dtB) {
   cts_ctx* ctx = op->ctx;
@@ -123,6 +184,7 @@ int cts_op_advection_create(cts_ctx* ctx, cts_dtype ft, size_t n, double c, doub
   return CTS_OK;
 }
 int cts_op_advection_destroy(cts_op_advection* op) {
+  if (op && op->edge) cts_free(op->ctx, op->edge);
   delete op;
   return CTS_OK;
 }
@@ -135,9 +197,20 @@ int cts_op_advection_incr(void* vop, void* du, const void* u, double t, double a
 
 }  // extern "C"
 
+bool cts_advection_inplace_supported(const cts_op_advection* op, const void* u, const void* du) {
+  const size_t vn = op->ft == CTS_F64 ? 2 : 4;
+  return (op->n % vn) == 0 && cts_aligned16(u) && cts_aligned16(du);
+}
+
 int cts_advection_fused_stage(cts_op_advection* op, void* u_out, const void* u_in, void* du, double A, double dtB,
                               int compute_native) {
-  if (!op || u_out == u_in) return CTS_EINVAL;
+  if (!op) return CTS_EINVAL;
+  if (u_out == u_in) {  // in place
+    if (!cts_advection_inplace_supported(op, u_out, du)) return CTS_EUNSUPPORTED;
+    if (op->ft == CTS_F64) return launch_advection_inplace<double, double>(op, du, u_out, A, dtB);
+    if (compute_native) return launch_advection_inplace<float, float>(op, du, u_out, A, dtB);
+    return launch_advection_inplace<float, double>(op, du, u_out, A, dtB);
+  }
   if (op->ft == CTS_F64) return launch_advection<double, double, true>(op, du, u_in, u_out, 1.0, A, dtB);
   if (compute_native) return launch_advection<float, float, true>(op, du, u_in, u_out, 1.0, A, dtB);
   return launch_advection<float, double, true>(op, du, u_in, u_out, 1.0, A, dtB);
@@ -1568,6 +1641,256 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
   }
   return CTS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// "Right-hand side + column solve" tile kernel: x = W \ rhs, where rhs is formed on the fly from level vectors in
+// registers (the operator's level neighbours come from warp shuffles) and never goes to HBM.  Two uses:
+//   MODE_ROS  Rosenbrock stage (rosenbrock.jl:164-224):  fU = 0; fU += T_imp(U) [; fU += fU_exp] [; fU += c_j k_j ...];
+//             fU *= -dtγ;  k_i = W \ fU            -- T_imp! + the `.+=` chain + ldiv! in one pass
+//             ((1 [+1] + nt + 3) w read, 1w written instead of 2w + (nt + 2 [+1]) w + 5w)
+//   MODE_JVP  left-preconditioned Jacobian-free matvec of GMRES (newtons_method.jl:173-182,497):
+//             q = W \ ((f(x + eps v) - f(x))/eps)  -- K7 + T_imp! + K3 + K8 + ldiv!: 8w instead of 5w + 5w
+// Same device functions and roundings as the stand-alone kernels (axpy_chain_vec_kernel, column_residual_kernel,
+// tridiag_tile_kernel): bit-identical results.  A CTA owns TileShape<T>::kCols columns (one contiguous range); W arrives
+// by bulk TMA while the right-hand side is assembled; the solve is the two-sided product-form Thomas of tile_device.cuh.
+// ---------------------------------------------------------------------------------------------
+constexpr int MODE_ROS = 0, MODE_JVP = 1;
+constexpr int kRhsMaxTerms = 6;
+struct RhsSolveArgs {
+  void* out;
+  const void* x;     // ROS: U          JVP: x
+  const void* v;     // ROS: fU_exp|0   JVP: Krylov vector
+  const void* U0;    // JVP: U0
+  const void* f;     // JVP: f(x)
+  const void* terms[kRhsMaxTerms];  // ROS: k_j of the C[i, j]/dt terms
+  double coef[kRhsMaxTerms];
+  int nt;
+  double scale;      // ROS: -dtγ
+  double eps;        // JVP
+  double dtg;
+  const void* acol;
+  const void* dl;
+  const void* d;
+  const void* du;
+  int nlev;
+  size_t ncols;
+  int pitch;
+};
+
+template <typename T, int MODE, bool NONLIN>
+__global__ void __launch_bounds__(kFusedThreads, 5) column_rhs_solve_kernel(const RhsSolveArgs a) {
+  using V = typename Vec<T>::type;
+  constexpr int VN = Vec<T>::N;
+  constexpr int kCols = TileShape<T>::kCols;
+  constexpr int kSolvers = TileShape<T>::kThreads;
+  extern __shared__ __align__(128) char smem[];
+  const int pitch = a.pitch;
+  const int tile_bytes = kCols * pitch;
+  char* sx = smem;
+  char* sdl = smem + tile_bytes;
+  char* sd = smem + 2 * tile_bytes;
+  char* sdu = smem + 3 * tile_bytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 4 * tile_bytes);
+  const int nlev = a.nlev;
+  const size_t col0 = (size_t)blockIdx.x * kCols;
+  const int nvalid = (int)((a.ncols - col0) < (size_t)kCols ? (a.ncols - col0) : (size_t)kCols);
+  const int col_bytes = nlev * (int)sizeof(T);
+  const size_t goff = col0 * (size_t)nlev;
+  const size_t gvec0 = goff * sizeof(T) / 16;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(bar, (uint32_t)(3 * nvalid * col_bytes));
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nvalid) {
+    const int c = threadIdx.x;
+    const size_t g = goff + (size_t)c * nlev;
+    bulk_g2s(sdl + c * pitch, (const T*)a.dl + g, col_bytes, bar);
+    bulk_g2s(sd + c * pitch, (const T*)a.d + g, col_bytes, bar);
+    bulk_g2s(sdu + c * pitch, (const T*)a.du + g, col_bytes, bar);
+  }
+  const int cpc = col_bytes / 16;  // vectors per column: a power of two <= 32 (a column is a lane group)
+  const int cshift = 31 - __clz(cpc);
+  const int total = nvalid * cpc;
+  const T eps = (T)a.eps;
+  const int round_each = sizeof(T) == 4;
+#pragma unroll 2
+  for (int r = 0; r < kKeep; ++r) {
+    const int q = (int)threadIdx.x + r * kFusedThreads;
+    const bool ok = q < total;
+    const int col = q >> cshift, kk = q & (cpc - 1);
+    const size_t gi = gvec0 + (size_t)q;
+    V vx = {}, vv = {}, vu = {}, vf = {}, vt[kRhsMaxTerms];
+    T acol = T(0);
+    if (ok) {
+      vx = reinterpret_cast<const V*>(a.x)[gi];
+      if (MODE == MODE_JVP || a.v) vv = reinterpret_cast<const V*>(a.v)[gi];
+      if (MODE == MODE_JVP) {
+        vu = reinterpret_cast<const V*>(a.U0)[gi];
+        vf = reinterpret_cast<const V*>(a.f)[gi];
+      } else {
+#pragma unroll
+        for (int k = 0; k < kRhsMaxTerms; ++k)
+          if (k < a.nt) vt[k] = reinterpret_cast<const V*>(a.terms[k])[gi];
+      }
+      acol = ((const T*)a.acol)[col0 + col];
+    }
+    T ex[VN], ev[VN], eu[VN], ef[VN], x2[VN], eo[VN];
+    vec_unpack<T>(vx, ex);
+    vec_unpack<T>(vv, ev);
+    vec_unpack<T>(vu, eu);
+    vec_unpack<T>(vf, ef);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) x2[e] = MODE == MODE_JVP ? radd(ex[e], rmul(eps, ev[e])) : ex[e];  // K7
+    T below = __shfl_up_sync(0xffffffffu, x2[VN - 1], 1, cpc);
+    T above = __shfl_down_sync(0xffffffffu, x2[0], 1, cpc);
+    if (kk == 0) below = T(0);
+    if (kk == cpc - 1) above = T(0);
+    T ti[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      const T um = e > 0 ? x2[e > 0 ? e - 1 : 0] : below;
+      const T up = e + 1 < VN ? x2[e + 1 < VN ? e + 1 : e] : above;
+      ti[e] = NONLIN ? timp_nonlinear<T>(acol, um, x2[e], up) : timp_linear<T>(acol, um, x2[e], up);
+    }
+    if (MODE == MODE_JVP) {
+#pragma unroll
+      for (int e = 0; e < VN; ++e) {
+        const T f2 = (T)__dsub_rn(__dadd_rn((double)eu[e], __dmul_rn(a.dtg, (double)ti[e])), (double)x2[e]);  // K3
+        eo[e] = rdiv(rsub(f2, ef[e]), eps);                                                                   // K8
+      }
+    } else {
+      T et[kRhsMaxTerms][VN];
+#pragma unroll
+      for (int k = 0; k < kRhsMaxTerms; ++k)
+        if (k < a.nt) vec_unpack<T>(vt[k], et[k]);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) {  // axpy_chain_vec_kernel's evaluation: Float64 accumulator, Float32 states round per term
+        double acc = op_add(0.0, op_mul(1.0, (double)ti[e]));
+        if (round_each) acc = (double)(T)acc;
+        if (a.v) {
+          acc = op_add(acc, op_mul(1.0, (double)ev[e]));
+          if (round_each) acc = (double)(T)acc;
+        }
+#pragma unroll
+        for (int k = 0; k < kRhsMaxTerms; ++k)
+          if (k < a.nt) {
+            acc = op_add(acc, op_mul(a.coef[k], (double)et[k][e]));
+            if (round_each) acc = (double)(T)acc;
+          }
+        eo[e] = (T)op_mul(acc, a.scale);
+      }
+    }
+    if (ok) *reinterpret_cast<V*>(sx + col * pitch + kk * 16) = vec_pack<T>(eo);
+  }
+  __syncthreads();
+  if (threadIdx.x < kSolvers) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = warp * 16 + lane_column(lane);
+    const bool is_up = lane_is_up(lane);
+    const bool valid = col < nvalid;
+    mbar_wait(bar, 0);
+    StoredRows<T> rows{sdl, sd, sdu};
+    babe_solve_lanepair<T, StoredRows<T>, RhsFromTile<T>, false>(rows, RhsFromTile<T>{}, sx, col * pitch, nlev, is_up, valid);
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < total; q += kFusedThreads) {
+    const int col = q >> cshift, kk = q & (cpc - 1);
+    reinterpret_cast<V*>(a.out)[gvec0 + (size_t)q] = *reinterpret_cast<const V*>(sx + col * pitch + kk * 16);
+  }
+}
+
+template <typename T>
+int launch_rhs_solve(cts_op_column* op, RhsSolveArgs& a, int mode) {
+  cts_ctx* ctx = op->ctx;
+  constexpr int kCols = TileShape<T>::kCols;
+  a.nlev = op->d.nlev;
+  a.ncols = op->ncols;
+  a.pitch = pitch_bytes(op->d.nlev, sizeof(T));
+  a.acol = op->a_col;
+  const size_t tiles = (op->ncols + kCols - 1) / kCols;
+  const size_t smem = (size_t)4 * kCols * a.pitch + 16;
+  auto launch = [&](auto k) -> int {
+    CTS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)tiles, kFusedThreads, smem, ctx->stream>>>(a);
+    return CTS_OK;
+  };
+  const bool nl = op->d.nonlinear;
+  if (mode == MODE_JVP) {
+    if (nl) CTS_TRY(launch(column_rhs_solve_kernel<T, MODE_JVP, true>));
+    else CTS_TRY(launch(column_rhs_solve_kernel<T, MODE_JVP, false>));
+  } else {
+    if (nl) CTS_TRY(launch(column_rhs_solve_kernel<T, MODE_ROS, true>));
+    else CTS_TRY(launch(column_rhs_solve_kernel<T, MODE_ROS, false>));
+  }
+  CTS_LAUNCH_CHECK(ctx);
+  return CTS_OK;
+}
+
+}  // namespace
+
+// a column must be a power-of-two number (<= 32) of 16-byte vectors and a tile must fit the threads' kKeep vectors
+bool cts_column_rhs_solve_fusable(const cts_op_column* op) {
+  const int es = op->ft == CTS_F64 ? 8 : 4;
+  const int cb = op->d.nlev * es;
+  if (op->matrix_free || op->d.nlev < 2 || (op->d.nlev % 2) || (cb % 16)) return false;
+  const int cpc = cb / 16;
+  const int cols = op->ft == CTS_F64 ? TileShape<double>::kCols : TileShape<float>::kCols;
+  return cpc <= 32 && (cpc & (cpc - 1)) == 0 && cpc * cols <= kKeep * kFusedThreads;
+}
+
+static bool rhs_solve_w_ok(const cts_op_column* op, const cts_tridiag* W) {
+  return W && W->nlev == op->d.nlev && W->ncols == op->ncols && cts_aligned16(W->dl) && cts_aligned16(W->d) && cts_aligned16(W->du);
+}
+
+int cts_column_jvp_precond(cts_op_column* op, void* q, const void* x, const void* v, double eps, const void* U0, const void* f,
+                           double dtg, const cts_tridiag* W) {
+  if (!op || !q || !x || !v || !U0 || !f) return CTS_EINVAL;
+  if (!cts_column_rhs_solve_fusable(op) || !rhs_solve_w_ok(op, W) || !cts_aligned16(q) || !cts_aligned16(x) || !cts_aligned16(v) ||
+      !cts_aligned16(U0) || !cts_aligned16(f))
+    return CTS_EUNSUPPORTED;
+  RhsSolveArgs a{};
+  a.out = q;
+  a.x = x;
+  a.v = v;
+  a.U0 = U0;
+  a.f = f;
+  a.eps = eps;
+  a.dtg = dtg;
+  a.dl = W->dl;
+  a.d = W->d;
+  a.du = W->du;
+  CTS_COUNT_BYTES(op->ctx, 8, cts_op_column_ndof(op), cts_sizeof(op->ft));  // x, v, U0, f, dl, d, du in; q out
+  return op->ft == CTS_F64 ? launch_rhs_solve<double>(op, a, MODE_JVP) : launch_rhs_solve<float>(op, a, MODE_JVP);
+}
+
+int cts_column_rosenbrock_stage(cts_op_column* op, void* k_out, const void* U, const void* fU_exp, int nt, const double* coef,
+                                const void* const* terms, double dtg, const cts_tridiag* W) {
+  if (!op || !k_out || !U || nt < 0) return CTS_EINVAL;
+  if (nt > kRhsMaxTerms || !cts_column_rhs_solve_fusable(op) || !rhs_solve_w_ok(op, W) || !cts_aligned16(k_out) || !cts_aligned16(U) ||
+      (fU_exp && !cts_aligned16(fU_exp)))
+    return CTS_EUNSUPPORTED;
+  RhsSolveArgs a{};
+  a.out = k_out;
+  a.x = U;
+  a.v = fU_exp;
+  a.nt = nt;
+  for (int k = 0; k < nt; ++k) {
+    if (!cts_aligned16(terms[k])) return CTS_EUNSUPPORTED;
+    a.terms[k] = terms[k];
+    a.coef[k] = coef[k];
+  }
+  a.scale = -dtg;
+  a.dtg = dtg;
+  a.dl = W->dl;
+  a.d = W->d;
+  a.du = W->du;
+  CTS_COUNT_BYTES(op->ctx, 1 + (fU_exp ? 1 : 0) + nt + 3 + 1, cts_op_column_ndof(op), cts_sizeof(op->ft));
+  return op->ft == CTS_F64 ? launch_rhs_solve<double>(op, a, MODE_ROS) : launch_rhs_solve<float>(op, a, MODE_ROS);
+}
+
+namespace {
 
 template <typename T, typename C>
 int dispatch_fused(cts_op_column* op, const cts_fused_stage_args* s) {

@@ -211,8 +211,11 @@ int get_rtol(cts_newton_cache* c, const void* f, int n_iter, double* rtol_out) {
 }
 
 // GMRES (left preconditioned, no restart; vectors beyond `memory` are appended)
+// `matvec_precond` (optional): q = M^-1 (A v) in one pass (the column operator's JVP + tridiagonal solve); same roundings
+// as matvec followed by precond, `w` is then never written.
 int gmres(cts_newton_cache* c, const std::function<int(void* out, const void* v)>& matvec,
-          const std::function<int(void* out, const void* w)>* precond, const void* b, void* x, double rtol) {
+          const std::function<int(void* out, const void* w)>* precond, const void* b, void* x, double rtol,
+          const std::function<int(void* out, const void* v)>* matvec_precond = nullptr) {
   cts_ctx* ctx = c->ctx;
   const cts_dtype ft = c->ft;
   const size_t n = c->n, bytes = n * cts_sizeof(ft);
@@ -263,12 +266,17 @@ int gmres(cts_newton_cache* c, const std::function<int(void* out, const void* v)
       c->known_norm_ptr = c->V[k - 1];
       c->known_norm = vnorm[k - 1];
     }
-    CTS_TRY(matvec(w, c->V[k - 1]));
-    c->known_norm_ptr = nullptr;
-    if (precond)
-      CTS_TRY((*precond)(q, w));
-    else
-      CTS_TRY(cts_memcpy_d2d(ctx, q, w, bytes));
+    if (matvec_precond && precond) {
+      CTS_TRY((*matvec_precond)(q, c->V[k - 1]));
+      c->known_norm_ptr = nullptr;
+    } else {
+      CTS_TRY(matvec(w, c->V[k - 1]));
+      c->known_norm_ptr = nullptr;
+      if (precond)
+        CTS_TRY((*precond)(q, w));
+      else
+        CTS_TRY(cts_memcpy_d2d(ctx, q, w, bytes));
+    }
     std::vector<double> col(k);
     double Hbis_fused = 0;
     if (c->cfg.batch_gram_schmidt) {  // classical GS: one fused sweep of k dots, then one k-term update
@@ -385,9 +393,30 @@ int solve_krylov(cts_newton_cache* c, void* dx, const void* x, const ResidualFn&
     c->stats.ldiv_calls++;
     return CTS_OK;
   };
+  // library column operator + its batched tridiagonal W as preconditioner: JVP and ldiv! of every Krylov iteration are
+  // one tile kernel (8w instead of 5w + 5w)
+  static const bool no_mvp = getenv("CTS_NO_JVP_PRECOND_FUSION") != nullptr;  // developer aid (A/B runs)
+  const bool fuse_mvp = !no_mvp && use_M && c->fused_op && c->ldiv == cts_op_column_ldiv && c->ud == (void*)c->fused_op &&
+                        cts_column_rhs_solve_fusable(c->fused_op) && cts_aligned16(x) && cts_aligned16(f) && cts_aligned16(c->q);
+  std::function<int(void*, const void*)> matvec_precond = [&](void* out, const void* v) -> int {
+    double e = 0;
+    CTS_TRY(jvp_step(c, v, x, &e));
+    cts_prof_scope ps(ctx, CTS_PROF_LDIV);
+    int r = cts_column_jvp_precond(c->fused_op, out, x, v, e, c->fused_U0, f, c->fused_dtg, static_cast<const cts_tridiag*>(c->W));
+    if (r == CTS_EUNSUPPORTED) {  // e.g. a W of another shape: the two separate passes
+      CTS_TRY(cts_column_fused_residual(c->fused_op, c->w, x, v, e, c->fused_U0, f, c->fused_dtg));
+      HOOK(ctx, c->ldiv(c->ud, out, c->W, c->w));
+    } else {
+      CTS_TRY(r);
+    }
+    c->stats.f_evals++;
+    c->stats.jvp_evals++;
+    c->stats.ldiv_calls++;
+    return CTS_OK;
+  };
   double rtol = 0;
   CTS_TRY(get_rtol(c, f, n_iter, &rtol));
-  return gmres(c, matvec, use_M ? &precond : nullptr, f, dx, rtol);
+  return gmres(c, matvec, use_M ? &precond : nullptr, f, dx, rtol, fuse_mvp ? &matvec_precond : nullptr);
 }
 
 // solve_newton! (newtons_method.jl:609-665); no line search, no convergence checker
@@ -1404,7 +1433,7 @@ int cts_imex_cache_create(cts_ctx* ctx, cts_dtype ft, size_t n, const cts_imex_t
 int cts_imex_cache_destroy(cts_imex_cache* c) {
   if (!c) return CTS_EINVAL;
   if (c->graph_exec) {
-    cudaStreamSynchronize(c->ctx->stream);
+    if (cts_ctx_alive(c->ctx)) cudaStreamSynchronize(c->ctx->stream);
     cudaGraphExecDestroy(c->graph_exec);
   }
   imex_free(c);
@@ -1628,18 +1657,24 @@ int cts_lsrk_step(cts_lsrk_cache* c, void* u, double t, double dt, int dt_is_f32
     auto* op = static_cast<cts_op_advection*>(c->ud);
     if (op && cts_op_advection_ctx(op) == ctx && cts_op_advection_dtype(op) == c->ft && cts_op_advection_n(op) == c->n) adv = op;
   }
-  int s0 = 0;
+  int s0 = 0, s_inplace = -1;
   if (adv) {
     if (!c->scratch) CTS_TRY(cts_alloc(ctx, c->n * cts_sizeof(c->ft), &c->scratch));
     // Out-of-place fused stages ping-pong between u and scratch and must end in u (the caller's array,
-    // integrators.jl:236): an even number of fused stages, preceded by one un-fused stage if nstages is odd.
-    s0 = c->nstages % 2;
+    // integrators.jl:236): an even number of them; with an odd stage count the LAST stage runs in place on u (same
+    // 4w B/DOF), or -- for a state the vector kernel cannot take -- the first stage runs un-fused.
+    if (c->nstages % 2) {
+      if (cts_advection_inplace_supported(adv, u, c->du))
+        s_inplace = c->nstages - 1;
+      else
+        s0 = 1;
+    }
   }
   for (int s = 0; s < c->nstages; ++s) {
     if (adv && s >= s0) {
       const bool from_u = ((s - s0) % 2) == 0;
-      void* src = from_u ? u : c->scratch;
-      void* dst = from_u ? c->scratch : u;
+      void* src = s == s_inplace ? u : (from_u ? u : c->scratch);
+      void* dst = s == s_inplace ? u : (from_u ? c->scratch : u);
       cts_prof_scope ps(ctx, CTS_PROF_LSRK_FUSED);
       CTS_TRY(cts_advection_fused_stage(adv, dst, src, c->du, c->A[s], dtB_of(s), native));
       c->stats.fused_stage_launches++;
@@ -1696,6 +1731,7 @@ struct cts_rosenbrock_cache {
   void* fU_lim = nullptr;
   void* dYdt = nullptr;
   void* k[CTS_MAX_STAGES] = {};
+  bool fusion = true;
   cts_solver_stats stats{};
 };
 
@@ -1772,6 +1808,12 @@ int cts_rosenbrock_cache_buffer(cts_rosenbrock_cache* c, const char* name, void*
   return *dptr ? CTS_OK : cts_fail(c->ctx, CTS_EINVAL, "unknown buffer name");
 }
 
+int cts_rosenbrock_cache_set_fusion(cts_rosenbrock_cache* c, int enabled) {
+  if (!c) return CTS_EINVAL;
+  c->fusion = enabled != 0;
+  return CTS_OK;
+}
+
 int cts_rosenbrock_cache_stats(cts_rosenbrock_cache* c, cts_solver_stats* out) {
   if (!c || !out) return CTS_EINVAL;
   *out = c->stats;
@@ -1788,6 +1830,16 @@ int cts_rosenbrock_step(cts_rosenbrock_cache* c, void* u, double t, double dt) {
   const cts_ode_function& f = c->f;
   const int s = tab.s;
   const double dtg = dt * tab.Gamma[0];  // "only valid when Γ[i, i] is constant" :151-153
+  // Library column operator as T_imp!/Wfact/ldiv! (no ∂Y∂t, no limiter): T_imp!, the `.+=` chain of the right-hand side and
+  // ldiv! of a stage are ONE tile kernel (cts_column_rosenbrock_stage; bit-identical to the three passes).
+  cts_op_column* rop = nullptr;
+  if (c->fusion && f.T_imp == cts_op_column_T_imp && f.Wfact == cts_op_column_Wfact && f.ldiv == cts_op_column_ldiv && !c->tgrad &&
+      !f.has_lim && f.ud && f.W) {
+    auto* op = static_cast<cts_op_column*>(f.ud);
+    if (cts_op_column_ctx(op) == ctx && cts_op_column_dtype(op) == c->ft && cts_op_column_ndof(op) == c->n &&
+        cts_column_rhs_solve_fusable(op))
+      rop = op;
+  }
   if (f.T_imp) {
     cts_prof_scope ps(ctx, CTS_PROF_WFACT);
     HOOK(ctx, f.Wfact(f.ud, f.W, u, dtg, t));
@@ -1827,6 +1879,30 @@ int cts_rosenbrock_step(cts_rosenbrock_cache* c, void* u, double t, double dt) {
       if (needs_update(f.update_cache, CTS_SIG_END_OF_STAGE)) CTS_TRY(ros_state(c, f.cache, U, ti));
     }
     nt = 0;
+    if (rop) {
+      if (f.T_exp_T_lim) {
+        cts_prof_scope ps(ctx, CTS_PROF_T_EXP);
+        HOOK(ctx, f.T_exp_T_lim(f.ud, c->fU_exp, c->fU_lim, U, ti));
+      }
+      for (int j = 0; j < i; ++j)
+        if (tab.C[i * s + j] != 0) {
+          coef[nt] = tab.C[i * s + j] / dt;
+          terms[nt++] = c->k[j];
+        }
+      int r;
+      {
+        cts_prof_scope ps(ctx, CTS_PROF_FUSED_STAGE);
+        r = cts_column_rosenbrock_stage(rop, c->k[i], U, f.T_exp_T_lim ? c->fU_exp : nullptr, nt, coef, terms, dtg,
+                                        static_cast<const cts_tridiag*>(f.W));
+      }
+      if (r == CTS_OK) {
+        c->stats.ldiv_calls++;
+        c->stats.fused_stage_launches++;
+        continue;
+      }
+      if (r != CTS_EUNSUPPORTED) return r;
+      nt = 0;  // unaligned buffers or too many terms: the generic passes below (T_exp! is simply evaluated again)
+    }
     if (f.T_imp) {
       cts_prof_scope ps(ctx, CTS_PROF_T_IMP);
       HOOK(ctx, f.T_imp(f.ud, c->fU_imp, U, ti));

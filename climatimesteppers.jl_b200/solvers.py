@@ -297,7 +297,7 @@ class RosenbrockCache:
         return s.as_dict()
 
     def set_fusion(self, enabled: bool):
-        pass
+        self.ctx.check(self.ctx.lib.cts_rosenbrock_cache_set_fusion(self.handle, 1 if enabled else 0))
 
     def step_u(self, integrator):
         u: B200Vector = integrator.u

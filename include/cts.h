@@ -331,6 +331,9 @@ int cts_rosenbrock_step(cts_rosenbrock_cache* c, void* u, double t, double dt);
 /* "U","fU","fU_imp","fU_exp","fU_lim","dYdt","k<i>" (1-based i) */
 int cts_rosenbrock_cache_buffer(cts_rosenbrock_cache* c, const char* name, void** dptr);
 int cts_rosenbrock_cache_stats(cts_rosenbrock_cache* c, cts_solver_stats* out);
+/* Developer switch: 0 = always the reference's pass structure (T_imp!, `.+=` chain, ldiv! as separate passes); default 1 =
+ * one tile kernel per stage when T_imp!/Wfact/ldiv! are the library's column operator (rosenbrock.jl:164-224). */
+int cts_rosenbrock_cache_set_fusion(cts_rosenbrock_cache* c, int enabled);
 int cts_lsrk_cache_stats(cts_lsrk_cache* c, cts_solver_stats* out);
 
 /* Newton's method on its own (`solve_newton!`, newtons_method.jl:609-665) for unit tests of the solver:

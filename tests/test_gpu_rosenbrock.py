@@ -46,9 +46,12 @@ def test_axpy_chain_matches_sequential_passes(cts, dtype, nterms, base, scale):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("halo,nu,nonlinear,explicit", [(1, 0.7, False, True), (0, 0.0, False, False), (0, 0.5, True, True)])
-def test_rosenbrock_column_steps_bit_exact(cts, dtype, halo, nu, nonlinear, explicit):
-    nlev, nx, ny = 32, 6, 5
+@pytest.mark.parametrize("fusion", [True, False])
+@pytest.mark.parametrize("halo,nu,nonlinear,explicit,nlev,nx,ny", [(1, 0.7, False, True, 32, 6, 5), (0, 0.0, False, False, 32, 6, 5),
+                                                                   (0, 0.5, True, True, 32, 6, 5), (1, 0.7, False, True, 64, 40, 9),
+                                                                   (0, 0.5, True, False, 64, 33, 7)])
+def test_rosenbrock_column_steps_bit_exact(cts, dtype, fusion, halo, nu, nonlinear, explicit, nlev, nx, ny):
+    # fusion: T_imp! + the `.+=` chain + ldiv! of a stage as one tile kernel (cts_column_rosenbrock_stage) vs the three passes
     K, T0, S = M.column_inputs(nlev, nx, ny, 0, ny, halo, dtype)
     model = M.ColumnModel(nlev, nx, ny, K, S_lev=S, nu=nu, halo=halo, nonlinear=nonlinear)
     op = cts.ColumnOperator(nlev, nx, ny, dev(cts, K), S_lev=dev(cts, S), nu=nu, halo=halo, nonlinear=nonlinear)
@@ -60,12 +63,14 @@ def test_rosenbrock_column_steps_bit_exact(cts, dtype, halo, nu, nonlinear, expl
     u = dev(cts, T0)
     integ = cts.init(cts.ODEProblem(op.ode_function(explicit=explicit), u, (0.0, 1e9), None),
                      cts.RosenbrockAlgorithm(cts.tableau(cts.SSPKnoth())), dt=dtype(0.01) if dtype == np.float32 else 0.01, save=False)
+    integ.cache.set_fusion(fusion)
     t = 0.0
     for _ in range(4):
         step(uo, None, t, 0.01 if dtype == np.float64 else float(np.float32(0.01)))
         cts.step_(integ)
         t = integ.t
     assert integ.cache.stats()["ldiv_calls"] == 12 and integ.cache.stats()["wfact_evals"] == 4
+    assert integ.cache.stats()["fused_stage_launches"] == (12 if fusion else 0)
     np.testing.assert_array_equal(u.to_host(), uo)
     assert len(integ.cache.k) == 3 and integ.cache.buffer("fU_lim") is not None   # test/unit/cache_sizes.jl:46-54
 

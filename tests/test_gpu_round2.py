@@ -366,3 +366,17 @@ def test_c4_ssp333_jfnk_at_2pow20_dof(cts, dtype, tol, adj):
     assert err <= 2 * tol
     if dtype == np.float64:
         np.testing.assert_array_equal(got, uo)
+
+
+def test_release_after_context_destroy_is_safe(cts):
+    """Finalizer order is unspecified in garbage-collected hosts (Julia finalizers, Python __del__): freeing a device
+    allocation or destroying a cache after its context has been destroyed must not touch the dead context."""
+    import ctypes as C
+    lib = cts._lib.load()
+    ctx = C.c_void_p()
+    assert lib.cts_ctx_create(C.byref(ctx), 0, None) == 0
+    p = C.c_void_p()
+    assert lib.cts_alloc(ctx, 1 << 20, C.byref(p)) == 0
+    assert lib.cts_ctx_destroy(ctx) == 0
+    assert lib.cts_free(ctx, p) == 0          # plain cudaFree, no use of the dead context
+    assert lib.cts_ctx_destroy(ctx) != 0      # double destroy is refused, not a double free
