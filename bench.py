@@ -91,6 +91,43 @@ def host_mem_gib():
     return 0.0
 
 
+def bind_to_gpu_numa_node(local):
+    """Best effort: run this rank's host threads on the CPUs of the NUMA node its GPU hangs off, so that the pinned staging
+    buffers of the end-to-end measurement (first touched by this process) are node-local and N ranks do not all stream
+    through one memory controller.  Returns what was found (reported in the JSON line); never fails."""
+    info = {"gpu_numa_node": None, "bound_cpus": None}
+    try:
+        import torch
+        try:
+            pr = torch.cuda.get_device_properties(local)
+            bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        except AttributeError:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = vis.split(",")[local] if vis else str(local)
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", idx],
+                                 capture_output=True, text=True, timeout=20).stdout.strip().lower()
+            dom, rest = out.split(":", 1)
+            bdf = f"{dom[-4:]}:{rest}"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        info["gpu_numa_node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed and allowed != set(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, allowed)
+            info["bound_cpus"] = len(allowed)
+    except Exception as e:  # no sysfs entry, no such property, container without the right to set affinity ...
+        info["error"] = repr(e)[:120]
+    return info
+
+
 def cpu_reference(steps, warmup, sample_cols_log2=18, threads=None):
     """The reference's pass structure (oracle/cts_oracle.c, OpenMP over all host cores) on 2^sample_cols_log2 columns x 64
     levels of the same workload (21 = the full BASELINE configuration).  `threads = 1` gives the single-core figure: the
@@ -303,6 +340,8 @@ def run_ours(args):
     if NY % world or NY // world < 32:
         raise SystemExit(f"bench.py: {NY} rows cannot be split into {world} slabs of >= 32 rows")
     torch.cuda.set_device(local)
+    all_cpus = set(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None
+    numa = bind_to_gpu_numa_node(local) if world > 1 else {"gpu_numa_node": None, "bound_cpus": None}
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -532,7 +571,12 @@ def run_ours(args):
                         "steps": pipe_steps, "note": "same per-step H2D + cts_imex_step + D2H, independent instances double-buffered "
                         "on three streams so the copies overlap the kernels"},
                     "api": "C ABI: cts_memcpy_h2d (pinned host state) + cts_imex_step (via cts_b200.step_) + cts_memcpy_d2h_sync, every step"},
-            "gpu_launches": launches, "clocks": clocks, "solver_stats": stats, "finite": finite}
+            "gpu_launches": launches, "clocks": clocks, "solver_stats": stats, "finite": finite, "host_numa": numa}
+    if all_cpus is not None:
+        try:
+            os.sched_setaffinity(0, all_cpus)   # the CPU baseline below uses every host core again
+        except Exception:
+            pass
     if not args.no_cpu_baseline:   # rank 0, every N (the CPU arm is the same fixed global problem)
         cb = cpu_reference(2, 1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

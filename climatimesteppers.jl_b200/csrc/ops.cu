@@ -1655,7 +1655,7 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
 // by bulk TMA while the right-hand side is assembled; the solve is the two-sided product-form Thomas of tile_device.cuh.
 // ---------------------------------------------------------------------------------------------
 constexpr int MODE_ROS = 0, MODE_JVP = 1;
-constexpr int kRhsMaxTerms = 6;
+constexpr int kRhsMaxTerms = 3;  // chain terms besides T_imp(U) and fU_exp (SSPKnoth needs 2)
 struct RhsSolveArgs {
   void* out;
   const void* x;     // ROS: U          JVP: x
@@ -1677,10 +1677,11 @@ struct RhsSolveArgs {
   int pitch;
 };
 
-template <typename T, int MODE, bool NONLIN>
+template <typename T, int MODE, bool NONLIN, int NTC>
 __global__ void __launch_bounds__(kFusedThreads, 5) column_rhs_solve_kernel(const RhsSolveArgs a) {
   using V = typename Vec<T>::type;
   constexpr int VN = Vec<T>::N;
+  constexpr int NTS = NTC > 0 ? NTC : 1;
   constexpr int kCols = TileShape<T>::kCols;
   constexpr int kSolvers = TileShape<T>::kThreads;
   extern __shared__ __align__(128) char smem[];
@@ -1714,75 +1715,89 @@ __global__ void __launch_bounds__(kFusedThreads, 5) column_rhs_solve_kernel(cons
   const int cshift = 31 - __clz(cpc);
   const int total = nvalid * cpc;
   const T eps = (T)a.eps;
-  const int round_each = sizeof(T) == 4;
-#pragma unroll 2
-  for (int r = 0; r < kKeep; ++r) {
-    const int q = (int)threadIdx.x + r * kFusedThreads;
-    const bool ok = q < total;
-    const int col = q >> cshift, kk = q & (cpc - 1);
-    const size_t gi = gvec0 + (size_t)q;
-    V vx = {}, vv = {}, vu = {}, vf = {}, vt[kRhsMaxTerms];
-    T acol = T(0);
-    if (ok) {
-      vx = reinterpret_cast<const V*>(a.x)[gi];
-      if (MODE == MODE_JVP || a.v) vv = reinterpret_cast<const V*>(a.v)[gi];
-      if (MODE == MODE_JVP) {
-        vu = reinterpret_cast<const V*>(a.U0)[gi];
-        vf = reinterpret_cast<const V*>(a.f)[gi];
-      } else {
+  constexpr bool round_each = sizeof(T) == 4;
+  const bool has_v = MODE == MODE_JVP || a.v != nullptr;
+  constexpr int UN = 2;  // rounds whose loads are all issued before the first use (as in the fused stage kernel)
+  static_assert(kKeep % UN == 0, "rounds are processed in pairs");
 #pragma unroll
-        for (int k = 0; k < kRhsMaxTerms; ++k)
-          if (k < a.nt) vt[k] = reinterpret_cast<const V*>(a.terms[k])[gi];
-      }
-      acol = ((const T*)a.acol)[col0 + col];
-    }
-    T ex[VN], ev[VN], eu[VN], ef[VN], x2[VN], eo[VN];
-    vec_unpack<T>(vx, ex);
-    vec_unpack<T>(vv, ev);
-    vec_unpack<T>(vu, eu);
-    vec_unpack<T>(vf, ef);
+  for (int r0 = 0; r0 < kKeep; r0 += UN) {
+    V vx[UN], vv[UN], vu[UN], vf[UN], vt[NTS][UN];
+    T acol[UN];
+    bool ok[UN];
+    int so[UN], kk[UN];
 #pragma unroll
-    for (int e = 0; e < VN; ++e) x2[e] = MODE == MODE_JVP ? radd(ex[e], rmul(eps, ev[e])) : ex[e];  // K7
-    T below = __shfl_up_sync(0xffffffffu, x2[VN - 1], 1, cpc);
-    T above = __shfl_down_sync(0xffffffffu, x2[0], 1, cpc);
-    if (kk == 0) below = T(0);
-    if (kk == cpc - 1) above = T(0);
-    T ti[VN];
-#pragma unroll
-    for (int e = 0; e < VN; ++e) {
-      const T um = e > 0 ? x2[e > 0 ? e - 1 : 0] : below;
-      const T up = e + 1 < VN ? x2[e + 1 < VN ? e + 1 : e] : above;
-      ti[e] = NONLIN ? timp_nonlinear<T>(acol, um, x2[e], up) : timp_linear<T>(acol, um, x2[e], up);
-    }
-    if (MODE == MODE_JVP) {
-#pragma unroll
-      for (int e = 0; e < VN; ++e) {
-        const T f2 = (T)__dsub_rn(__dadd_rn((double)eu[e], __dmul_rn(a.dtg, (double)ti[e])), (double)x2[e]);  // K3
-        eo[e] = rdiv(rsub(f2, ef[e]), eps);                                                                   // K8
-      }
-    } else {
-      T et[kRhsMaxTerms][VN];
-#pragma unroll
-      for (int k = 0; k < kRhsMaxTerms; ++k)
-        if (k < a.nt) vec_unpack<T>(vt[k], et[k]);
-#pragma unroll
-      for (int e = 0; e < VN; ++e) {  // axpy_chain_vec_kernel's evaluation: Float64 accumulator, Float32 states round per term
-        double acc = op_add(0.0, op_mul(1.0, (double)ti[e]));
-        if (round_each) acc = (double)(T)acc;
-        if (a.v) {
-          acc = op_add(acc, op_mul(1.0, (double)ev[e]));
-          if (round_each) acc = (double)(T)acc;
+    for (int u = 0; u < UN; ++u) {
+      const int q = (int)threadIdx.x + (r0 + u) * kFusedThreads;
+      ok[u] = q < total;
+      const int col = q >> cshift;
+      kk[u] = q & (cpc - 1);
+      so[u] = col * pitch + kk[u] * 16;
+      const size_t gi = gvec0 + (size_t)q;
+      vx[u] = V{};
+      vv[u] = V{};
+      vu[u] = V{};
+      vf[u] = V{};
+      acol[u] = T(0);
+      if (ok[u]) {
+        vx[u] = reinterpret_cast<const V*>(a.x)[gi];
+        if (has_v) vv[u] = reinterpret_cast<const V*>(a.v)[gi];
+        if (MODE == MODE_JVP) {
+          vu[u] = reinterpret_cast<const V*>(a.U0)[gi];
+          vf[u] = reinterpret_cast<const V*>(a.f)[gi];
         }
 #pragma unroll
-        for (int k = 0; k < kRhsMaxTerms; ++k)
-          if (k < a.nt) {
+        for (int k = 0; k < NTC; ++k) vt[k][u] = reinterpret_cast<const V*>(a.terms[k])[gi];
+        acol[u] = ((const T*)a.acol)[col0 + col];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      T ex[VN], ev[VN], eu[VN], ef[VN], x2[VN], eo[VN];
+      vec_unpack<T>(vx[u], ex);
+      vec_unpack<T>(vv[u], ev);
+      vec_unpack<T>(vu[u], eu);
+      vec_unpack<T>(vf[u], ef);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) x2[e] = MODE == MODE_JVP ? radd(ex[e], rmul(eps, ev[e])) : ex[e];  // K7
+      T below = __shfl_up_sync(0xffffffffu, x2[VN - 1], 1, cpc);
+      T above = __shfl_down_sync(0xffffffffu, x2[0], 1, cpc);
+      if (kk[u] == 0) below = T(0);
+      if (kk[u] == cpc - 1) above = T(0);
+      T ti[VN];
+#pragma unroll
+      for (int e = 0; e < VN; ++e) {
+        const T um = e > 0 ? x2[e > 0 ? e - 1 : 0] : below;
+        const T up = e + 1 < VN ? x2[e + 1 < VN ? e + 1 : e] : above;
+        ti[e] = NONLIN ? timp_nonlinear<T>(acol[u], um, x2[e], up) : timp_linear<T>(acol[u], um, x2[e], up);
+      }
+      if (MODE == MODE_JVP) {
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+          const T f2 = (T)__dsub_rn(__dadd_rn((double)eu[e], __dmul_rn(a.dtg, (double)ti[e])), (double)x2[e]);  // K3
+          eo[e] = rdiv(rsub(f2, ef[e]), eps);                                                                   // K8
+        }
+      } else {
+        T et[NTS][VN];
+#pragma unroll
+        for (int k = 0; k < NTC; ++k) vec_unpack<T>(vt[k][u], et[k]);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {  // axpy_chain_vec_kernel's evaluation: Float64 accumulator, Float32 states round per term
+          double acc = op_add(0.0, op_mul(1.0, (double)ti[e]));
+          if (round_each) acc = (double)(T)acc;
+          if (has_v) {
+            acc = op_add(acc, op_mul(1.0, (double)ev[e]));
+            if (round_each) acc = (double)(T)acc;
+          }
+#pragma unroll
+          for (int k = 0; k < NTC; ++k) {
             acc = op_add(acc, op_mul(a.coef[k], (double)et[k][e]));
             if (round_each) acc = (double)(T)acc;
           }
-        eo[e] = (T)op_mul(acc, a.scale);
+          eo[e] = (T)op_mul(acc, a.scale);
+        }
       }
+      if (ok[u]) *reinterpret_cast<V*>(sx + so[u]) = vec_pack<T>(eo);
     }
-    if (ok) *reinterpret_cast<V*>(sx + col * pitch + kk * 16) = vec_pack<T>(eo);
   }
   __syncthreads();
   if (threadIdx.x < kSolvers) {
@@ -1794,10 +1809,14 @@ __global__ void __launch_bounds__(kFusedThreads, 5) column_rhs_solve_kernel(cons
     StoredRows<T> rows{sdl, sd, sdu};
     babe_solve_lanepair<T, StoredRows<T>, RhsFromTile<T>, false>(rows, RhsFromTile<T>{}, sx, col * pitch, nlev, is_up, valid);
   }
+  // x leaves as one bulk copy per column (padded tile -> contiguous global range), like K4
+  fence_proxy_async_smem();  // generic-proxy writes of x -> visible to the async proxy
   __syncthreads();
-  for (int q = threadIdx.x; q < total; q += kFusedThreads) {
-    const int col = q >> cshift, kk = q & (cpc - 1);
-    reinterpret_cast<V*>(a.out)[gvec0 + (size_t)q] = *reinterpret_cast<const V*>(sx + col * pitch + kk * 16);
+  if ((int)threadIdx.x < nvalid) {
+    const int c = threadIdx.x;
+    bulk_s2g((T*)a.out + goff + (size_t)c * nlev, sx + c * pitch, col_bytes);
+    bulk_commit();
+    bulk_wait_read0();
   }
 }
 
@@ -1818,11 +1837,20 @@ int launch_rhs_solve(cts_op_column* op, RhsSolveArgs& a, int mode) {
   };
   const bool nl = op->d.nonlinear;
   if (mode == MODE_JVP) {
-    if (nl) CTS_TRY(launch(column_rhs_solve_kernel<T, MODE_JVP, true>));
-    else CTS_TRY(launch(column_rhs_solve_kernel<T, MODE_JVP, false>));
+    if (nl) CTS_TRY(launch(column_rhs_solve_kernel<T, MODE_JVP, true, 0>));
+    else CTS_TRY(launch(column_rhs_solve_kernel<T, MODE_JVP, false, 0>));
   } else {
-    if (nl) CTS_TRY(launch(column_rhs_solve_kernel<T, MODE_ROS, true>));
-    else CTS_TRY(launch(column_rhs_solve_kernel<T, MODE_ROS, false>));
+#define ROS_CASE(N)                                                              \
+  case N:                                                                        \
+    if (nl) CTS_TRY(launch(column_rhs_solve_kernel<T, MODE_ROS, true, N>));      \
+    else CTS_TRY(launch(column_rhs_solve_kernel<T, MODE_ROS, false, N>));        \
+    break;
+    switch (a.nt) {
+      ROS_CASE(0) ROS_CASE(1) ROS_CASE(2) ROS_CASE(3)
+      default:
+        return CTS_EUNSUPPORTED;
+    }
+#undef ROS_CASE
   }
   CTS_LAUNCH_CHECK(ctx);
   return CTS_OK;

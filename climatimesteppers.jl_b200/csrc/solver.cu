@@ -393,10 +393,12 @@ int solve_krylov(cts_newton_cache* c, void* dx, const void* x, const ResidualFn&
     c->stats.ldiv_calls++;
     return CTS_OK;
   };
-  // library column operator + its batched tridiagonal W as preconditioner: JVP and ldiv! of every Krylov iteration are
-  // one tile kernel (8w instead of 5w + 5w)
-  static const bool no_mvp = getenv("CTS_NO_JVP_PRECOND_FUSION") != nullptr;  // developer aid (A/B runs)
-  const bool fuse_mvp = !no_mvp && use_M && c->fused_op && c->ldiv == cts_op_column_ldiv && c->ud == (void*)c->fused_op &&
+  // library column operator + its batched tridiagonal W as preconditioner: JVP and ldiv! of a Krylov iteration can run as
+  // one tile kernel (8w instead of 5w + 5w, bit-identical).  Opt-in (CTS_JVP_PRECOND_FUSION=1, read per solve): with the
+  // nonlinear operator the tile kernel is FP64-issue bound at its 5 CTAs/SM and measured SLOWER on B200 than the two
+  // full-occupancy passes (1.72 ms vs 0.75 + 0.83 ms per Krylov iteration at 2^27 DOF).
+  const char* mvp_env = getenv("CTS_JVP_PRECOND_FUSION");
+  const bool fuse_mvp = mvp_env && mvp_env[0] == '1' && use_M && c->fused_op && c->ldiv == cts_op_column_ldiv && c->ud == (void*)c->fused_op &&
                         cts_column_rhs_solve_fusable(c->fused_op) && cts_aligned16(x) && cts_aligned16(f) && cts_aligned16(c->q);
   std::function<int(void*, const void*)> matvec_precond = [&](void* out, const void* v) -> int {
     double e = 0;

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Turn the ncu outputs brought back in gpurun_out/ into the small text summaries committed under profiles/.
   python profiles/summarize.py launches gpurun_out/r1_launches.csv > profiles/r1_launches_summary.txt
-  python profiles/summarize.py raw gpurun_out/r1_fused.ncu-rep   > profiles/r1_fused_stage_ncu.txt
+  python profiles/summarize.py raw gpurun_out/r1_fused.ncu-rep   > profiles/r1_fused_stage_ncu.txt   (or the raw-page CSV)
+  python profiles/summarize.py traffic gpurun_out/r2_fused_raw.csv stored_n1   -> profiles/fused_stage_traffic.json
 """
 import csv
 import io
@@ -43,9 +44,38 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__cycles_elapsed.max", "lts__t_sector_hit_rate.pct"]
 
 
-def raw(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def _raw_rows(path):
+    """Rows of `ncu --page raw --csv`: from a .ncu-rep (converted here) or from a CSV already converted on the GPU box
+    (a full capture with source is > 64 MiB, the size gpurun brings back)."""
+    if path.endswith(".csv"):
+        out = open(path, errors="replace").read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
+    i0 = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    return rows[i0:]
+
+
+def traffic(path, key="stored_n1"):
+    """profiles/fused_stage_traffic.json entry: mean dram read + write bytes per launch of the captured fused-stage launches
+    (bench.py's roofline.traffic reads that file)."""
+    import json
+    import os
+    rows = _raw_rows(path)
+    hdr, units = rows[0], rows[1]
+    sc = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    per = [float(r[ir].replace(",", "")) * sc[units[ir]] + float(r[iw].replace(",", "")) * sc[units[iw]] for r in rows[2:]]
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fused_stage_traffic.json")
+    data = json.load(open(out)) if os.path.exists(out) else {}
+    data[key] = {"traffic_bytes_per_launch": sum(per) / len(per), "per_launch": per, "launches": len(per), "source": os.path.basename(path),
+                 "kernels": [r[hdr.index("Kernel Name")][:120] for r in rows[2:]]}
+    json.dump(data, open(out, "w"), indent=1)
+    print(json.dumps(data[key], indent=1))
+
+
+def raw(path):
+    rows = _raw_rows(path)
     hdr, units = rows[0], rows[1]
     print(f"# ncu --set full --clock-control none --import-source on  ({path})")
     for r in rows[2:]:
@@ -71,4 +101,4 @@ def raw(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "raw": raw, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])

@@ -332,13 +332,16 @@ print("HASH", *out)
 
 
 # ------------------------------------------------------------------ config C4 at size ------------------------------
+@pytest.mark.parametrize("fuse_mvp", [False, True])
 @pytest.mark.parametrize("dtype,tol,adj", [(np.float64, 1e-12, 1.0), (np.float32, 1e-5, 64.0)])
-def test_c4_ssp333_jfnk_at_2pow20_dof(cts, dtype, tol, adj):
+def test_c4_ssp333_jfnk_at_2pow20_dof(cts, dtype, tol, adj, fuse_mvp, monkeypatch):
     """BASELINE configs[3] in the exact set-up bench.py times (`run_c4`): SSP333 (SSPRK path) + NewtonsMethod(max_iters = 2,
     KrylovMethod(ForwardDiffJVP, ConstantForcing(1e-2))), nonlinear column diffusion, frozen-coefficient W as left
     preconditioner, smooth state with a 2 % hashed perturbation -- on 2^14 columns x 64 levels = 2^20 DOF instead of 2^27,
     against the numpy oracle (imex_ssprk.jl:95-220, newtons_method.jl:465-509,609-665; GMRES per Krylov.jl v0.10.6).
-    Float64 is bit-exact (one reduction tree on both sides), Float32 within the north-star tolerance."""
+    Float64 is bit-exact (one reduction tree on both sides), Float32 within the north-star tolerance.
+    `fuse_mvp`: the opt-in one-pass JVP + preconditioner solve of every Krylov iteration (cts_column_jvp_precond)."""
+    monkeypatch.setenv("CTS_JVP_PRECOND_FUSION", "1" if fuse_mvp else "0")
     nlev, nx, ny = 64, 128, 128
     K = M.fill_hash(nx * ny, 2, 0, 0.25, 2.0, dtype=dtype)
     T0 = M.fill_hash(nx * ny * nlev, 3, 0, 0.02, 25.0, dtype=dtype)
