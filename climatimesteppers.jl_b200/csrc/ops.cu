@@ -1442,6 +1442,354 @@ __global__ void __launch_bounds__(kPipeThreads, 1) column_fused_stage_pipe_kerne
   }
 }
 
+constexpr int kSpData = 128;  // data threads per lane: kKeep vectors of a 512-vector tile each
+#ifndef CTS_SP_PINGPONG
+#define CTS_SP_PINGPONG true
+#endif
+constexpr int kSpMaxLanes = 3;
+constexpr int kSpHeader = 256;  // mbarriers of all lanes
+
+// ---------------------------------------------------------------------------------------------
+// Software-pipelined, TMA-only variant of the fused stage: one persistent CTA per SM runs `nlanes` independent pipelines
+// ("lanes"), each made of dedicated solver warps and 128 data threads, and EVERY byte of global traffic moves by bulk TMA.
+//
+// Why (all measured on B200, scratch/solve_latency.cu, solve_contention.cu, solve_noise.cu):
+//   * the two-sided product-form Thomas solve of a 16-column tile takes 3400-4000 cycles for a warp that has its SM
+//     sub-partition to itself, 4900 with two solver warps on one sub-partition, 7700 with four;
+//   * next to warps that stream global memory with LDG/STG the same solve takes 10 000 - 180 000 cycles: its LDS/STS queue up
+//     behind the global loads/stores in the sub-partition's memory-instruction path; next to bulk-TMA copies that move the
+//     same bytes (6.6 TB/s) it takes 6200 -- the async proxy does not go through that path.  This is what separates the
+//     fused stage (0.84-0.90 of the copy bandwidth with LDG/STG, ncu: 39 % long-scoreboard + 34 % barrier stalls) from K4
+//     (0.98, TMA only).
+// So: operands (base + NT tendencies) arrive as flat 8 KiB bulk copies in a staging area, W as one 512-byte copy per column
+// into padded tiles; the data threads combine them in shared memory -> registers (K1), write U0 and the K3 residual to shared
+// memory, and after the solve form U and T_imp IN PLACE in shared memory, from where bulk stores take them to HBM.  A lane
+// keeps two tiles in flight: while the solver warp works on tile i the operands of tile i+1 land and are combined, and the
+// operands of tile i+2 are requested.  Solver warps are the CTA's first warps (hardware warp ids of a CTA's warps 0..3 are a
+// rotation of one group of four = one warp per sub-partition).  Waiting is done at hardware named barriers (a warp parked
+// at bar.sync issues nothing); mbarriers are only polled for TMA arrivals that have normally long happened.
+// Same device functions, operation order and roundings as the kernels above: bit-identical results.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct SpShape {
+  static constexpr int kLaneThreads = TileShape<T>::kThreads + kSpData;
+  static constexpr int kMaxThreads = kSpMaxLanes * kLaneThreads;
+};
+
+template <typename T, typename C, int NT, bool MATRIX_FREE, int N1SPEC>
+__global__ void __launch_bounds__(SpShape<T>::kMaxThreads, 1) column_fused_stage_sp_kernel(const FusedArgs<NT> a, int nlanes) {
+  using V = typename Vec<T>::type;
+  constexpr int VN = Vec<T>::N;
+  constexpr int NTS = NT > 0 ? NT : 1;
+  constexpr int kCols = TileShape<T>::kCols;
+  constexpr int kSolvers = TileShape<T>::kThreads;
+  constexpr int kRounds = kKeep;
+  constexpr int kFlat = kRounds * kSpData * 16;  // one flat operand / output tile (8 KiB)
+  extern __shared__ __align__(128) char smem_all[];
+  // role of this thread: solver warps come first (CTA warps 0..nlanes*kSolvers/32-1), then the data threads
+  const bool is_solver = (int)threadIdx.x < nlanes * kSolvers;
+  const int swarp = threadIdx.x >> 5;
+  const int lane_id = is_solver ? swarp % nlanes : ((int)threadIdx.x - nlanes * kSolvers) / kSpData;  // pipeline of this thread
+  const int pitch = a.pitch;
+  const int tile_bytes = kCols * pitch;
+  const int lane_bytes = (MATRIX_FREE ? 2 : 4) * tile_bytes + kFlat + (1 + NT) * kFlat + (MATRIX_FREE ? 3 * kFlat : 0) + 256;
+  char* smem = smem_all + kSpHeader + (size_t)lane_id * lane_bytes;
+  char* sx = smem;                 // residual -> rp -> dx -> T_imp (out)
+  char* sw = smem + tile_bytes;    // stored: dl | d | du tiles; matrix-free: cp scratch
+  char* sU0c = smem + (MATRIX_FREE ? 2 : 4) * tile_bytes;  // U0 -> U (out), flat
+  V* sU0 = reinterpret_cast<V*>(sU0c);
+  char* sOP = sU0c + kFlat;                                 // operand staging: base | terms[0..NT-1], flat
+  char* sWo = sOP + (1 + NT) * kFlat;                       // matrix-free + emit_w: dl | d | du to be written, flat
+  T* sK = reinterpret_cast<T*>(sWo + (MATRIX_FREE ? 3 * kFlat : 0));  // K/dz^2 of the tile's columns, two tiles: [2][kCols]
+  uint64_t* op_full = reinterpret_cast<uint64_t*>(smem_all) + 2 * lane_id;      // operands(i) have landed
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(smem_all) + 2 * lane_id + 1;   // W(i) has landed
+  // hardware named barriers of this lane
+  const int kBarR = 1 + 4 * lane_id;   // residual(i) ready: data arrive, solver sync   (kSolvers + 128 threads)
+  const int kBarS = 2 + 4 * lane_id;   // dx(i) ready:       solver arrive, data sync  (kSolvers + 128 threads)
+  const int kBarD = 3 + 4 * lane_id;   // data threads only (128)
+  const int kBarV = 4 + 4 * lane_id;   // solver warps only (kSolvers), Float32 tiles
+  constexpr int kBarThreads = kSolvers + kSpData;
+  auto bar_arrive = [](int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kBarThreads) : "memory"); };
+  auto bar_sync = [](int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kBarThreads) : "memory"); };
+  auto bar_data = [](int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kSpData) : "memory"); };
+
+  const int nlev = a.nlev;
+  const int col_bytes = nlev * (int)sizeof(T);
+  const int cpc = col_bytes / 16;
+  const int cshift = 31 - __clz(cpc);
+  const size_t ntiles = (a.ncols + kCols - 1) / kCols;
+  const size_t first = (size_t)blockIdx.x * nlanes + lane_id, stride = (size_t)gridDim.x * nlanes;
+  const int count = ntiles > first ? (int)((ntiles - first + stride - 1) / stride) : 0;
+  auto tile_of = [&](int i, size_t& col0, int& nvalid) {
+    const size_t tile = first + (size_t)i * stride;
+    col0 = tile * kCols;
+    nvalid = (int)((a.ncols - col0) < (size_t)kCols ? (a.ncols - col0) : (size_t)kCols);
+  };
+  // optional wait-time profile (CTS_FUSED_TIMELINE): the first solver thread and the first data thread of lane 0
+  long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool prof = a.dbg != nullptr && (threadIdx.x == 0 || (int)threadIdx.x == nlanes * kSolvers);
+  const long long t_begin = prof ? clock64() : 0;
+  auto wait_mbar = [&](uint64_t* bar, uint32_t parity, int tag) {  // (all lanes of a warp take the same path)
+    const long long t0 = a.dbg ? clock64() : 0;
+    mbar_wait_wd(bar, parity, tag);
+    if (prof) acc[tag] += clock64() - t0;
+  };
+  auto wait_bar = [&](int id, int tag) {
+    const long long t0 = a.dbg ? clock64() : 0;
+    bar_sync(id);
+    if (prof) acc[tag] += clock64() - t0;
+  };
+  if (threadIdx.x == 0) {
+    for (int l = 0; l < 2 * nlanes; ++l) mbar_init(reinterpret_cast<uint64_t*>(smem_all) + l, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (is_solver) {
+    // ------------------------------------------------------------------ solver warps -----------------------------
+    const int lane = threadIdx.x & 31, warp = swarp / nlanes;  // warp = 16-column job of this lane's tile
+    const int col = warp * 16 + lane_column(lane);
+    const bool is_up = lane_is_up(lane);
+    const int col_off = col * pitch;
+    auto issue_w = [&](int i) {  // job 0: W(i) -> sw, one 1-D bulk copy per column and diagonal
+      size_t col0;
+      int nvalid;
+      tile_of(i, col0, nvalid);
+      const size_t goff = col0 * (size_t)nlev;
+      if (lane == 0) mbar_arrive_expect_tx(w_full, (uint32_t)(3 * nvalid * col_bytes));
+      __syncwarp();
+      for (int c = lane; c < nvalid; c += 32) {
+        const size_t g = goff + (size_t)c * nlev;
+        bulk_g2s(sw + c * pitch, (const T*)a.dl + g, col_bytes, w_full);
+        bulk_g2s(sw + tile_bytes + c * pitch, (const T*)a.d + g, col_bytes, w_full);
+        bulk_g2s(sw + 2 * tile_bytes + c * pitch, (const T*)a.du + g, col_bytes, w_full);
+      }
+    };
+    if (!MATRIX_FREE && warp == 0 && count > 0) issue_w(0);
+    for (int i = 0; i < count; ++i) {
+      size_t col0;
+      int nvalid;
+      tile_of(i, col0, nvalid);
+      const bool valid = col < nvalid;
+      wait_bar(kBarR, 1);
+      if (MATRIX_FREE) {
+        const T ac = valid ? sK[(i & 1) * kCols + col] : T(0);
+        const double o = __dmul_rn(a.dtg, (double)ac);
+        ConstRows<T> rows{(T)o, (T)__dsub_rn(__dmul_rn(-2.0, o), 1.0), sw};
+        const long long ts = a.dbg ? clock64() : 0;
+        babe_solve_lanepair<T, ConstRows<T>, RhsFromTile<T>, CTS_SP_PINGPONG>(rows, RhsFromTile<T>{}, sx, col_off, nlev, is_up, valid);
+        if (prof) acc[4] += clock64() - ts;
+        bar_arrive(kBarS);
+      } else {
+        wait_mbar(w_full, i & 1, 2);
+        StoredRows<T> rows{sw, sw + tile_bytes, sw + 2 * tile_bytes};
+        const long long ts = a.dbg ? clock64() : 0;
+        babe_solve_lanepair<T, StoredRows<T>, RhsFromTile<T>, CTS_SP_PINGPONG>(rows, RhsFromTile<T>{}, sx, col_off, nlev, is_up, valid);
+        if (prof) acc[4] += clock64() - ts;
+        fence_proxy_async_smem();  // the factors overwrote dl/du in place; the next writer of these bytes is a bulk copy
+        bar_arrive(kBarS);
+        if (i + 1 < count) {
+          if (kSolvers > 32)
+            asm volatile("bar.sync %0, %1;" ::"r"(kBarV), "n"(kSolvers) : "memory");  // every solver warp of the lane is done with W(i)
+          else
+            __syncwarp();
+          if (warp == 0) issue_w(i + 1);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ data threads -----------------------------
+    const int dt = ((int)threadIdx.x - nlanes * kSolvers) % kSpData;
+    const DivConst dc = div_const_prepare(a.dtg);
+    const bool emit = MATRIX_FREE && a.emit_w;
+    V U0r[kRounds];
+    auto issue_ops = [&](int i) {  // one thread: base + terms of tile i -> sOP, one flat bulk copy each
+      size_t col0;
+      int nvalid;
+      tile_of(i, col0, nvalid);
+      const size_t goff = col0 * (size_t)nlev;
+      const uint32_t flat = (uint32_t)(nvalid * col_bytes);
+      mbar_arrive_expect_tx(op_full, (uint32_t)(1 + NT) * flat);
+      bulk_g2s(sOP, (const T*)a.ax.base + goff, flat, op_full);
+#pragma unroll
+      for (int k = 0; k < NT; ++k) bulk_g2s(sOP + (k + 1) * kFlat, (const T*)a.ax.terms[k] + goff, flat, op_full);
+    };
+    auto fetch_K = [&](int i) {  // K/dz^2 of tile i's columns -> sK[i & 1] (one scalar load per column)
+      size_t col0;
+      int nvalid;
+      tile_of(i, col0, nvalid);
+      if (dt < nvalid) sK[(i & 1) * kCols + dt] = ((const T*)a.Kcol)[col0 + dt];
+    };
+    auto combine = [&](int i) {  // U0(i) = K1(base, terms): staging -> registers
+      size_t col0;
+      int nvalid;
+      tile_of(i, col0, nvalid);
+      const int total = nvalid * cpc;
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        const int q = dt + r * kSpData;
+        V vb = V{}, vt[NTS];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) vt[t] = V{};
+        if (q < total) {
+          vb = reinterpret_cast<const V*>(sOP)[q];
+#pragma unroll
+          for (int t = 0; t < NT; ++t) vt[t] = reinterpret_cast<const V*>(sOP + (t + 1) * kFlat)[q];
+        }
+        T eb[VN], uu[VN], et[NTS][VN];
+        vec_unpack<T>(vb, eb);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) vec_unpack<T>(vt[t], et[t]);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+          T x[NTS];
+#pragma unroll
+          for (int t = 0; t < NT; ++t) x[t] = et[t][e];
+          constexpr int N1 = GroupSplit<NT, N1SPEC>::value;
+          if constexpr (N1 >= 0)
+            uu[e] = axpy_combine_n1<T, C, NT, (N1 >= 0 ? N1 : 0)>(eb[e], x, a.ax);
+          else
+            uu[e] = axpy_combine<T, C, NT>(eb[e], x, a.ax);
+        }
+        U0r[r] = vec_pack<T>(uu);
+      }
+    };
+    if (count > 0) {
+      if (dt == 0) issue_ops(0);
+      fetch_K(0);
+      wait_mbar(op_full, 0, 4);
+      combine(0);
+      bar_data(kBarD);  // every data thread has read the staging area (and sK[0] is visible)
+      if (dt == 0 && count > 1) issue_ops(1);
+    }
+    for (int i = 0; i < count; ++i) {
+      size_t col0;
+      int nvalid;
+      tile_of(i, col0, nvalid);
+      const int total = nvalid * cpc;
+      const size_t goff = col0 * (size_t)nlev;
+      const size_t gvec0 = goff * sizeof(T) / 16;
+      // U0(i) and the K3 residual f = (U0 + dtγ T_imp(U0)) - U0 (level neighbours by warp shuffles) -> shared memory
+      const long long tr = a.dbg ? clock64() : 0;
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        const int q = dt + r * kSpData;
+        const bool ok = q < total;
+        const int col = q >> cshift, kk = q & (cpc - 1);
+        const T acol = ok ? sK[(i & 1) * kCols + col] : T(0);
+        T uu[VN], rr[VN];
+        vec_unpack<T>(U0r[r], uu);
+        T below = __shfl_up_sync(0xffffffffu, uu[VN - 1], 1, cpc);
+        T above = __shfl_down_sync(0xffffffffu, uu[0], 1, cpc);
+        if (kk == 0) below = T(0);
+        if (kk == cpc - 1) above = T(0);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+          const T um = e > 0 ? uu[e > 0 ? e - 1 : 0] : below;
+          const T up = e + 1 < VN ? uu[e + 1 < VN ? e + 1 : e] : above;
+          const T ti = timp_linear<T>(acol, um, uu[e], up);
+          rr[e] = (T)__dsub_rn(__dadd_rn((double)uu[e], __dmul_rn(a.dtg, (double)ti)), (double)uu[e]);
+        }
+        if (ok) {
+          sU0[q] = U0r[r];
+          *reinterpret_cast<V*>(sx + col * pitch + kk * 16) = vec_pack<T>(rr);
+          if (a.temp) reinterpret_cast<V*>(a.temp)[gvec0 + q] = U0r[r];
+          if (emit) {  // W = dtγJ - I of the stored copy (same expressions as column_wfact_kernel), staged for a bulk store
+            const double o = __dmul_rn(a.dtg, (double)acol);
+            T eo[VN], ed[VN];
+#pragma unroll
+            for (int e = 0; e < VN; ++e) {
+              eo[e] = (T)o;
+              ed[e] = (T)__dsub_rn(__dmul_rn(-2.0, o), 1.0);
+            }
+            const V vo = vec_pack<T>(eo);
+            reinterpret_cast<V*>(sWo)[q] = vo;
+            reinterpret_cast<V*>(sWo + kFlat)[q] = vec_pack<T>(ed);
+            reinterpret_cast<V*>(sWo + 2 * kFlat)[q] = vo;
+          }
+        }
+      }
+      bar_arrive(kBarR);
+      if (prof) acc[1] += clock64() - tr;
+      if (i + 1 < count) {  // while the solver works on tile i: the operands of tile i+1 (long landed) -> U0(i+1) in registers
+        const long long t0 = a.dbg ? clock64() : 0;
+        fetch_K(i + 1);
+        wait_mbar(op_full, (i + 1) & 1, 4);
+        combine(i + 1);
+        bar_data(kBarD);
+        if (dt == 0 && i + 2 < count) issue_ops(i + 2);
+        if (prof) acc[5] += clock64() - t0;
+      }
+      wait_bar(kBarS, 3);
+      const long long te = a.dbg ? clock64() : 0;
+      // epilogue in place: sU0 <- U = U0 - dx ; sx <- T_imp = (U - U0)/dtγ
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        const int q = dt + r * kSpData;
+        if (q >= total) continue;
+        const int col = q >> cshift, kk = q & (cpc - 1);
+        V* px = reinterpret_cast<V*>(sx + col * pitch + kk * 16);
+        T e0[VN], ex[VN], eU[VN], eT[VN];
+        vec_unpack<T>(sU0[q], e0);
+        vec_unpack<T>(*px, ex);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+          eU[e] = rsub(e0[e], ex[e]);
+          eT[e] = (T)div_const((double)rsub(eU[e], e0[e]), dc);
+        }
+        sU0[q] = vec_pack<T>(eU);
+        *px = vec_pack<T>(eT);
+      }
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk stores
+      bar_data(kBarD);
+      if (prof) acc[2] += clock64() - te;
+      {
+        const long long t0 = a.dbg ? clock64() : 0;
+        const uint32_t flat = (uint32_t)(nvalid * col_bytes);
+        bool issued = false;
+        if (dt == 0) {
+          bulk_s2g((T*)a.U + goff, sU0c, flat);
+          if (emit) {
+            bulk_s2g((T*)const_cast<void*>(a.dl) + goff, sWo, flat);
+            bulk_s2g((T*)const_cast<void*>(a.d) + goff, sWo + kFlat, flat);
+            bulk_s2g((T*)const_cast<void*>(a.du) + goff, sWo + 2 * kFlat, flat);
+          }
+          issued = true;
+        }
+        if (a.Timp && dt < nvalid) {
+          bulk_s2g((T*)a.Timp + goff + (size_t)dt * nlev, sx + dt * pitch, col_bytes);
+          issued = true;
+        }
+        if (issued) {
+          bulk_commit();
+          bulk_wait_read0();  // the stores have read shared memory: sU0 / sx / sWo may be rewritten
+        }
+        bar_data(kBarD);
+        if (prof) acc[6] += clock64() - t0;
+      }
+    }
+  }
+  if (prof) {
+    acc[0] = clock64() - t_begin;
+    unsigned hw;
+    asm("mov.u32 %0, %%warpid;" : "=r"(hw));
+    acc[7] = (long long)(hw % 4);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a.dbg[((size_t)blockIdx.x * 2 + (threadIdx.x == 0 ? 0 : 1)) * 8 + j] = acc[j];
+  }
+}
+
+// lanes of the TMA-only kernel that fit one SM for this launch (0: none)
+static int sp_lanes(int nt, int tile_bytes, bool mf, size_t* smem_out) {
+  const size_t flat = (size_t)kKeep * kSpData * 16;
+  const size_t lane = (size_t)(mf ? 2 : 4) * tile_bytes + flat + (size_t)(1 + nt) * flat + (mf ? 3 * flat : 0) + 256;
+  int lanes = (int)std::min<size_t>(kSpMaxLanes, ((size_t)227 * 1024 - kSpHeader) / lane);
+  static const int env_lanes = getenv("CTS_SP_LANES") ? atoi(getenv("CTS_SP_LANES")) : 0;  // developer aid
+  if (env_lanes > 0) lanes = std::min(lanes, env_lanes);
+  *smem_out = kSpHeader + (size_t)lanes * lane;
+  return lanes;
+}
+
 // ring depths of the pipelined kernel for this launch (n_op == 0: does not fit).  CTS_PIPE_OP / CTS_PIPE_X / CTS_PIPE_TEAMS
 // override the defaults (developer aid for tuning).
 static PipeCfg pipe_config(int nt, int tile_bytes, bool mf, int jobs) {
@@ -1579,6 +1927,72 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
       }
       return CTS_OK;
     }
+  }
+  }
+  const bool no_pipe_on = !no_pipe && (cpc == 16 || cpc == 32);  // (the opt-in ring-pipelined kernel above took the launch)
+  // software-pipelined TMA-only kernel (one persistent CTA per SM, lanes of solver warps + data threads): opt-in
+  // (CTS_FUSED_SP=1) -- bit-identical, 5.7-5.9 ms of fused stages per step against 4.9-5.1 ms for the register kernel below
+  static const bool no_sp = getenv("CTS_FUSED_SP") == nullptr || getenv("CTS_FUSED_SP")[0] == '0';
+  if constexpr (NT <= 5) {
+  size_t sp_probe = 0;
+  if (!no_reg && !no_sp && !no_pipe_on && cpc >= 1 && cpc * kCols == kKeep * kSpData && (cpc & (cpc - 1)) == 0 &&
+      sp_lanes(NT, kCols * a.pitch, mf, &sp_probe) >= 1) {
+    const size_t sp_tiles = (op->ncols + kCols - 1) / kCols;
+    size_t smem_sp = 0;
+    const int sp_nl = sp_lanes(NT, kCols * a.pitch, mf, &smem_sp);
+    a.dbg = nullptr;
+    unsigned sp_grid = 0;
+    auto launch_sp = [&](auto k) -> int {
+      CTS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sp));
+      const unsigned grid = (unsigned)std::min<size_t>((sp_tiles + sp_nl - 1) / sp_nl, (size_t)ctx->num_sms);
+      sp_grid = grid;
+      if (timeline) {
+        CTS_CUDA(ctx, cudaMalloc(&a.dbg, (size_t)grid * 16 * sizeof(long long)));
+        CTS_CUDA(ctx, cudaMemsetAsync(a.dbg, 0, (size_t)grid * 16 * sizeof(long long), ctx->stream));
+      }
+      k<<<grid, sp_nl * SpShape<T>::kLaneThreads, smem_sp, ctx->stream>>>(a, sp_nl);
+      return CTS_OK;
+    };
+    int spec = 0;
+    if constexpr (NT >= 1) {
+      if (a.ax.n1 == NT)
+        spec = 1;
+      else if (a.ax.n1 == (NT + 1) / 2)
+        spec = 2;
+    }
+    if (spec == 1) {
+      if (mf) CTS_TRY(launch_sp(column_fused_stage_sp_kernel<T, C, NT, true, 1>));
+      else CTS_TRY(launch_sp(column_fused_stage_sp_kernel<T, C, NT, false, 1>));
+    } else if (spec == 2) {
+      if (mf) CTS_TRY(launch_sp(column_fused_stage_sp_kernel<T, C, NT, true, 2>));
+      else CTS_TRY(launch_sp(column_fused_stage_sp_kernel<T, C, NT, false, 2>));
+    } else {
+      if (mf) CTS_TRY(launch_sp(column_fused_stage_sp_kernel<T, C, NT, true, 0>));
+      else CTS_TRY(launch_sp(column_fused_stage_sp_kernel<T, C, NT, false, 0>));
+    }
+    CTS_LAUNCH_CHECK(ctx);
+    if (timeline) {
+      std::vector<long long> h((size_t)sp_grid * 16);
+      cudaStreamSynchronize(ctx->stream);
+      cudaMemcpy(h.data(), a.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      cudaFree(a.dbg);
+      static const char* roles[2] = {"solver", "data"};
+      static const char* tags0[8] = {"total", "wait residual", "wait w_full", "-", "SOLVE", "-", "-", "-"};
+      static const char* tags1[8] = {"total", "residual->smem", "epilogue+fence+sync", "wait solved", "wait op_full", "prefetch+combine(i+1)", "store+wait_read", "-"};
+      fprintf(stderr, "[cts sp timeline] NT=%d mf=%d tiles=%zu grid=%u lanes=%d smem=%zu\n", NT, (int)mf, sp_tiles, sp_grid, sp_nl, smem_sp);
+      for (int r = 0; r < 2; ++r) {
+        double sum[8] = {0};
+        for (unsigned bk = 0; bk < sp_grid; ++bk)
+          for (int j = 0; j < 8; ++j) sum[j] += (double)h[((size_t)bk * 2 + r) * 8 + j];
+        fprintf(stderr, "  %-7s total %.0f cycles/CTA (%.0f per tile of a lane);", roles[r], sum[0] / sp_grid, sum[0] / sp_grid / ((double)sp_tiles / sp_grid / sp_nl));
+        for (int j = 1; j < 7; ++j)
+          if (sum[j] > 0) fprintf(stderr, " %s %.1f%%", (r == 0 ? tags0 : tags1)[j], 100.0 * sum[j] / sum[0]);
+        int hist[4] = {0, 0, 0, 0};
+        for (unsigned bk = 0; bk < sp_grid; ++bk) hist[h[((size_t)bk * 2 + r) * 8 + 7] & 3]++;
+        fprintf(stderr, "  [hw warpid %% 4 of the reporting warp: %d %d %d %d]\n", hist[0], hist[1], hist[2], hist[3]);
+      }
+    }
+    return CTS_OK;
   }
   }
   if (!timeline && !no_reg && cpc >= 1 && cpc * kCols <= kKeep * kFusedThreads && (cpc & (cpc - 1)) == 0) {

@@ -292,8 +292,9 @@ def test_foreign_hooks_generic_path_bit_exact(cts, dtype, halo):
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
 def test_pipelined_fused_stage_kernel_is_bit_identical(dtype):
     """`CTS_FUSED_PIPE=1` selects the persistent, warp-specialised variant of the fused column stage (operand / W / x
-    rings over mbarriers, csrc/ops.cu).  Same device functions, same roundings: two ARS343 steps on several waves of tiles
-    (stored W with the Wfact-emitting first stage, and matrix-free) must equal the default kernel's result bit for bit."""
+    rings over mbarriers) and `CTS_FUSED_SP=1` the software-pipelined TMA-only variant (lanes of solver warps + data threads,
+    hardware named barriers), csrc/ops.cu.  Same device functions, same roundings: two ARS343 steps on several waves of
+    tiles (stored W with the Wfact-emitting first stage, and matrix-free) must equal the default kernel's result bit for bit."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -323,12 +324,12 @@ for mf in (False, True):
 print("HASH", *out)
 """ % (root, dtype)
     hashes = {}
-    for pipe in ("0", "1"):
-        env = dict(os.environ, CTS_FUSED_PIPE=pipe)
+    for name, extra in (("default", {}), ("pipe", {"CTS_FUSED_PIPE": "1"}), ("sp", {"CTS_FUSED_SP": "1"})):
+        env = dict(os.environ, **extra)
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
-        hashes[pipe] = [ln for ln in r.stdout.splitlines() if ln.startswith("HASH")][-1]
-    assert hashes["0"] == hashes["1"]
+        hashes[name] = [ln for ln in r.stdout.splitlines() if ln.startswith("HASH")][-1]
+    assert hashes["default"] == hashes["pipe"] == hashes["sp"]
 
 
 # ------------------------------------------------------------------ config C4 at size ------------------------------
