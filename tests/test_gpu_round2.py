@@ -384,3 +384,38 @@ def test_release_after_context_destroy_is_safe(cts):
     assert lib.cts_ctx_destroy(ctx) == 0
     assert lib.cts_free(ctx, p) == 0          # plain cudaFree, no use of the dead context
     assert lib.cts_ctx_destroy(ctx) != 0      # double destroy is refused, not a double free
+
+
+# ------------------------------------------------------------------ integrator steps with the other Krylov options --------
+@pytest.mark.parametrize("step_kind", [1, 2, 3])
+@pytest.mark.parametrize("forcing", ["constant", "eisenstat_walker"])
+def test_imex_steps_with_eisenstat_walker_and_step_sizes(cts, step_kind, forcing):
+    """SSP333 + NewtonsMethod(max_iters = 3) + KrylovMethod on the nonlinear column operator, stepped on the device and by the
+    oracle with `EisenstatWalkerForcing` (newtons_method.jl:248-280) and `ForwardDiffStepSize1/2/3` (:107-135): same Krylov
+    iteration counts, Float64 results bit for bit (the forcing term only consumes norms of the shared reduction tree)."""
+    nlev, nx, ny = 16, 6, 5
+    dtype = np.float64
+    K = M.fill_hash(nx * ny, 2, 0, 0.25, 2.0, dtype=dtype)
+    T0 = M.fill_hash(nx * ny * nlev, 3, 0, 0.05, 2.0, dtype=dtype)
+    model = M.ColumnModel(nlev, nx, ny, K, S_lev=None, nu=0.0, halo=0, nonlinear=True)
+    f_o = R.EisenstatWalkerForcing() if forcing == "eisenstat_walker" else R.ConstantForcing(1e-4)
+    f_c = cts.EisenstatWalkerForcing() if forcing == "eisenstat_walker" else cts.ConstantForcing(1e-4)
+    step_c = {1: cts.ForwardDiffStepSize1, 2: cts.ForwardDiffStepSize2, 3: cts.ForwardDiffStepSize3}[step_kind]()
+    km_o = R.KrylovMethod(jacobian_free_jvp=R.ForwardDiffJVP(default_step=step_kind), forcing_term=f_o)
+    km_c = cts.KrylovMethod(jacobian_free_jvp=cts.ForwardDiffJVP(default_step=step_c), forcing_term=f_c)
+    uo = T0.copy()
+    cache_o, step_o = R.make_stepper(model.ode_function(explicit=False),
+                                     R.imex_algorithm("SSP333", R.NewtonsMethod(max_iters=3, krylov_method=km_o), None), uo)
+    op = cts.ColumnOperator(nlev, nx, ny, cts.B200Vector.from_host(K), nu=0.0, halo=0, nonlinear=True)
+    u = cts.B200Vector.from_host(T0)
+    integ = cts.init(cts.ODEProblem(op.ode_function(explicit=False), u, (0.0, 1e9), None),
+                     cts.IMEXAlgorithm(cts.SSP333(), cts.NewtonsMethod(max_iters=3, krylov_method=km_c)), dt=5e-3, save=False)
+    t = 0.0
+    for _ in range(3):
+        step_o(uo, None, t, 5e-3)
+        cts.step_(integ)
+        t += 5e-3
+    got = u.to_host()
+    assert np.isfinite(got).all()
+    assert integ.cache.stats()["krylov_iters"] == sum(s["niter"] for s in cache_o["nm_cache"]["stats"]) > 0
+    np.testing.assert_array_equal(got, uo)
