@@ -13,6 +13,7 @@
 #include "cts_internal.h"
 #include "ew_device.cuh"
 #include "tile_device.cuh"
+#include "fused_args.cuh"
 
 using namespace cts_tile;
 using cts_ew::AxpyArgs;
@@ -23,6 +24,9 @@ using cts_ew::vec_pack;
 using cts_ew::vec_unpack;
 using cts_ew::op_add;
 using cts_ew::op_mul;
+using cts_fused::FusedArgs;
+using cts_fused::GroupSplit;
+using cts_fused::timp_linear;
 
 // =============================================================================================
 // 1-D periodic upwind advection (config C2)
@@ -238,11 +242,6 @@ namespace {
 template <typename T>
 __device__ __forceinline__ T col_a(T K, T dz) {
   return rdiv(K, rmul(dz, dz));
-}
-// linear operator row: a*((um - 2 uc) + up)
-template <typename T>
-__device__ __forceinline__ T timp_linear(T a, T um, T uc, T up) {
-  return rmul(a, radd(rsub(um, rmul(T(2), uc)), up));
 }
 // nonlinear face diffusivity a*(1 + ubar^2), ubar = (ua+ub)/2
 template <typename T>
@@ -641,24 +640,6 @@ __global__ void __launch_bounds__(256) column_final_update_kernel(const FinalArg
 // One CTA per 32-column tile; U0 is assembled straight from global memory with 128-bit loads into a
 // padded shared tile, the elimination runs out of shared memory, U / T_imp leave with 128-bit stores.
 // ---------------------------------------------------------------------------------------------
-template <int NT>
-struct FusedArgs {
-  AxpyArgs<NT> ax;   // base/terms/coef (out/out2 unused)
-  void* U;
-  void* Timp;
-  void* temp;
-  const void* Kcol;
-  const void* dl;
-  const void* d;
-  const void* du;
-  double dtg;
-  double dz;
-  int nlev;
-  size_t ncols;
-  int pitch;
-  int emit_w;      // matrix-free launch that also writes W = dtγJ - I into dl/d/du (replaces a separate Wfact pass)
-  long long* dbg;  // optional phase timeline (CTS_FUSED_TIMELINE=1): 5 clock64 stamps per CTA
-};
 
 #ifndef CTS_FUSED_THREADS
 #define CTS_FUSED_THREADS 128
@@ -858,10 +839,6 @@ constexpr int kKeep = (CTS_FUSED_TILE_COLS * 32 + kFusedThreads - 1) / kFusedThr
 // N1SPEC: how the kernel learns the split of the NT operands into the explicit group (first n1) and the implicit group:
 // 0 = from the arguments at run time, 1 = all in group 1 (n1 == NT), 2 = n1 == ceil(NT/2) (stage i of an IMEX-ARK tableau
 // with dense lower triangles: i-1 explicit and i-2 implicit tendencies).  A compile-time split needs no selects.
-template <int NT, int N1SPEC>
-struct GroupSplit {
-  static constexpr int value = N1SPEC == 1 ? NT : (N1SPEC == 2 ? (NT + 1) / 2 : -1);
-};
 
 template <typename T, typename C, int NT, bool MATRIX_FREE, int N1SPEC>
 __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) column_fused_stage_reg_kernel(const FusedArgs<NT> a) {
@@ -1865,6 +1842,21 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
   static const bool no_reg = getenv("CTS_FUSED_NO_REG") != nullptr;      // developer aid: force the 5-tile kernel
   const int cpc = op->d.nlev * (int)sizeof(T) / 16;
   constexpr int kCols = TileShape<T>::kCols;
+  // cluster variant (loader CTA + solver CTA on two SMs, fused_cluster.cu): Float64, 64-level columns; opt-in
+  static const bool use_cluster = getenv("CTS_FUSED_CLUSTER") != nullptr && getenv("CTS_FUSED_CLUSTER")[0] == '1';
+  if constexpr (std::is_same<T, double>::value && std::is_same<C, double>::value) {
+    if (use_cluster && !no_reg && cpc == 32) {
+      int cspec = 0;
+      if constexpr (NT >= 1) {
+        if (a.ax.n1 == NT)
+          cspec = 1;
+        else if (a.ax.n1 == (NT + 1) / 2)
+          cspec = 2;
+      }
+      const int rc = cts_fused_cluster_f64(ctx, NT, cspec, mf, &a, timeline);
+      if (rc != CTS_EUNSUPPORTED) return rc;
+    }
+  }
   // pipelined persistent kernel: a tile is 512 vectors, a column 8..32 of them (a power of two)
   // The pipelined kernel is opt-in (CTS_FUSED_PIPE=1): bit-identical, but measured slower on B200
   static const bool no_pipe = getenv("CTS_FUSED_PIPE") == nullptr || getenv("CTS_FUSED_PIPE")[0] == '0';

@@ -324,12 +324,13 @@ for mf in (False, True):
 print("HASH", *out)
 """ % (root, dtype)
     hashes = {}
-    for name, extra in (("default", {}), ("pipe", {"CTS_FUSED_PIPE": "1"}), ("sp", {"CTS_FUSED_SP": "1"})):
+    for name, extra in (("default", {}), ("pipe", {"CTS_FUSED_PIPE": "1"}), ("sp", {"CTS_FUSED_SP": "1"}),
+                        ("cluster", {"CTS_FUSED_CLUSTER": "1"})):
         env = dict(os.environ, **extra)
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         hashes[name] = [ln for ln in r.stdout.splitlines() if ln.startswith("HASH")][-1]
-    assert hashes["default"] == hashes["pipe"] == hashes["sp"]
+    assert hashes["default"] == hashes["pipe"] == hashes["sp"] == hashes["cluster"]
 
 
 # ------------------------------------------------------------------ config C4 at size ------------------------------
