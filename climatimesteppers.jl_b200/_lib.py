@@ -112,6 +112,8 @@ SIGNATURES = [
     ("cts_last_error", C.c_char_p, [_P]),
     ("cts_ctx_stream", _P, [_P]),
     ("cts_launch_count", _I, [_P, C.POINTER(_U64)]),
+    ("cts_nvtx_range_push", _I, [C.c_char_p]),
+    ("cts_nvtx_range_pop", _I, []),
     ("cts_prof_enable", _I, [_P, _I]),
     ("cts_prof_read", _I, [_P, c_double_p, C.POINTER(_U64)]),
     ("cts_alloc", _I, [_P, _SZ, c_void_pp]),

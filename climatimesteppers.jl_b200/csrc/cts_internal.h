@@ -1,6 +1,7 @@
 // Internal declarations shared by the translation units of libcts_sm100a.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdint>
 #include <cstdio>
@@ -53,6 +54,16 @@ struct cts_ctx {
 };
 
 // RAII bracket: records a start/stop event pair on the context's stream around a kernel family.
+// NVTX ranges with the reference's names (`NVTX.@annotate` on solve!, step_u!, solve_newton!, solve_krylov!:
+// integrators.jl:345,442, newtons_method.jl:465,609).  nvtx3 is header-only: without a profiler attached a range is one
+// load and a predictable branch.
+struct cts_nvtx_scope {
+  explicit cts_nvtx_scope(const char* name) { nvtxRangePushA(name); }
+  ~cts_nvtx_scope() { nvtxRangePop(); }
+  cts_nvtx_scope(const cts_nvtx_scope&) = delete;
+  cts_nvtx_scope& operator=(const cts_nvtx_scope&) = delete;
+};
+
 struct cts_prof_scope {
   cts_ctx* ctx;
   int idx = -1;

@@ -115,6 +115,17 @@ int cts_launch_count(cts_ctx* ctx, uint64_t* out) {
   return CTS_OK;
 }
 
+int cts_nvtx_range_push(const char* name) {
+  if (!name) return CTS_EINVAL;
+  nvtxRangePushA(name);
+  return CTS_OK;
+}
+
+int cts_nvtx_range_pop(void) {
+  nvtxRangePop();
+  return CTS_OK;
+}
+
 int cts_bytes_count(cts_ctx* ctx, uint64_t* out) {
   CTS_CHECK_CTX(ctx);
   if (!out) return CTS_EINVAL;

@@ -352,6 +352,7 @@ int gmres(cts_newton_cache* c, const std::function<int(void* out, const void* v)
 // solve_krylov! (newtons_method.jl:465-509)
 int solve_krylov(cts_newton_cache* c, void* dx, const void* x, const ResidualFn& f_, const void* f, int n_iter,
                  const PrepareFn* prepare) {
+  cts_nvtx_scope nvtx("solve_krylov!");  // newtons_method.jl:465
   cts_ctx* ctx = c->ctx;
   const bool jfree = c->cfg.jacobian_free_jvp != 0;
   c->xstat_valid = false;  // x is fixed for the whole GMRES solve; with the reference pass structure recompute per JVP
@@ -533,6 +534,7 @@ int line_search(cts_newton_cache* c, void* x, const ResidualFn& f_, const Prepar
 }
 
 int solve_newton(cts_newton_cache* c, void* x, const ResidualFn& f_, const JacFn* j_, const PrepareFn* prepare) {
+  cts_nvtx_scope nvtx("solve_newton!");  // newtons_method.jl:609
   cts_ctx* ctx = c->ctx;
   const cts_newton_config& cfg = c->cfg;
   const bool has_j = c->W != nullptr && j_ != nullptr;
@@ -1512,6 +1514,7 @@ static int graphed_ark_step(cts_imex_cache* c, void* u, double t, double dt) {
 
 int cts_imex_step(cts_imex_cache* c, void* u, double t, double dt, int dt_is_f32) {
   if (!c || !u) return CTS_EINVAL;
+  cts_nvtx_scope nvtx("step_u!");  // integrators.jl:442
   c->dt_f32 = dt_is_f32 != 0;
   if (c->constraint == 0) {
     if (graph_capturable(c, u)) {
@@ -1648,6 +1651,7 @@ int cts_lsrk_cache_destroy(cts_lsrk_cache* c) {
 
 int cts_lsrk_step(cts_lsrk_cache* c, void* u, double t, double dt, int dt_is_f32) {
   if (!c || !u) return CTS_EINVAL;
+  cts_nvtx_scope nvtx("step_u!");  // integrators.jl:442
   cts_ctx* ctx = c->ctx;
   const bool f32 = c->ft == CTS_F32;
   const int native = (f32 && dt_is_f32) ? 1 : 0;
@@ -1827,6 +1831,7 @@ int cts_rosenbrock_cache_stats(cts_rosenbrock_cache* c, cts_solver_stats* out) {
 // zero are not read (the reference multiplies them by zero).
 int cts_rosenbrock_step(cts_rosenbrock_cache* c, void* u, double t, double dt) {
   if (!c || !u) return CTS_EINVAL;
+  cts_nvtx_scope nvtx("step_u!");  // integrators.jl:442
   cts_ctx* ctx = c->ctx;
   const cts_rosenbrock_tableau& tab = c->tab;
   const cts_ode_function& f = c->f;

@@ -215,12 +215,25 @@ def __step_(integrator):
 
 
 def solve_(integrator):
-    """``solve!`` (integrators.jl:345-351)."""
-    while (not integrator.tstops.isempty()) and integrator.step != integrator.stepstop:
-        __step_(integrator)
-    for cb in integrator.callback.discrete_callbacks:
-        cb.finalize(cb, integrator.u, integrator.t, integrator)
+    """``solve!`` (integrators.jl:345-351; `NVTX.@annotate`d there, so the range is opened here as well)."""
+    lib = _nvtx_lib(integrator)
+    if lib is not None:
+        lib.cts_nvtx_range_push(b"solve!")
+    try:
+        while (not integrator.tstops.isempty()) and integrator.step != integrator.stepstop:
+            __step_(integrator)
+        for cb in integrator.callback.discrete_callbacks:
+            cb.finalize(cb, integrator.u, integrator.t, integrator)
+    finally:
+        if lib is not None:
+            lib.cts_nvtx_range_pop()
     return integrator.sol
+
+
+def _nvtx_lib(integrator):
+    """The C-ABI library behind a device state (None for the host-only integrators of the CPU tests)."""
+    ctx = getattr(integrator.u, "ctx", None)
+    return getattr(ctx, "lib", None)
 
 
 def solve(prob, alg, **kwargs):

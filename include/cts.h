@@ -63,6 +63,11 @@ int cts_launch_count(cts_ctx* ctx, uint64_t* out);
  * sizeof(FT) per pass, the per-kernel figures of the design document -- the numerator of bench.py's achieved GB/s for
  * workloads whose pass count is data dependent (Newton-Krylov) */
 int cts_bytes_count(cts_ctx* ctx, uint64_t* out);
+/* NVTX ranges for the host side of the reference's annotated functions (`NVTX.@annotate function solve!`,
+ * integrators.jl:345; the library itself opens "step_u!" (integrators.jl:442), "solve_newton!" (newtons_method.jl:609) and
+ * "solve_krylov!" (newtons_method.jl:465) around its own entry points).  No-ops unless a profiler is attached. */
+int cts_nvtx_range_push(const char* name);
+int cts_nvtx_range_pop(void);
 /* `zero(u0)` in init_cache (imex_ark.jl:44-48): zero-filled device allocation */
 int cts_alloc(cts_ctx* ctx, size_t bytes, void** dptr);
 int cts_free(cts_ctx* ctx, void* dptr);
