@@ -840,13 +840,43 @@ constexpr int kKeep = (CTS_FUSED_TILE_COLS * 32 + kFusedThreads - 1) / kFusedThr
 // 0 = from the arguments at run time, 1 = all in group 1 (n1 == NT), 2 = n1 == ceil(NT/2) (stage i of an IMEX-ARK tableau
 // with dense lower triangles: i-1 explicit and i-2 implicit tendencies).  A compile-time split needs no selects.
 
+// Resident CTAs per SM the register allocation aims at: 5 (<= 96 registers) in general; launches with at most
+// CTS_FUSED_SIX_BLOCKS_NT_MAX operands are held to 80 registers so that a sixth CTA fits (shared memory allows six stored-W
+// tiles of 64 Float64 levels: 6 x (35 984 + 1024) B <= 228 KB).  With U0 parked in shared memory during the solve these
+// instantiations need no spills at 80 registers.
+#ifndef CTS_FUSED_SIX_BLOCKS_NT_MAX
+#define CTS_FUSED_SIX_BLOCKS_NT_MAX 5
+#endif
+#ifndef CTS_FUSED_PARK_F32
+#define CTS_FUSED_PARK_F32 2
+#endif
+#ifndef CTS_FUSED_MF_BLOCKS
+#define CTS_FUSED_MF_BLOCKS 6
+#endif
+#ifndef CTS_FUSED_MF_BLOCKS_NT_MAX
+#define CTS_FUSED_MF_BLOCKS_NT_MAX 5
+#endif
+// U0 vectors a solver thread parks in shared memory during the solve (the rest stay in registers).  A stored-W tile of
+// Float32 (32 columns) has twice the solver threads of a Float64 tile: parking all four vectors (4 KiB) would leave room for
+// only five CTAs per SM, parking two of them (2 KiB) lets the sixth in.
+template <typename T, bool MATRIX_FREE>
+struct FusedPark {
+  static constexpr int value = (sizeof(T) == 4 && !MATRIX_FREE) ? CTS_FUSED_PARK_F32 : kKeep;
+};
+template <int NT, bool MATRIX_FREE>
+struct FusedMinBlocks {
+  static constexpr int value = MATRIX_FREE ? (NT <= CTS_FUSED_MF_BLOCKS_NT_MAX ? CTS_FUSED_MF_BLOCKS : CTS_FUSED_REG_MIN_BLOCKS)
+                                           : (NT <= CTS_FUSED_SIX_BLOCKS_NT_MAX ? 6 : CTS_FUSED_REG_MIN_BLOCKS);
+};
+
 template <typename T, typename C, int NT, bool MATRIX_FREE, int N1SPEC>
-__global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) column_fused_stage_reg_kernel(const FusedArgs<NT> a) {
+__global__ void __launch_bounds__(kFusedThreads, FusedMinBlocks<NT, MATRIX_FREE>::value) column_fused_stage_reg_kernel(const FusedArgs<NT> a) {
   using V = typename Vec<T>::type;
   constexpr int VN = Vec<T>::N;
   constexpr int NTS = NT > 0 ? NT : 1;
   constexpr int kCols = TileShape<T>::kCols;       // 16 columns of Float64, 32 of Float32
   constexpr int kSolvers = TileShape<T>::kThreads;  // solver threads: a lane pair per column
+  constexpr int kPark = FusedPark<T, MATRIX_FREE>::value;
   extern __shared__ __align__(128) char smem[];
   const int pitch = a.pitch;
   const int tile_bytes = kCols * pitch;
@@ -961,7 +991,7 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
   if (threadIdx.x < kSolvers) {
 #if CTS_FUSED_PARK
 #pragma unroll
-    for (int r = 0; r < kKeep; ++r) sPark[r * kSolvers + threadIdx.x] = keep[r];
+    for (int r = 0; r < kPark; ++r) sPark[r * kSolvers + threadIdx.x] = keep[r];
 #endif
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int col = warp * 16 + lane_column(lane);
@@ -982,7 +1012,7 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_REG_MIN_BLOCKS) colum
     asm volatile("bar.sync 1, %0;" ::"n"(kFusedThreads) : "memory");
 #if CTS_FUSED_PARK
 #pragma unroll
-    for (int r = 0; r < kKeep; ++r) keep[r] = sPark[r * kSolvers + threadIdx.x];
+    for (int r = 0; r < kPark; ++r) keep[r] = sPark[r * kSolvers + threadIdx.x];
 #endif
   } else {
     if (MATRIX_FREE && a.emit_w) {
@@ -1990,7 +2020,7 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
   if (!timeline && !no_reg && cpc >= 1 && cpc * kCols <= kKeep * kFusedThreads && (cpc & (cpc - 1)) == 0) {
     tiles = (op->ncols + kCols - 1) / kCols;
     size_t smem_reg = (size_t)(mf ? 2 : 4) * kCols * a.pitch + 16 + ((kCols * sizeof(T) + 15) / 16) * 16 +
-                      (size_t)TileShape<T>::kThreads * kKeep * 16;  // tiles + mbarrier + K/dz^2 + parked U0 of the solver threads
+                      (size_t)TileShape<T>::kThreads * (mf ? FusedPark<T, true>::value : FusedPark<T, false>::value) * 16;  // tiles + mbarrier + K/dz^2 + parked U0 of the solver threads
     a.dbg = nullptr;
     auto launch = [&](auto k) -> int {
       CTS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_reg));
@@ -2083,8 +2113,11 @@ struct RhsSolveArgs {
   int pitch;
 };
 
+#ifndef CTS_RHS_SOLVE_MIN_BLOCKS
+#define CTS_RHS_SOLVE_MIN_BLOCKS 6  // four tiles + barrier = 33 808 B of shared memory: six CTAs per SM at <= 80 registers
+#endif
 template <typename T, int MODE, bool NONLIN, int NTC>
-__global__ void __launch_bounds__(kFusedThreads, 5) column_rhs_solve_kernel(const RhsSolveArgs a) {
+__global__ void __launch_bounds__(kFusedThreads, CTS_RHS_SOLVE_MIN_BLOCKS) column_rhs_solve_kernel(const RhsSolveArgs a) {
   using V = typename Vec<T>::type;
   constexpr int VN = Vec<T>::N;
   constexpr int NTS = NTC > 0 ? NTC : 1;
