@@ -840,12 +840,14 @@ constexpr int kKeep = (CTS_FUSED_TILE_COLS * 32 + kFusedThreads - 1) / kFusedThr
 // 0 = from the arguments at run time, 1 = all in group 1 (n1 == NT), 2 = n1 == ceil(NT/2) (stage i of an IMEX-ARK tableau
 // with dense lower triangles: i-1 explicit and i-2 implicit tendencies).  A compile-time split needs no selects.
 
-// Resident CTAs per SM the register allocation aims at: 5 (<= 96 registers) in general; launches with at most
-// CTS_FUSED_SIX_BLOCKS_NT_MAX operands are held to 80 registers so that a sixth CTA fits (shared memory allows six stored-W
-// tiles of 64 Float64 levels: 6 x (35 984 + 1024) B <= 228 KB).  With U0 parked in shared memory during the solve these
-// instantiations need no spills at 80 registers.
+// Resident CTAs per SM the register allocation aims at.  The stage is bound by the number of tiles in flight (a tile lives
+// ~19 000 cycles: load -> solve -> store), so a sixth CTA is worth more than registers: stored-W launches with at most
+// CTS_FUSED_SIX_BLOCKS_NT_MAX operands (Float64; all Float32 ones) and all matrix-free launches are held to 80 registers --
+// spill-free since U0 is parked in shared memory during the solve -- and shared memory allows six stored-W tiles of 64
+// levels (6 x (35 984 + 1024) B <= 228 KB).  Measured (ncu, 2^21 columns): 3 operands 1.77 -> 1.51 ms per launch, 1 operand
+// matrix-free 1.20 -> 1.14 ms; 5 operands 1.87 -> 1.91 ms (the 12 loads of a round need the 96 registers), so it stays at 5.
 #ifndef CTS_FUSED_SIX_BLOCKS_NT_MAX
-#define CTS_FUSED_SIX_BLOCKS_NT_MAX 5
+#define CTS_FUSED_SIX_BLOCKS_NT_MAX 4
 #endif
 #ifndef CTS_FUSED_PARK_F32
 #define CTS_FUSED_PARK_F32 2
@@ -863,14 +865,14 @@ template <typename T, bool MATRIX_FREE>
 struct FusedPark {
   static constexpr int value = (sizeof(T) == 4 && !MATRIX_FREE) ? CTS_FUSED_PARK_F32 : kKeep;
 };
-template <int NT, bool MATRIX_FREE>
+template <typename T, int NT, bool MATRIX_FREE>
 struct FusedMinBlocks {
   static constexpr int value = MATRIX_FREE ? (NT <= CTS_FUSED_MF_BLOCKS_NT_MAX ? CTS_FUSED_MF_BLOCKS : CTS_FUSED_REG_MIN_BLOCKS)
-                                           : (NT <= CTS_FUSED_SIX_BLOCKS_NT_MAX ? 6 : CTS_FUSED_REG_MIN_BLOCKS);
+                                           : ((NT <= CTS_FUSED_SIX_BLOCKS_NT_MAX || (sizeof(T) == 4 && NT <= 5)) ? 6 : CTS_FUSED_REG_MIN_BLOCKS);
 };
 
 template <typename T, typename C, int NT, bool MATRIX_FREE, int N1SPEC>
-__global__ void __launch_bounds__(kFusedThreads, FusedMinBlocks<NT, MATRIX_FREE>::value) column_fused_stage_reg_kernel(const FusedArgs<NT> a) {
+__global__ void __launch_bounds__(kFusedThreads, FusedMinBlocks<T, NT, MATRIX_FREE>::value) column_fused_stage_reg_kernel(const FusedArgs<NT> a) {
   using V = typename Vec<T>::type;
   constexpr int VN = Vec<T>::N;
   constexpr int NTS = NT > 0 ? NT : 1;
