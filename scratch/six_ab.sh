@@ -5,6 +5,5 @@ import json; d=json.load(open('/tmp/b.json')); print('$1', round(d['ms_per_step'
 }
 for i in 1 2; do
 run default
-CTS_LIB_PATH=$PWD/scratch/variants/lib_six5.so run six5
-CTS_LIB_PATH=$PWD/scratch/variants/lib_six3.so run six3
+for v in "$@"; do CTS_LIB_PATH=$PWD/scratch/variants/lib_$v.so run $v; done
 done
