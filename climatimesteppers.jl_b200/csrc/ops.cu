@@ -922,11 +922,7 @@ __global__ void __launch_bounds__(kFusedThreads, FusedMinBlocks<T, NT, MATRIX_FR
   const int cshift = 31 - __clz(cpc);
   const int total = nvalid * cpc;
   V keep[kKeep];
-#ifdef CTS_FUSED_UN_NT5
-  constexpr int UN = NT >= 5 ? CTS_FUSED_UN_NT5 : 2;
-#else
-  constexpr int UN = 2;
-#endif
+  constexpr int UN = 2;  // (one round at a time so that the 5-operand stage fits 80 registers / six CTAs: within noise, 6.94-6.95 vs 6.98 ms/step)
   static_assert(kKeep % UN == 0, "rounds are processed in pairs");
   // N1c: the number of group-1 terms as a compile-time constant (-1: take it from the arguments at run time)
   auto phase_a = [&](auto N1c) {
