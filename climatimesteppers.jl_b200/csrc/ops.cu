@@ -8,6 +8,8 @@
 #include <algorithm>
 #include <type_traits>
 #include <cmath>
+#include <mutex>
+#include <unordered_map>
 #include <cstdlib>
 
 #include "cts_internal.h"
@@ -438,11 +440,12 @@ __global__ void __launch_bounds__(256) column_texp_kernel(T* __restrict__ out, c
 // Marching variant (used whenever the level count is a multiple of the 16-byte vector): a thread owns one 16-byte level vector of a row chunk and walks ROWS rows of the slow horizontal
 // axis with a sliding (south, centre, north) register window, so each element is fetched once per strip instead of
 // three times; west/east come from lines the CTA touched one iteration earlier (L1).  Same arithmetic.
-template <typename T, int VN, int ROWS>
+template <typename T, int VN>
 __global__ void __launch_bounds__(256) column_texp_march_kernel(T* __restrict__ out, const T* __restrict__ u,
                                                                 const T* __restrict__ S, T g, T nu, unsigned nlev,
                                                                 unsigned nx, unsigned row_elems, size_t ny_local,
-                                                                int halo, int has_src, size_t jr_begin, size_t jr_end) {
+                                                                int halo, int has_src, size_t jr_begin, size_t jr_end,
+                                                                int ROWS) {
   using V = typename Vec<T>::type;
   const unsigned r = (blockIdx.x * 256u + threadIdx.x) * VN;
   if (r >= row_elems) return;
@@ -513,6 +516,43 @@ __global__ void __launch_bounds__(256) column_texp_march_kernel(T* __restrict__ 
   }
 }
 
+// Rows a CTA of the marching kernels walks through.  8 is the measured optimum on a full 1024-row slab (more rows per strip
+// = fewer re-fetched rows, fewer CTAs in flight).  A rank's share of a sharded problem has few strips: 112 interior rows in
+// strips of 8 are 3584 CTAs = 4.04 waves of 888, i.e. a fifth round for 4 % of the work -- so on small launches the strip
+// height is the one of 4..16 that minimises (rounds of CTA waves) x (rows + the two extra rows a strip fetches).
+template <typename K>
+int march_strip_rows(K kernel, cts_ctx* ctx, size_t nrows, size_t xblocks) {
+  static std::mutex mu;  // (K is a function-pointer TYPE shared by several instantiations: key the cache by the pointer)
+  static std::unordered_map<const void*, int> cache;
+  int per_sm = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find((const void*)kernel);
+    if (it == cache.end()) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+      }
+      cache.emplace((const void*)kernel, per_sm);
+    } else {
+      per_sm = it->second;
+    }
+  }
+  const double wave = (double)per_sm * ctx->num_sms;
+  auto rounds = [&](int r) { return std::ceil((double)((nrows + r - 1) / r) * xblocks / wave); };
+  if ((double)((nrows + 7) / 8) * xblocks / wave >= 16.0) return 8;
+  int best = 8;
+  double best_cost = rounds(8) * (8 + 0.6);
+  for (int r = 4; r <= 16; ++r) {
+    const double c = rounds(r) * (r + 0.6);
+    if (c < best_cost - 1e-9) {
+      best_cost = c;
+      best = r;
+    }
+  }
+  return best;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Final update of an IMEX-ARK step fused with the LAST stage's explicit tendency (imex_ark.jl:79-101 + :256-258): the last
 // T_exp! output is only ever read by the final update (a_exp[:, s] == 0), so instead of writing it and reading it back
@@ -531,9 +571,10 @@ struct FinalArgs {
   size_t ny_local;
   int halo, has_src;
   size_t jr_begin, jr_end;  // owned rows [jr_begin, jr_end) of this launch
+  int strip_rows;           // rows a CTA marches through (march_strip_rows)
 };
 
-template <typename T, typename C, int NT, int ROWS>
+template <typename T, typename C, int NT>
 __global__ void __launch_bounds__(256) column_final_update_kernel(const FinalArgs<NT> a) {
   using V = typename Vec<T>::type;
   constexpr int VN = Vec<T>::N;
@@ -556,8 +597,8 @@ __global__ void __launch_bounds__(256) column_final_update_kernel(const FinalArg
 #pragma unroll
     for (int e = 0; e < VN; ++e) src[e] = rmul(t[e], g);
   }
-  const size_t jr0 = a.jr_begin + (size_t)blockIdx.y * ROWS;
-  const size_t jr1 = jr0 + ROWS < a.jr_end ? jr0 + ROWS : a.jr_end;
+  const size_t jr0 = a.jr_begin + (size_t)blockIdx.y * a.strip_rows;
+  const size_t jr1 = jr0 + a.strip_rows < a.jr_end ? jr0 + a.strip_rows : a.jr_end;
   auto local_row = [&](long long jr) -> size_t {
     if (a.halo) return (size_t)(jr + 1);
     return jr < 0 ? rows - 1 : ((size_t)jr == rows ? 0 : (size_t)jr);
@@ -2425,10 +2466,11 @@ int launch_final(cts_op_column* op, const cts_final_update_args* s, size_t jr_be
   a.jr_begin = jr_begin;
   a.jr_end = jr_end;
   CTS_COUNT_BYTES(ctx, 3 + NT, (jr_end - jr_begin) * a.row_elems, sizeof(T));  // u, U_s, terms in; u out
-  constexpr int ROWS = 8;
   constexpr int VN = Vec<T>::N;
-  dim3 grid((unsigned)((a.row_elems / VN + 255) / 256), (unsigned)((jr_end - jr_begin + ROWS - 1) / ROWS));
-  column_final_update_kernel<T, C, NT, ROWS><<<grid, 256, 0, ctx->stream>>>(a);
+  const unsigned xblocks = (unsigned)((a.row_elems / VN + 255) / 256);
+  a.strip_rows = march_strip_rows(column_final_update_kernel<T, C, NT>, ctx, jr_end - jr_begin, xblocks);
+  dim3 grid(xblocks, (unsigned)((jr_end - jr_begin + a.strip_rows - 1) / a.strip_rows));
+  column_final_update_kernel<T, C, NT><<<grid, 256, 0, ctx->stream>>>(a);
   CTS_LAUNCH_CHECK(ctx);
   return CTS_OK;
 }
@@ -2657,14 +2699,17 @@ static int column_T_exp_rows(cts_op_column* op, void* du_exp, const void* u, dou
   const size_t row_elems = d.nx * (size_t)d.nlev;
   const size_t nrows = jr_end - jr_begin;
   CTS_COUNT_BYTES(ctx, 2, nrows * row_elems, cts_sizeof(op->ft));
-  if (vec && row_elems < (1ull << 31) && d.nu != 0.0 && (nrows + 7) / 8 <= 65535) {
-    // strips of 8 rows (25 % of the rows are fetched twice, from L2): measured best of 8/16/32/64/128 on B200
-    constexpr int ROWS = 8;
-    dim3 grid((unsigned)((row_elems / vn + 255) / 256), (unsigned)((nrows + ROWS - 1) / ROWS));
+  if (vec && row_elems < (1ull << 31) && d.nu != 0.0 && (nrows + 3) / 4 <= 65535) {
+    // strips of 8 rows (25 % of the rows are fetched twice, from L2): measured best of 8/16/32/64/128 on B200 for a full slab;
+    // small launches pick the strip height that fills the waves of CTAs (march_strip_rows)
+    const unsigned xblocks = (unsigned)((row_elems / vn + 255) / 256);
+    const int ROWS = op->ft == CTS_F64 ? march_strip_rows(column_texp_march_kernel<double, 2>, ctx, nrows, xblocks)
+                                       : march_strip_rows(column_texp_march_kernel<float, 4>, ctx, nrows, xblocks);
+    dim3 grid(xblocks, (unsigned)((nrows + ROWS - 1) / ROWS));
     if (op->ft == CTS_F64)
-      column_texp_march_kernel<double, 2, ROWS><<<grid, 256, 0, ctx->stream>>>((double*)du_exp, (const double*)u, (const double*)d.S_lev, g, d.nu, (unsigned)d.nlev, (unsigned)d.nx, (unsigned)row_elems, d.ny_local, d.halo, has_src, jr_begin, jr_end);
+      column_texp_march_kernel<double, 2><<<grid, 256, 0, ctx->stream>>>((double*)du_exp, (const double*)u, (const double*)d.S_lev, g, d.nu, (unsigned)d.nlev, (unsigned)d.nx, (unsigned)row_elems, d.ny_local, d.halo, has_src, jr_begin, jr_end, ROWS);
     else
-      column_texp_march_kernel<float, 4, ROWS><<<grid, 256, 0, ctx->stream>>>((float*)du_exp, (const float*)u, (const float*)d.S_lev, (float)g, (float)d.nu, (unsigned)d.nlev, (unsigned)d.nx, (unsigned)row_elems, d.ny_local, d.halo, has_src, jr_begin, jr_end);
+      column_texp_march_kernel<float, 4><<<grid, 256, 0, ctx->stream>>>((float*)du_exp, (const float*)u, (const float*)d.S_lev, (float)g, (float)d.nu, (unsigned)d.nlev, (unsigned)d.nx, (unsigned)row_elems, d.ny_local, d.halo, has_src, jr_begin, jr_end, ROWS);
     CTS_LAUNCH_CHECK(ctx);
     return CTS_OK;
   }
