@@ -149,6 +149,7 @@ SIGNATURES = [
     ("cts_axpby", _I, [_P, _I, _SZ, _D, _P, _D, _P]),
     ("cts_div_scalar", _I, [_P, _I, _SZ, _P, _P, _D]),
     ("cts_lincomb", _I, [_P, _I, _SZ, _P, _I, c_double_p, c_void_pp, _I]),
+    ("cts_lincomb_sub", _I, [_P, _I, _SZ, _P, _P, _I, c_double_p, c_void_pp]),
     ("cts_dot", _I, [_P, _I, _SZ, _P, _P, c_double_p]),
     ("cts_nrm2", _I, [_P, _I, _SZ, _P, c_double_p]),
     ("cts_sum1pabs", _I, [_P, _I, _SZ, _P, c_double_p]),

@@ -805,7 +805,75 @@ __global__ void __launch_bounds__(256) lincomb_kernel(T* out, const LincombArgs 
   for (int j = 0; j < a.k; ++j) acc = __dadd_rn(acc, __dmul_rn(a.coef[j], (double)reinterpret_cast<const T*>(a.V[j])[i]));
   out[i] = (T)acc;
 }
+// K9 + K5 in one pass: d = sum_j coef[j]*V[j] (the fold of lincomb_kernel, rounded to T as its store would), x -= d in the
+// state precision (SubF); d itself is stored only when somebody reads it afterwards.  VN elements per thread (16-byte
+// vectors when the arrays allow it).
+template <typename T, int VN>
+__global__ void __launch_bounds__(256) lincomb_sub_kernel(T* __restrict__ x, T* __restrict__ dx, const LincombArgs a, size_t nvec) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  using V = typename cts_ew::Vec<T>::type;
+  double acc[VN];
+#pragma unroll
+  for (int e = 0; e < VN; ++e) acc[e] = 0.0;
+  for (int j = 0; j < a.k; ++j) {
+    T v[VN];
+    if constexpr (VN == 1)
+      v[0] = reinterpret_cast<const T*>(a.V[j])[i];
+    else
+      cts_ew::vec_unpack<T>(reinterpret_cast<const V*>(a.V[j])[i], v);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) acc[e] = __dadd_rn(acc[e], __dmul_rn(a.coef[j], (double)v[e]));
+  }
+  T xe[VN], de[VN];
+  if constexpr (VN == 1)
+    xe[0] = x[i];
+  else
+    cts_ew::vec_unpack<T>(reinterpret_cast<const V*>(x)[i], xe);
+#pragma unroll
+  for (int e = 0; e < VN; ++e) {
+    de[e] = (T)acc[e];
+    xe[e] = cts_ew::op_sub(xe[e], de[e]);
+  }
+  if constexpr (VN == 1) {
+    x[i] = xe[0];
+    if (dx) dx[i] = de[0];
+  } else {
+    reinterpret_cast<V*>(x)[i] = cts_ew::vec_pack<T>(xe);
+    if (dx) reinterpret_cast<V*>(dx)[i] = cts_ew::vec_pack<T>(de);
+  }
+}
 }  // namespace
+
+extern "C" int cts_lincomb_sub(cts_ctx* ctx, cts_dtype ft, size_t n, void* x, void* dx, int k, const double* coef,
+                               const void* const* V) {
+  CTS_CHECK_CTX(ctx);
+  if (!x || k < 1 || k > kLincombMax || !coef || !V) return cts_fail(ctx, CTS_EINVAL, "cts_lincomb_sub: bad argument");
+  if (n == 0) return CTS_OK;
+  LincombArgs a;
+  a.k = k;
+  a.accumulate = 0;
+  const int vn = ft == CTS_F64 ? 2 : 4;
+  bool vec = (n % vn) == 0 && cts_aligned16(x) && (!dx || cts_aligned16(dx));
+  for (int j = 0; j < k; ++j) {
+    if (!V[j]) return cts_fail(ctx, CTS_EINVAL, "cts_lincomb_sub: null basis vector");
+    a.V[j] = V[j];
+    a.coef[j] = coef[j];
+    vec = vec && cts_aligned16(V[j]);
+  }
+  CTS_COUNT_BYTES(ctx, k + 2 + (dx ? 1 : 0), n, cts_sizeof(ft));
+  const size_t nvec = vec ? n / vn : n;
+  const unsigned blocks = (unsigned)((nvec + 255) / 256);
+  if (ft == CTS_F64) {
+    if (vec) lincomb_sub_kernel<double, 2><<<blocks, 256, 0, ctx->stream>>>((double*)x, (double*)dx, a, nvec);
+    else lincomb_sub_kernel<double, 1><<<blocks, 256, 0, ctx->stream>>>((double*)x, (double*)dx, a, nvec);
+  } else {
+    if (vec) lincomb_sub_kernel<float, 4><<<blocks, 256, 0, ctx->stream>>>((float*)x, (float*)dx, a, nvec);
+    else lincomb_sub_kernel<float, 1><<<blocks, 256, 0, ctx->stream>>>((float*)x, (float*)dx, a, nvec);
+  }
+  CTS_LAUNCH_CHECK(ctx);
+  return CTS_OK;
+}
 
 extern "C" int cts_div_scalar(cts_ctx* ctx, cts_dtype ft, size_t n, void* y, const void* x, double denom) {
   CTS_CHECK_CTX(ctx);

@@ -215,7 +215,8 @@ int get_rtol(cts_newton_cache* c, const void* f, int n_iter, double* rtol_out) {
 // as matvec followed by precond, `w` is then never written.
 int gmres(cts_newton_cache* c, const std::function<int(void* out, const void* v)>& matvec,
           const std::function<int(void* out, const void* w)>* precond, const void* b, void* x, double rtol,
-          const std::function<int(void* out, const void* v)>* matvec_precond = nullptr) {
+          const std::function<int(void* out, const void* v)>* matvec_precond = nullptr, void* newton_x = nullptr,
+          bool keep_dx = true, bool* applied = nullptr) {
   cts_ctx* ctx = c->ctx;
   const cts_dtype ft = c->ft;
   const size_t n = c->n, bytes = n * cts_sizeof(ft);
@@ -345,13 +346,21 @@ int gmres(cts_newton_cache* c, const std::function<int(void* out, const void* v)
     y[ii] = (std::fabs(R[ii][ii]) <= btol) ? 0.0 : acc / R[ii][ii];
   }
   std::vector<const void*> Vp(c->V.begin(), c->V.begin() + k);
+  if (newton_x && applied && k >= 1 && k <= 32) {
+    // K9 + K5 (newtons_method.jl:508,651) in one pass: the Newton iterate takes the update straight from the basis; Δx is
+    // written only for a convergence checker / line search (same fold, same roundings as cts_lincomb + cts_sub_inplace)
+    cts_prof_scope ps(ctx, CTS_PROF_NEWTON_EW);
+    CTS_TRY(cts_lincomb_sub(ctx, ft, n, newton_x, keep_dx ? x : nullptr, (int)k, y.data(), Vp.data()));
+    *applied = true;
+    return CTS_OK;
+  }
   CTS_TRY(cts_lincomb(ctx, ft, n, x, (int)k, y.data(), Vp.data(), 0));
   return CTS_OK;
 }
 
 // solve_krylov! (newtons_method.jl:465-509)
 int solve_krylov(cts_newton_cache* c, void* dx, const void* x, const ResidualFn& f_, const void* f, int n_iter,
-                 const PrepareFn* prepare) {
+                 const PrepareFn* prepare, void* newton_x = nullptr, bool keep_dx = true, bool* applied = nullptr) {
   cts_nvtx_scope nvtx("solve_krylov!");  // newtons_method.jl:465
   cts_ctx* ctx = c->ctx;
   const bool jfree = c->cfg.jacobian_free_jvp != 0;
@@ -394,12 +403,14 @@ int solve_krylov(cts_newton_cache* c, void* dx, const void* x, const ResidualFn&
     c->stats.ldiv_calls++;
     return CTS_OK;
   };
-  // library column operator + its batched tridiagonal W as preconditioner: JVP and ldiv! of a Krylov iteration can run as
-  // one tile kernel (8w instead of 5w + 5w, bit-identical).  Opt-in (CTS_JVP_PRECOND_FUSION=1, read per solve): with the
-  // nonlinear operator the tile kernel is FP64-issue bound at its 5 CTAs/SM and measured SLOWER on B200 than the two
-  // full-occupancy passes (1.72 ms vs 0.75 + 0.83 ms per Krylov iteration at 2^27 DOF).
+  // library column operator + its batched tridiagonal W as preconditioner: JVP and ldiv! of a Krylov iteration run as one
+  // tile kernel (8w instead of 5w + 5w, bit-identical).  Default: on for Float64 (since the tile kernels hold six CTAs per
+  // SM it beats the two full-occupancy passes: C4 at 2^27 DOF 39.5 vs 40.4 ms/step), off for Float32 (23.7 vs 23.1 ms:
+  // twice the elements per byte through the nonlinear operator's Float64 arithmetic); CTS_JVP_PRECOND_FUSION=0/1 overrides
+  // (read per solve).
   const char* mvp_env = getenv("CTS_JVP_PRECOND_FUSION");
-  const bool fuse_mvp = mvp_env && mvp_env[0] == '1' && use_M && c->fused_op && c->ldiv == cts_op_column_ldiv && c->ud == (void*)c->fused_op &&
+  const bool mvp_on = mvp_env ? mvp_env[0] == '1' : c->ft == CTS_F64;
+  const bool fuse_mvp = mvp_on && use_M && c->fused_op && c->ldiv == cts_op_column_ldiv && c->ud == (void*)c->fused_op &&
                         cts_column_rhs_solve_fusable(c->fused_op) && cts_aligned16(x) && cts_aligned16(f) && cts_aligned16(c->q);
   std::function<int(void*, const void*)> matvec_precond = [&](void* out, const void* v) -> int {
     double e = 0;
@@ -419,7 +430,7 @@ int solve_krylov(cts_newton_cache* c, void* dx, const void* x, const ResidualFn&
   };
   double rtol = 0;
   CTS_TRY(get_rtol(c, f, n_iter, &rtol));
-  return gmres(c, matvec, use_M ? &precond : nullptr, f, dx, rtol, fuse_mvp ? &matvec_precond : nullptr);
+  return gmres(c, matvec, use_M ? &precond : nullptr, f, dx, rtol, fuse_mvp ? &matvec_precond : nullptr, newton_x, keep_dx, applied);
 }
 
 // solve_newton! (newtons_method.jl:609-665); no line search, no convergence checker
@@ -550,6 +561,8 @@ int solve_newton(cts_newton_cache* c, void* x, const ResidualFn& f_, const JacFn
       CTS_TRY((*j_)(c->W, x));
       c->stats.wfact_evals++;
     }
+    bool k5_done = false;
+    const bool defer = c->defer_update && cfg.max_iters == 1 && !c->line_search && !c->has_checker;  // K5 fused by the caller
     if (!cfg.use_krylov) {
       if (!c->ldiv || !c->W) return cts_fail(ctx, CTS_EINVAL, "direct Newton needs ldiv! and a Jacobian");
       {
@@ -557,11 +570,14 @@ int solve_newton(cts_newton_cache* c, void* x, const ResidualFn& f_, const JacFn
         HOOK(ctx, c->ldiv(c->ud, c->dx, c->W, c->f));
       }
       c->stats.ldiv_calls++;
+    } else if (c->fuse_reductions && !defer) {
+      // GMRES hands the update over fused with K5 (x is read-only inside solve_krylov! until then)
+      CTS_TRY(solve_krylov(c, c->dx, x, f_, c->f, n - 1, prepare, x, c->line_search || c->has_checker, &k5_done));
     } else {
       CTS_TRY(solve_krylov(c, c->dx, x, f_, c->f, n - 1, prepare));
     }
-    if (c->defer_update && cfg.max_iters == 1 && !c->line_search && !c->has_checker) return CTS_OK;  // K5 fused by the caller
-    {
+    if (defer) return CTS_OK;
+    if (!k5_done) {
       cts_prof_scope ps(ctx, CTS_PROF_NEWTON_EW);
       CTS_TRY(cts_sub_inplace(ctx, c->ft, c->n, x, c->dx));  // K5
     }

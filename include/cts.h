@@ -152,6 +152,12 @@ int cts_div_scalar(cts_ctx* ctx, cts_dtype ft, size_t n, void* y, const void* x,
 int cts_lincomb(cts_ctx* ctx, cts_dtype ft, size_t n, void* out, int k, const double* coef /*host*/,
                 const void* const* V /*host array of device ptrs*/, int accumulate);
 
+/* K9 + K5 in one pass (newtons_method.jl:508 `Δx .= Krylov.solution(solver)` and :651 `x .-= Δx`): d = sum_j coef[j]*V[j]
+ * (the same fold and rounding as cts_lincomb), x -= d in the state precision; `dx` (may be NULL) receives d when a
+ * convergence checker or the line search reads Δx afterwards.  1 <= k <= 32. */
+int cts_lincomb_sub(cts_ctx* ctx, cts_dtype ft, size_t n, void* x, void* dx, int k, const double* coef /*host*/,
+                    const void* const* V /*host array of device ptrs*/);
+
 /* ------------------------------------------------------------------ reductions (R1-R4) ------- */
 /* `norm`, `sum(x_i -> 1 + abs(x_i), x)` and Krylov dots (newtons_method.jl:108,120,135,265; convergence_checker.jl:81-82).
  * Deterministic tree in Float64 defined on fixed chunks of the element index (csrc/reduce.cu): independent of the SM

@@ -28,7 +28,8 @@ with torch.cuda.stream(stream):
         import numpy as np
         for fuse in ("0", "1"):
             os.environ["CTS_JVP_PRECOND_FUSION"] = fuse
-            r = B.run_c4(cts, ctx, stream, np.float64)
-            out.append(f"c4-f64 fuse={fuse} {r['ms_per_step']:.2f} ms frac {r['frac']:.3f}")
-            torch.cuda.empty_cache()
+            for dt_, nm in ((np.float64, "f64"), (np.float32, "f32")):
+                r = B.run_c4(cts, ctx, stream, dt_)
+                out.append(f"c4-{nm} fuse={fuse} {r['ms_per_step']:.2f} ms frac {r['frac']:.3f} B/DOF {r['bytes_per_dof_step']:.0f}")
+                torch.cuda.empty_cache()
     print(os.environ.get("CTS_LIB_PATH", "default").split("/")[-1], "|", "; ".join(out))

@@ -420,3 +420,46 @@ def test_imex_steps_with_eisenstat_walker_and_step_sizes(cts, step_kind, forcing
     assert np.isfinite(got).all()
     assert integ.cache.stats()["krylov_iters"] == sum(s["niter"] for s in cache_o["nm_cache"]["stats"]) > 0
     np.testing.assert_array_equal(got, uo)
+
+
+# ------------------------------------------------------------------ K9 + K5 in one pass ---------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,k,keep_dx,offset", [(4096, 1, True, 0), (4096, 2, False, 0), (100003, 3, True, 0), (8192, 20, False, 0),
+                                                (8192, 32, True, 0), (4099, 2, True, 1), (64, 5, False, 0)])
+def test_lincomb_sub_equals_solution_update_then_k5(cts, dtype, n, k, keep_dx, offset):
+    """`cts_lincomb_sub` (GMRES solution update fused with `x .-= Δx`, newtons_method.jl:508,651) against the oracle's two
+    statements -- the sequential Float64 fold rounded to FT, then the subtraction in FT -- and against the two separate
+    passes (`cts_lincomb`, `cts_sub_inplace`): bit for bit, vector and scalar paths (odd n, an 8- or 4-byte offset view)."""
+    import ctypes as C
+    from cts_b200 import _lib as L
+    ctx = cts.Context.default()
+    ft = L.CTS_F64 if dtype == np.float64 else L.CTS_F32
+    Vh = [(M.fill_hash(n + offset, 30 + j) - 0.5).astype(dtype) for j in range(k)]
+    xh = (M.fill_hash(n + offset, 5) * 3.0).astype(dtype)
+    coef_h = [0.7 * (-1) ** j / (j + 1) for j in range(k)]
+    acc = np.zeros(n, np.float64)
+    for c, v in zip(coef_h, Vh):
+        acc = acc + c * v[offset:].astype(np.float64)
+    d_want = acc.astype(dtype)
+    x_want = (xh[offset:] - d_want).astype(dtype)
+
+    item = np.dtype(dtype).itemsize
+    Vd = [cts.B200Vector.from_host(v, ctx) for v in Vh]
+    coef = (C.c_double * k)(*coef_h)
+    ptrs = (C.c_void_p * k)(*[v.ptr + offset * item for v in Vd])
+    # fused
+    x1 = cts.B200Vector.from_host(xh, ctx)
+    dx1 = cts.B200Vector.zeros(n + offset, dtype, ctx)
+    ctx.check(ctx.lib.cts_lincomb_sub(ctx.handle, ft, n, x1.ptr + offset * item, (dx1.ptr + offset * item) if keep_dx else None, k, coef, ptrs))
+    # two passes
+    x2 = cts.B200Vector.from_host(xh, ctx)
+    dx2 = cts.B200Vector.zeros(n + offset, dtype, ctx)
+    ctx.check(ctx.lib.cts_lincomb(ctx.handle, ft, n, dx2.ptr + offset * item, k, coef, ptrs, 0))
+    ctx.check(ctx.lib.cts_sub_inplace(ctx.handle, ft, n, x2.ptr + offset * item, dx2.ptr + offset * item))
+    np.testing.assert_array_equal(x1.to_host()[offset:], x_want)
+    np.testing.assert_array_equal(x2.to_host()[offset:], x_want)
+    np.testing.assert_array_equal(x1.to_host()[:offset], xh[:offset])
+    if keep_dx:
+        np.testing.assert_array_equal(dx1.to_host()[offset:], d_want)
+    else:
+        assert not dx1.to_host().any()
