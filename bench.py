@@ -691,6 +691,8 @@ def run_extras(cts, ctx, stream, op, u):
     # --- config C4: SSP333 (SSPRK path) + JFNK/GMRES, Newton max_iters = 2, nonlinear column diffusion, f64 and f32
     for dtype, name in ((np.float64, "f64"), (np.float32, "f32")):
         out[f"C4_ssp333_jfnk_{name}"] = run_c4(cts, ctx, stream, dtype)
+        # the same config with the operator declared matrix-free: the Krylov tile kernels generate W(x) themselves (bit-identical)
+        out[f"C4_ssp333_jfnk_{name}_matrix_free"] = run_c4(cts, ctx, stream, dtype, matrix_free=True)
         torch.cuda.empty_cache()
     out["C3_ars343_column_f32"] = run_c3_f32(cts, ctx, stream)
     torch.cuda.empty_cache()
@@ -763,7 +765,7 @@ def run_rosenbrock(cts, ctx, stream, fused):
     return res
 
 
-def run_c4(cts, ctx, stream, dtype):
+def run_c4(cts, ctx, stream, dtype, matrix_free=False):
     """BASELINE configs[3] as written: IMEXAlgorithm(SSP333(), NewtonsMethod(; max_iters = 2, krylov_method = KrylovMethod(;
     jacobian_free_jvp = ForwardDiffJVP(), forcing_term = ConstantForcing(rtol)))) on d/dz(K(1+T^2) dT/dz), 2^27 DOF, the
     frozen-coefficient W (batched tridiagonal) as left preconditioner, GMRES `memory = 20` and `itmax` at their defaults
@@ -775,7 +777,7 @@ def run_c4(cts, ctx, stream, dtype):
     K = cts.B200Vector.zeros(nx * ny, dtype, ctx).fill_hash(2, 0, 0.25, 2.0)
     # smooth state + 2 % hashed perturbation (white noise would make the frozen-coefficient preconditioner useless)
     u = cts.B200Vector.zeros(nx * ny * nlev, dtype, ctx).fill_hash(3, 0, 0.02, 25.0)
-    op = cts.ColumnOperator(nlev, nx, ny, K, nu=0.0, halo=0, nonlinear=True, ctx=ctx)
+    op = cts.ColumnOperator(nlev, nx, ny, K, nu=0.0, halo=0, nonlinear=True, ctx=ctx).set_matrix_free(matrix_free)
     rtol = 1e-2
     # ForwardDiffStepSize3 shrinks like 1/sqrt(n): at n = 2^27 the Float32 perturbation eps*v_i falls below eps(Float32)*x_i
     # and the JVP vanishes; `step_adjustment` (ForwardDiffJVP's own knob, newtons_method.jl:152-168) restores it.

@@ -197,6 +197,8 @@ int cts_column_fused_residual(cts_op_column* op, void* out, const void* x, const
 // right-hand side + column solve in one pass (ops.cu): the left-preconditioned Jacobian-free GMRES matvec
 //   q = W \ ((f(x + eps v) - f(x))/eps)   and the Rosenbrock stage   k_i = W \ (-dtγ (T_imp(U) [+ fU_exp] + sum_j coef_j terms_j))
 bool cts_column_rhs_solve_fusable(const cts_op_column* op);
+bool cts_column_krylov_matrix_free(const cts_op_column* op);
+int cts_column_precond_matrix_free(cts_op_column* op, void* q, const void* x, const void* b, double dtg);
 int cts_column_jvp_precond(cts_op_column* op, void* q, const void* x, const void* v, double eps, const void* U0, const void* f,
                            double dtgamma, const cts_tridiag* W);
 int cts_column_rosenbrock_stage(cts_op_column* op, void* k_out, const void* U, const void* fU_exp, int nt, const double* coef,

@@ -2133,7 +2133,12 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
 // tridiag_tile_kernel): bit-identical results.  A CTA owns TileShape<T>::kCols columns (one contiguous range); W arrives
 // by bulk TMA while the right-hand side is assembled; the solve is the two-sided product-form Thomas of tile_device.cuh.
 // ---------------------------------------------------------------------------------------------
-constexpr int MODE_ROS = 0, MODE_JVP = 1;
+//   MODE_PRE  (matrix-free W only) the first preconditioner solve of a GMRES call, q = W(x) \ b (newtons_method.jl:484):
+//             3w instead of 5w
+// WGEN ("matrix-free W", cts_op_column_set_matrix_free): the rows of W = dtγ J(x) - I are computed from x inside the kernel
+// with the expressions of column_wfact_kernel (frozen coefficients at x for the nonlinear operator) instead of being read:
+// 3w less per solve and no Wfact pass -- valid whenever the stored W would have been refreshed at this very x.
+constexpr int MODE_ROS = 0, MODE_JVP = 1, MODE_PRE = 2;
 constexpr int kRhsMaxTerms = 3;  // chain terms besides T_imp(U) and fU_exp (SSPKnoth needs 2)
 struct RhsSolveArgs {
   void* out;
@@ -2159,7 +2164,7 @@ struct RhsSolveArgs {
 #ifndef CTS_RHS_SOLVE_MIN_BLOCKS
 #define CTS_RHS_SOLVE_MIN_BLOCKS 6  // four tiles + barrier = 33 808 B of shared memory: six CTAs per SM at <= 80 registers
 #endif
-template <typename T, int MODE, bool NONLIN, int NTC>
+template <typename T, int MODE, bool NONLIN, int NTC, bool WGEN = false>
 __global__ void __launch_bounds__(kFusedThreads, CTS_RHS_SOLVE_MIN_BLOCKS) column_rhs_solve_kernel(const RhsSolveArgs a) {
   using V = typename Vec<T>::type;
   constexpr int VN = Vec<T>::N;
@@ -2180,25 +2185,27 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_RHS_SOLVE_MIN_BLOCKS) colum
   const int col_bytes = nlev * (int)sizeof(T);
   const size_t goff = col0 * (size_t)nlev;
   const size_t gvec0 = goff * sizeof(T) / 16;
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-    mbar_arrive_expect_tx(bar, (uint32_t)(3 * nvalid * col_bytes));
-  }
-  __syncthreads();
-  if ((int)threadIdx.x < nvalid) {
-    const int c = threadIdx.x;
-    const size_t g = goff + (size_t)c * nlev;
-    bulk_g2s(sdl + c * pitch, (const T*)a.dl + g, col_bytes, bar);
-    bulk_g2s(sd + c * pitch, (const T*)a.d + g, col_bytes, bar);
-    bulk_g2s(sdu + c * pitch, (const T*)a.du + g, col_bytes, bar);
+  if (!WGEN) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+      mbar_arrive_expect_tx(bar, (uint32_t)(3 * nvalid * col_bytes));
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nvalid) {
+      const int c = threadIdx.x;
+      const size_t g = goff + (size_t)c * nlev;
+      bulk_g2s(sdl + c * pitch, (const T*)a.dl + g, col_bytes, bar);
+      bulk_g2s(sd + c * pitch, (const T*)a.d + g, col_bytes, bar);
+      bulk_g2s(sdu + c * pitch, (const T*)a.du + g, col_bytes, bar);
+    }
   }
   const int cpc = col_bytes / 16;  // vectors per column: a power of two <= 32 (a column is a lane group)
   const int cshift = 31 - __clz(cpc);
   const int total = nvalid * cpc;
   const T eps = (T)a.eps;
   constexpr bool round_each = sizeof(T) == 4;
-  const bool has_v = MODE == MODE_JVP || a.v != nullptr;
+  const bool has_v = MODE == MODE_JVP || MODE == MODE_PRE || a.v != nullptr;
   constexpr int UN = 2;  // rounds whose loads are all issued before the first use (as in the fused stage kernel)
   static_assert(kKeep % UN == 0, "rounds are processed in pairs");
 #pragma unroll
@@ -2239,6 +2246,39 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_RHS_SOLVE_MIN_BLOCKS) colum
       vec_unpack<T>(vv[u], ev);
       vec_unpack<T>(vu[u], eu);
       vec_unpack<T>(vf[u], ef);
+      if (WGEN) {  // rows of W = dtγ J(x) - I at this thread's levels (column_wfact_kernel's expressions) -> shared tiles
+        T xb = __shfl_up_sync(0xffffffffu, ex[VN - 1], 1, cpc);
+        T xa = __shfl_down_sync(0xffffffffu, ex[0], 1, cpc);
+        if (kk[u] == 0) xb = T(0);
+        if (kk[u] == cpc - 1) xa = T(0);
+        T rl[VN], rd[VN], ru[VN];
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+          if (!NONLIN) {
+            const double o = __dmul_rn(a.dtg, (double)acol[u]);
+            rl[e] = (T)o;
+            ru[e] = (T)o;
+            rd[e] = (T)__dsub_rn(__dmul_rn(-2.0, o), 1.0);
+          } else {
+            const T um = e > 0 ? ex[e > 0 ? e - 1 : 0] : xb;
+            const T up = e + 1 < VN ? ex[e + 1 < VN ? e + 1 : e] : xa;
+            const double lo = __dmul_rn(a.dtg, (double)kface(acol[u], um, ex[e]));
+            const double hi = __dmul_rn(a.dtg, (double)kface(acol[u], ex[e], up));
+            rl[e] = (T)lo;
+            ru[e] = (T)hi;
+            rd[e] = (T)__dsub_rn(-__dadd_rn(lo, hi), 1.0);
+          }
+        }
+        if (ok[u]) {
+          *reinterpret_cast<V*>(sdl + so[u]) = vec_pack<T>(rl);
+          *reinterpret_cast<V*>(sd + so[u]) = vec_pack<T>(rd);
+          *reinterpret_cast<V*>(sdu + so[u]) = vec_pack<T>(ru);
+        }
+      }
+      if (MODE == MODE_PRE) {  // the right-hand side is the array itself
+        if (ok[u]) *reinterpret_cast<V*>(sx + so[u]) = vv[u];
+        continue;
+      }
 #pragma unroll
       for (int e = 0; e < VN; ++e) x2[e] = MODE == MODE_JVP ? radd(ex[e], rmul(eps, ev[e])) : ex[e];  // K7
       T below = __shfl_up_sync(0xffffffffu, x2[VN - 1], 1, cpc);
@@ -2287,7 +2327,7 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_RHS_SOLVE_MIN_BLOCKS) colum
     const int col = warp * 16 + lane_column(lane);
     const bool is_up = lane_is_up(lane);
     const bool valid = col < nvalid;
-    mbar_wait(bar, 0);
+    if (!WGEN) mbar_wait(bar, 0);
     StoredRows<T> rows{sdl, sd, sdu};
     babe_solve_lanepair<T, StoredRows<T>, RhsFromTile<T>, false>(rows, RhsFromTile<T>{}, sx, col * pitch, nlev, is_up, valid);
   }
@@ -2318,7 +2358,13 @@ int launch_rhs_solve(cts_op_column* op, RhsSolveArgs& a, int mode) {
     return CTS_OK;
   };
   const bool nl = op->d.nonlinear;
-  if (mode == MODE_JVP) {
+  if (mode == MODE_JVP && !a.dl) {
+    if (nl) CTS_TRY(launch(column_rhs_solve_kernel<T, MODE_JVP, true, 0, true>));
+    else CTS_TRY(launch(column_rhs_solve_kernel<T, MODE_JVP, false, 0, true>));
+  } else if (mode == MODE_PRE) {
+    if (nl) CTS_TRY(launch(column_rhs_solve_kernel<T, MODE_PRE, true, 0, true>));
+    else CTS_TRY(launch(column_rhs_solve_kernel<T, MODE_PRE, false, 0, true>));
+  } else if (mode == MODE_JVP) {
     if (nl) CTS_TRY(launch(column_rhs_solve_kernel<T, MODE_JVP, true, 0>));
     else CTS_TRY(launch(column_rhs_solve_kernel<T, MODE_JVP, false, 0>));
   } else {
@@ -2341,10 +2387,14 @@ int launch_rhs_solve(cts_op_column* op, RhsSolveArgs& a, int mode) {
 }  // namespace
 
 // a column must be a power-of-two number (<= 32) of 16-byte vectors and a tile must fit the threads' kKeep vectors
-bool cts_column_rhs_solve_fusable(const cts_op_column* op) {
+static bool rhs_solve_shape_ok(const cts_op_column* op);
+bool cts_column_rhs_solve_fusable(const cts_op_column* op) { return !op->matrix_free && rhs_solve_shape_ok(op); }
+// the matrix-free form of the Krylov kernels (W rows computed from x in the kernel): needs the flag, not a stored W
+bool cts_column_krylov_matrix_free(const cts_op_column* op) { return op->matrix_free && rhs_solve_shape_ok(op); }
+static bool rhs_solve_shape_ok(const cts_op_column* op) {
   const int es = op->ft == CTS_F64 ? 8 : 4;
   const int cb = op->d.nlev * es;
-  if (op->matrix_free || op->d.nlev < 2 || (op->d.nlev % 2) || (cb % 16)) return false;
+  if (op->d.nlev < 2 || (op->d.nlev % 2) || (cb % 16)) return false;
   const int cpc = cb / 16;
   const int cols = op->ft == CTS_F64 ? TileShape<double>::kCols : TileShape<float>::kCols;
   return cpc <= 32 && (cpc & (cpc - 1)) == 0 && cpc * cols <= kKeep * kFusedThreads;
@@ -2354,11 +2404,38 @@ static bool rhs_solve_w_ok(const cts_op_column* op, const cts_tridiag* W) {
   return W && W->nlev == op->d.nlev && W->ncols == op->ncols && cts_aligned16(W->dl) && cts_aligned16(W->d) && cts_aligned16(W->du);
 }
 
+// q = W(x) \ b with the rows of W generated in the kernel (matrix-free operator)
+int cts_column_precond_matrix_free(cts_op_column* op, void* q, const void* x, const void* b, double dtg) {
+  if (!op || !q || !x || !b) return CTS_EINVAL;
+  if (!cts_column_krylov_matrix_free(op) || !cts_aligned16(q) || !cts_aligned16(x) || !cts_aligned16(b)) return CTS_EUNSUPPORTED;
+  RhsSolveArgs a{};
+  a.out = q;
+  a.x = x;
+  a.v = b;
+  a.dtg = dtg;
+  CTS_COUNT_BYTES(op->ctx, 3, cts_op_column_ndof(op), cts_sizeof(op->ft));  // x, b in; q out
+  return op->ft == CTS_F64 ? launch_rhs_solve<double>(op, a, MODE_PRE) : launch_rhs_solve<float>(op, a, MODE_PRE);
+}
+
+// W == nullptr: matrix-free operator, the rows of W are generated in the kernel from x
 int cts_column_jvp_precond(cts_op_column* op, void* q, const void* x, const void* v, double eps, const void* U0, const void* f,
                            double dtg, const cts_tridiag* W) {
   if (!op || !q || !x || !v || !U0 || !f) return CTS_EINVAL;
-  if (!cts_column_rhs_solve_fusable(op) || !rhs_solve_w_ok(op, W) || !cts_aligned16(q) || !cts_aligned16(x) || !cts_aligned16(v) ||
-      !cts_aligned16(U0) || !cts_aligned16(f))
+  if (!cts_aligned16(q) || !cts_aligned16(x) || !cts_aligned16(v) || !cts_aligned16(U0) || !cts_aligned16(f)) return CTS_EUNSUPPORTED;
+  if (!W) {
+    if (!cts_column_krylov_matrix_free(op)) return CTS_EUNSUPPORTED;
+    RhsSolveArgs a{};
+    a.out = q;
+    a.x = x;
+    a.v = v;
+    a.U0 = U0;
+    a.f = f;
+    a.eps = eps;
+    a.dtg = dtg;
+    CTS_COUNT_BYTES(op->ctx, 5, cts_op_column_ndof(op), cts_sizeof(op->ft));  // x, v, U0, f in; q out
+    return op->ft == CTS_F64 ? launch_rhs_solve<double>(op, a, MODE_JVP) : launch_rhs_solve<float>(op, a, MODE_JVP);
+  }
+  if (!cts_column_rhs_solve_fusable(op) || !rhs_solve_w_ok(op, W))
     return CTS_EUNSUPPORTED;
   RhsSolveArgs a{};
   a.out = q;
@@ -2595,7 +2672,9 @@ size_t cts_op_column_ndof(const cts_op_column* op) { return op ? op->ncols * (si
 
 int cts_op_column_set_matrix_free(cts_op_column* op, int enabled) {
   if (!op) return CTS_EINVAL;
-  if (enabled && op->d.nonlinear) return cts_fail(op->ctx, CTS_EINVAL, "matrix-free W needs the linear operator");
+  // linear operator: the fused stage kernels regenerate W from K_col; nonlinear operator: the Newton-Krylov tile kernels
+  // generate the frozen-coefficient W(x) from the Newton iterate (column_rhs_solve_kernel<.., WGEN>); every other path of a
+  // matrix-free operator still goes through Wfact / ldiv! on the stored W
   op->matrix_free = enabled != 0;
   return CTS_OK;
 }

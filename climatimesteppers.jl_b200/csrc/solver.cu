@@ -84,6 +84,7 @@ struct cts_newton_cache {
   const void* known_norm_ptr = nullptr;  // a basis vector whose norm came out of the kernel that produced it
   double known_norm = 0.0;
   bool fuse_reductions = true;           // cleared together with the engine's fusion switch (reference pass structure)
+  bool fused_wfact_is_lib = false;       // the Wfact hook of the current solve is the library column operator's
   bool xstat_valid = false;              // sum(1+|x|) (or norm(x)) of the current solve_krylov! call
   double xstat = 0.0;
   // one-iteration direct solve whose `x .-= Δx` (K5) the caller fuses with what follows (K6): solve_newton leaves Δx
@@ -358,6 +359,12 @@ int gmres(cts_newton_cache* c, const std::function<int(void* out, const void* v)
   return CTS_OK;
 }
 
+// Matrix-free Newton-Krylov on the library column operator (cts_op_column_set_matrix_free): W is never stored; the
+// preconditioner solves generate its rows from the Newton iterate inside the tile kernel.  That is the stored-W algorithm
+// bit for bit exactly when the reference would have refreshed W at this very x before every solve_krylov! call, i.e. for
+// update_j = UpdateEvery(NewNewtonIteration) (the default, newtons_method.jl:571,626).
+bool krylov_matrix_free(const cts_newton_cache* c, const void* x, const void* f);
+
 // solve_krylov! (newtons_method.jl:465-509)
 int solve_krylov(cts_newton_cache* c, void* dx, const void* x, const ResidualFn& f_, const void* f, int n_iter,
                  const PrepareFn* prepare, void* newton_x = nullptr, bool keep_dx = true, bool* applied = nullptr) {
@@ -397,9 +404,15 @@ int solve_krylov(cts_newton_cache* c, void* dx, const void* x, const ResidualFn&
     return CTS_OK;
   };
   const bool use_M = !(c->cfg.disable_preconditioner || !c->W || !jfree);
+  const bool kmf = use_M && krylov_matrix_free(c, x, f);
   std::function<int(void*, const void*)> precond = [&](void* out, const void* w) -> int {
     cts_prof_scope ps(ctx, CTS_PROF_LDIV);
-    HOOK(ctx, c->ldiv(c->ud, out, c->W, w));
+    if (kmf && cts_aligned16(out) && cts_aligned16(w)) {
+      CTS_TRY(cts_column_precond_matrix_free(c->fused_op, out, x, w, c->fused_dtg));
+    } else {
+      if (kmf) return cts_fail(ctx, CTS_EUNSUPPORTED, "matrix-free Krylov preconditioner needs 16-byte aligned vectors");
+      HOOK(ctx, c->ldiv(c->ud, out, c->W, w));
+    }
     c->stats.ldiv_calls++;
     return CTS_OK;
   };
@@ -410,13 +423,14 @@ int solve_krylov(cts_newton_cache* c, void* dx, const void* x, const ResidualFn&
   // (read per solve).
   const char* mvp_env = getenv("CTS_JVP_PRECOND_FUSION");
   const bool mvp_on = mvp_env ? mvp_env[0] == '1' : c->ft == CTS_F64;
-  const bool fuse_mvp = mvp_on && use_M && c->fused_op && c->ldiv == cts_op_column_ldiv && c->ud == (void*)c->fused_op &&
-                        cts_column_rhs_solve_fusable(c->fused_op) && cts_aligned16(x) && cts_aligned16(f) && cts_aligned16(c->q);
+  const bool fuse_mvp = kmf || (mvp_on && use_M && c->fused_op && c->ldiv == cts_op_column_ldiv && c->ud == (void*)c->fused_op &&
+                        cts_column_rhs_solve_fusable(c->fused_op) && cts_aligned16(x) && cts_aligned16(f) && cts_aligned16(c->q));
   std::function<int(void*, const void*)> matvec_precond = [&](void* out, const void* v) -> int {
     double e = 0;
     CTS_TRY(jvp_step(c, v, x, &e));
     cts_prof_scope ps(ctx, CTS_PROF_LDIV);
-    int r = cts_column_jvp_precond(c->fused_op, out, x, v, e, c->fused_U0, f, c->fused_dtg, static_cast<const cts_tridiag*>(c->W));
+    int r = cts_column_jvp_precond(c->fused_op, out, x, v, e, c->fused_U0, f, c->fused_dtg, kmf ? nullptr : static_cast<const cts_tridiag*>(c->W));
+    if (r == CTS_EUNSUPPORTED && kmf) return cts_fail(ctx, CTS_EUNSUPPORTED, "matrix-free Krylov matvec: unsupported operand");
     if (r == CTS_EUNSUPPORTED) {  // e.g. a W of another shape: the two separate passes
       CTS_TRY(cts_column_fused_residual(c->fused_op, c->w, x, v, e, c->fused_U0, f, c->fused_dtg));
       HOOK(ctx, c->ldiv(c->ud, out, c->W, c->w));
@@ -431,6 +445,13 @@ int solve_krylov(cts_newton_cache* c, void* dx, const void* x, const ResidualFn&
   double rtol = 0;
   CTS_TRY(get_rtol(c, f, n_iter, &rtol));
   return gmres(c, matvec, use_M ? &precond : nullptr, f, dx, rtol, fuse_mvp ? &matvec_precond : nullptr, newton_x, keep_dx, applied);
+}
+
+bool krylov_matrix_free(const cts_newton_cache* c, const void* x, const void* f) {
+  if (!c->fused_op || !c->cfg.use_krylov || !c->cfg.jacobian_free_jvp || c->cfg.disable_preconditioner || !c->W) return false;
+  if (c->cfg.update_j.fn || c->cfg.update_j.every_signal != CTS_SIG_NEW_NEWTON_ITERATION) return false;
+  if (c->ldiv != cts_op_column_ldiv || c->ud != (void*)c->fused_op || !c->fused_wfact_is_lib) return false;
+  return cts_column_krylov_matrix_free(c->fused_op) && cts_aligned16(x) && cts_aligned16(f) && cts_aligned16(c->q);
 }
 
 // solve_newton! (newtons_method.jl:609-665); no line search, no convergence checker
@@ -558,7 +579,8 @@ int solve_newton(cts_newton_cache* c, void* x, const ResidualFn& f_, const JacFn
   for (int n = 1; n <= cfg.max_iters; ++n) {
     c->stats.newton_iters++;
     if (has_j && needs_update(cfg.update_j, CTS_SIG_NEW_NEWTON_ITERATION)) {
-      CTS_TRY((*j_)(c->W, x));
+      // matrix-free Krylov: the kernels of this iteration generate W(x) themselves, the stored copy is not refreshed
+      if (!krylov_matrix_free(c, x, c->f)) CTS_TRY((*j_)(c->W, x));
       c->stats.wfact_evals++;
     }
     bool k5_done = false;
@@ -888,6 +910,7 @@ int solve_implicit_equation(cts_imex_cache* c, void* U, const void* U0, double t
   c->nm->fused_op = rop;
   c->nm->fused_U0 = U0;
   c->nm->fused_dtg = dtg;
+  c->nm->fused_wfact_is_lib = c->f.Wfact == cts_op_column_Wfact;
   JacFn j_ = [&](void* W, const void* Up) -> int {
     cts_prof_scope ps(ctx, CTS_PROF_WFACT);
     HOOK(ctx, c->f.Wfact(c->f.ud, W, Up, dtg, t_imp));

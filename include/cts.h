@@ -433,7 +433,10 @@ int cts_op_column_Wfact(void* op, void* W, const void* u, double dtgamma, double
 int cts_op_column_ldiv(void* op, void* x, const void* W, const void* b);                      /* cts_ldiv_fn     */
 int cts_op_column_jac_mul(void* op, void* y, const void* W, const void* x);                   /* cts_ldiv_fn     */
 int cts_op_column_dss(void* op, void* u, double t);                                           /* cts_state_fn    */
-/* 1: the fused stage kernel regenerates W from K_col instead of reading dl,d,du (linear operator only) */
+/* 1: kernels that know the operator regenerate W = dtγJ - I instead of reading dl,d,du: the fused implicit stage (linear
+ * operator, from K_col) and the Newton-Krylov preconditioner solves (linear or nonlinear operator, frozen coefficients at the
+ * Newton iterate; used when update_j = UpdateEvery(NewNewtonIteration), where the stored W would be the same bits and its
+ * Wfact pass is skipped).  Results are bit-identical to the stored-W run. */
 int cts_op_column_set_matrix_free(cts_op_column* op, int enabled);
 
 /* ------------------------------------------------------------------ multi-GPU ---------------- */

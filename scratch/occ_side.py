@@ -32,4 +32,11 @@ with torch.cuda.stream(stream):
                 r = B.run_c4(cts, ctx, stream, dt_)
                 out.append(f"c4-{nm} fuse={fuse} {r['ms_per_step']:.2f} ms frac {r['frac']:.3f} B/DOF {r['bytes_per_dof_step']:.0f}")
                 torch.cuda.empty_cache()
+    if "c4mf" in which:
+        import numpy as np
+        for dt_, nm in ((np.float64, "f64"), (np.float32, "f32")):
+            for mf in (False, True):
+                r = B.run_c4(cts, ctx, stream, dt_, matrix_free=mf)
+                out.append(f"c4-{nm} mf={int(mf)} {r['ms_per_step']:.2f} ms frac {r['frac']:.3f} B/DOF {r['bytes_per_dof_step']:.0f}")
+                torch.cuda.empty_cache()
     print(os.environ.get("CTS_LIB_PATH", "default").split("/")[-1], "|", "; ".join(out))

@@ -463,3 +463,42 @@ def test_lincomb_sub_equals_solution_update_then_k5(cts, dtype, n, k, keep_dx, o
         np.testing.assert_array_equal(dx1.to_host()[offset:], d_want)
     else:
         assert not dx1.to_host().any()
+
+
+# ------------------------------------------------------------------ matrix-free Newton-Krylov -----------------------
+@pytest.mark.parametrize("dtype,adj", [(np.float64, 1.0), (np.float32, 64.0)])
+@pytest.mark.parametrize("nlev,nx,ny", [(64, 128, 16), (32, 37, 5), (16, 9, 3)])
+def test_matrix_free_newton_krylov_is_bit_identical(cts, dtype, adj, nlev, nx, ny):
+    """`ColumnOperator.set_matrix_free(True)` on BASELINE configs[3] (SSP333 on the SSPRK path, NewtonsMethod(max_iters = 2,
+    KrylovMethod(ForwardDiffJVP, ConstantForcing)), nonlinear column diffusion, W as left preconditioner): the Krylov tile
+    kernels compute the rows of W = dtγ J(x) - I from the Newton iterate (column_wfact_kernel's expressions) instead of
+    reading a stored W, and no Wfact pass runs.  With update_j = UpdateEvery(NewNewtonIteration) (the default,
+    newtons_method.jl:571,626) that is the stored-W algorithm bit for bit; with UpdateEvery(NewNewtonSolve) the stored W is
+    NOT the one at x, so the engine must keep the stored path (same result as without the flag)."""
+    def run(mf, update_j=None):
+        ctx = cts.Context.default()
+        K = cts.B200Vector.zeros(ny * nx, dtype, ctx).fill_hash(2, 0, 0.25, 2.0)
+        op = cts.ColumnOperator(nlev, nx, ny, K, nu=0.0, halo=0, nonlinear=True).set_matrix_free(mf)
+        u = cts.B200Vector.zeros(op.ndof, dtype, ctx).fill_hash(3, 0, 0.02, 25.0)
+        km = cts.KrylovMethod(jacobian_free_jvp=cts.ForwardDiffJVP(step_adjustment=adj), forcing_term=cts.ConstantForcing(1e-2))
+        kw = {} if update_j is None else {"update_j": update_j}
+        alg = cts.IMEXAlgorithm(cts.SSP333(), cts.NewtonsMethod(max_iters=2, krylov_method=km, **kw))
+        integ = cts.init(cts.ODEProblem(op.ode_function(explicit=False), u, (0.0, 1e9), None), alg, dt=2e-3, save=False)
+        b0 = ctx.bytes_count()
+        for _ in range(2):
+            cts.step_(integ)
+        return u.to_host(), integ.cache.stats(), ctx.bytes_count() - b0
+
+    stored, st_s, bytes_s = run(False)
+    free, st_f, bytes_f = run(True)
+    assert np.isfinite(stored).all()
+    np.testing.assert_array_equal(free, stored)
+    for key in ("newton_iters", "krylov_iters", "wfact_evals", "ldiv_calls", "jvp_evals"):
+        assert st_f[key] == st_s[key], key
+    assert st_s["krylov_iters"] > 0 and bytes_f < 0.9 * bytes_s
+    # W refreshed once per Newton solve only: the matrix-free kernels do not apply
+    upd = cts.UpdateEvery(cts.NewNewtonSolve)
+    stored2, _, bytes_s2 = run(False, upd)
+    free2, _, bytes_f2 = run(True, upd)
+    np.testing.assert_array_equal(free2, stored2)
+    assert bytes_f2 >= bytes_s2   # (a matrix-free operator also keeps off the stored-W JVP + solve tile kernel)
