@@ -893,6 +893,9 @@ constexpr int kKeep = (CTS_FUSED_TILE_COLS * 32 + kFusedThreads - 1) / kFusedThr
 #ifndef CTS_FUSED_PARK_F32
 #define CTS_FUSED_PARK_F32 2
 #endif
+#ifndef CTS_FUSED_F32_BLOCKS
+#define CTS_FUSED_F32_BLOCKS 6
+#endif
 #ifndef CTS_FUSED_MF_BLOCKS
 #define CTS_FUSED_MF_BLOCKS 6
 #endif
@@ -909,7 +912,7 @@ struct FusedPark {
 template <typename T, int NT, bool MATRIX_FREE>
 struct FusedMinBlocks {
   static constexpr int value = MATRIX_FREE ? (NT <= CTS_FUSED_MF_BLOCKS_NT_MAX ? CTS_FUSED_MF_BLOCKS : CTS_FUSED_REG_MIN_BLOCKS)
-                                           : ((NT <= CTS_FUSED_SIX_BLOCKS_NT_MAX || (sizeof(T) == 4 && NT <= 5)) ? 6 : CTS_FUSED_REG_MIN_BLOCKS);
+                                           : ((sizeof(T) == 4 && NT <= 5) ? CTS_FUSED_F32_BLOCKS : (NT <= CTS_FUSED_SIX_BLOCKS_NT_MAX ? 6 : CTS_FUSED_REG_MIN_BLOCKS));
 };
 
 template <typename T, typename C, int NT, bool MATRIX_FREE, int N1SPEC>
