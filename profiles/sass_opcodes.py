@@ -3,7 +3,7 @@
 mnemonics that matter for this path (bulk TMA UBLKCP / mbarrier SYNCS / 128-bit LDG-STG / FP64 pipe / system-scope
 atomics and fences of the peer-memory halo kernel).  No tensor-core opcodes are expected: nothing here is a contraction.
 
-    python profiles/sass_opcodes.py > profiles/r2_sass_opcodes.txt
+    python profiles/sass_opcodes.py > profiles/r2b_sass_opcodes.txt
 """
 import collections
 import os
@@ -17,7 +17,7 @@ GROUPS = [("UBLKCP", r"^UBLKCP"), ("UTMALDG/UTMASTG", r"^UTMA(LDG|STG)"), ("SYNC
           ("LDG.128", r"^LDG\.E(\.\w+)*\.128"), ("STG.128", r"^STG\.E(\.\w+)*\.128"), ("LDG", r"^LDG"), ("STG", r"^STG"),
           ("LDS", r"^LDS"), ("STS", r"^STS"), ("SHFL", r"^SHFL"), ("BAR", r"^BAR"), ("DFMA/DADD/DMUL", r"^D(FMA|ADD|MUL)"),
           ("MUFU.RCP64H", r"^MUFU\.RCP64H"), ("ATOM/RED", r"^(ATOMG|ATOM|RED)"), ("*.SYS (system scope)", r"\.SYS"),
-          ("MEMBAR", r"^MEMBAR"), ("UTC*MMA/HMMA (tensor)", r"^(UTC\w*MMA|HMMA|HGMMA|LDTM|STTM)")]
+          ("MEMBAR", r"^MEMBAR"), ("DSMEM (MAPA / ST.*CLUSTER / UCGABAR)", r"^(MAPA|UCGABAR|ST\.E?\.?.*CLUSTER|STS.*CLUSTER)"), ("UTC*MMA/HMMA (tensor)", r"^(UTC\w*MMA|HMMA|HGMMA|LDTM|STTM)")]
 
 
 def main():
