@@ -278,6 +278,9 @@ typedef struct {
   int batch_gram_schmidt;     /* 0: modified GS (Krylov.jl order); 1: one fused sweep (classical GS) */
 } cts_newton_config;
 
+/* Counters follow the reference's call sites, not the kernels: `wfact_evals` counts the points at which the reference calls
+ * `Wfact` (async_utils.jl:25, newtons_method.jl:620,626) and `ldiv_calls` its `ldiv!`s (:484,633), also when a fused or
+ * matrix-free kernel did that work inside another pass (then no separate launch shows up in the profile). */
 typedef struct {
   uint64_t newton_iters, krylov_iters, f_evals, jvp_evals, wfact_evals, ldiv_calls, dss_calls;
   uint64_t fused_stage_launches;  /* stages that ran on the fused column fast path */
