@@ -278,9 +278,11 @@ typedef struct {
   int batch_gram_schmidt;     /* 0: modified GS (Krylov.jl order); 1: one fused sweep (classical GS) */
 } cts_newton_config;
 
-/* Counters follow the reference's call sites, not the kernels: `wfact_evals` counts the points at which the reference calls
- * `Wfact` (async_utils.jl:25, newtons_method.jl:620,626) and `ldiv_calls` its `ldiv!`s (:484,633), also when a fused or
- * matrix-free kernel did that work inside another pass (then no separate launch shows up in the profile). */
+/* `wfact_evals` counts the points at which the reference calls `Wfact` (async_utils.jl:25, newtons_method.jl:620,626), also
+ * when the work was folded into a stage kernel or done in-kernel by a matrix-free operator (no separate launch shows up in
+ * the profile then).  In a Newton-Krylov solve `ldiv_calls`/`jvp_evals`/`f_evals` count the preconditioner solves and
+ * operator evaluations whether or not they shared a tile kernel; a stage that ran on the fused column fast path adds one to
+ * `fused_stage_launches` and `newton_iters` and nothing to `f_evals`/`ldiv_calls`. */
 typedef struct {
   uint64_t newton_iters, krylov_iters, f_evals, jvp_evals, wfact_evals, ldiv_calls, dss_calls;
   uint64_t fused_stage_launches;  /* stages that ran on the fused column fast path */
