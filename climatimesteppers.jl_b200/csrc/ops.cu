@@ -867,6 +867,11 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_FUSED_MIN_BLOCKS) column_fu
 // 6 CTAs per SM costs the solver more than the extra CTA gives: 6.1 ms vs 5.4 ms per step; 64/96-thread CTAs have too
 // few loads in flight: 6.7 ms.  So: 128 threads, <= 96 registers, 5 CTAs per SM.)
 constexpr int kKeep = (CTS_FUSED_TILE_COLS * 32 + kFusedThreads - 1) / kFusedThreads;  // U0 vectors per thread (f64: 16 cols x <= 32 vectors, f32: 32 x <= 16)
+// ... per element type: a Float32 tile of CTS_FUSED_TILE_COLS_F32 columns holds <= 16 vectors per column at 64 levels
+template <typename T>
+struct KeepOf {
+  static constexpr int value = sizeof(T) == 4 ? (TileShape<float>::kCols * 16 + kFusedThreads - 1) / kFusedThreads : kKeep;
+};
 
 #ifndef CTS_FUSED_PARK
 #define CTS_FUSED_PARK 1
@@ -907,7 +912,7 @@ constexpr int kKeep = (CTS_FUSED_TILE_COLS * 32 + kFusedThreads - 1) / kFusedThr
 // only five CTAs per SM, parking two of them (2 KiB) lets the sixth in.
 template <typename T, bool MATRIX_FREE>
 struct FusedPark {
-  static constexpr int value = (sizeof(T) == 4 && !MATRIX_FREE) ? CTS_FUSED_PARK_F32 : kKeep;
+  static constexpr int value = (sizeof(T) == 4 && !MATRIX_FREE && CTS_FUSED_PARK_F32 < KeepOf<T>::value) ? CTS_FUSED_PARK_F32 : KeepOf<T>::value;
 };
 template <typename T, int NT, bool MATRIX_FREE>
 struct FusedMinBlocks {
@@ -923,6 +928,7 @@ __global__ void __launch_bounds__(kFusedThreads, FusedMinBlocks<T, NT, MATRIX_FR
   constexpr int kCols = TileShape<T>::kCols;       // 16 columns of Float64, 32 of Float32
   constexpr int kSolvers = TileShape<T>::kThreads;  // solver threads: a lane pair per column
   constexpr int kPark = FusedPark<T, MATRIX_FREE>::value;
+  constexpr int KEEP = KeepOf<T>::value;  // 16-byte vectors per thread and tile
   extern __shared__ __align__(128) char smem[];
   const int pitch = a.pitch;
   const int tile_bytes = kCols * pitch;
@@ -965,14 +971,14 @@ __global__ void __launch_bounds__(kFusedThreads, FusedMinBlocks<T, NT, MATRIX_FR
   const int cpc = col_bytes / 16;
   const int cshift = 31 - __clz(cpc);
   const int total = nvalid * cpc;
-  V keep[kKeep];
+  V keep[KEEP];
   constexpr int UN = 2;  // (one round at a time so that the 5-operand stage fits 80 registers / six CTAs: within noise, 6.94-6.95 vs 6.98 ms/step)
-  static_assert(kKeep % UN == 0, "rounds are processed in pairs");
+  static_assert(KEEP % UN == 0, "rounds are processed in pairs");
   // N1c: the number of group-1 terms as a compile-time constant (-1: take it from the arguments at run time)
   auto phase_a = [&](auto N1c) {
   constexpr int N1 = decltype(N1c)::value;
 #pragma unroll
-  for (int r0 = 0; r0 < kKeep; r0 += UN) {
+  for (int r0 = 0; r0 < KEEP; r0 += UN) {
     V vb[UN], vt[NTS][UN];
     size_t gi[UN];
     int so[UN], kk[UN];
@@ -1086,7 +1092,7 @@ __global__ void __launch_bounds__(kFusedThreads, FusedMinBlocks<T, NT, MATRIX_FR
   // ---- phase C: U = U0 - dx ; Timp = (U - U0)/dtγ ; coalesced 128-bit stores; U0 from registers ----------
   const DivConst dc = div_const_prepare(a.dtg);
 #pragma unroll
-  for (int r = 0; r < kKeep; ++r) {
+  for (int r = 0; r < KEEP; ++r) {
     const int q = (int)threadIdx.x + r * kFusedThreads;
     if (q >= total) continue;
     const int c = q >> cshift, k = q & (cpc - 1);
@@ -1937,7 +1943,7 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
   // The pipelined kernel is opt-in (CTS_FUSED_PIPE=1): bit-identical, but measured slower on B200
   static const bool no_pipe = getenv("CTS_FUSED_PIPE") == nullptr || getenv("CTS_FUSED_PIPE")[0] == '0';
   if constexpr (NT <= 5) {
-  if (!no_reg && !no_pipe && (cpc == 16 || cpc == 32)) {
+  if (!no_reg && !no_pipe && (cpc == 16 || cpc == 32) && cpc * kCols == 512) {
     const int pcols = kPipeTileVecs / cpc;
     const int ptile = pcols * a.pitch;
     const PipeCfg cfg = pipe_config(NT, ptile, mf, pcols / 16);
@@ -1997,7 +2003,7 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
     }
   }
   }
-  const bool no_pipe_on = !no_pipe && (cpc == 16 || cpc == 32);  // (the opt-in ring-pipelined kernel above took the launch)
+  const bool no_pipe_on = !no_pipe && (cpc == 16 || cpc == 32) && cpc * kCols == 512;  // (the opt-in ring-pipelined kernel above took the launch)
   // software-pipelined TMA-only kernel (one persistent CTA per SM, lanes of solver warps + data threads): opt-in
   // (CTS_FUSED_SP=1) -- bit-identical, 5.7-5.9 ms of fused stages per step against 4.9-5.1 ms for the register kernel below
   static const bool no_sp = getenv("CTS_FUSED_SP") == nullptr || getenv("CTS_FUSED_SP")[0] == '0';
@@ -2063,7 +2069,7 @@ int launch_fused(cts_op_column* op, const cts_fused_stage_args* s) {
     return CTS_OK;
   }
   }
-  if (!timeline && !no_reg && cpc >= 1 && cpc * kCols <= kKeep * kFusedThreads && (cpc & (cpc - 1)) == 0) {
+  if (!timeline && !no_reg && cpc >= 1 && cpc * kCols <= KeepOf<T>::value * kFusedThreads && (cpc & (cpc - 1)) == 0) {
     tiles = (op->ncols + kCols - 1) / kCols;
     size_t smem_reg = (size_t)(mf ? 2 : 4) * kCols * a.pitch + 16 + ((kCols * sizeof(T) + 15) / 16) * 16 +
                       (size_t)TileShape<T>::kThreads * (mf ? FusedPark<T, true>::value : FusedPark<T, false>::value) * 16;  // tiles + mbarrier + K/dz^2 + parked U0 of the solver threads
@@ -2174,6 +2180,7 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_RHS_SOLVE_MIN_BLOCKS) colum
   constexpr int NTS = NTC > 0 ? NTC : 1;
   constexpr int kCols = TileShape<T>::kCols;
   constexpr int kSolvers = TileShape<T>::kThreads;
+  constexpr int KEEP = KeepOf<T>::value;
   extern __shared__ __align__(128) char smem[];
   const int pitch = a.pitch;
   const int tile_bytes = kCols * pitch;
@@ -2210,9 +2217,9 @@ __global__ void __launch_bounds__(kFusedThreads, CTS_RHS_SOLVE_MIN_BLOCKS) colum
   constexpr bool round_each = sizeof(T) == 4;
   const bool has_v = MODE == MODE_JVP || MODE == MODE_PRE || a.v != nullptr;
   constexpr int UN = 2;  // rounds whose loads are all issued before the first use (as in the fused stage kernel)
-  static_assert(kKeep % UN == 0, "rounds are processed in pairs");
+  static_assert(KEEP % UN == 0, "rounds are processed in pairs");
 #pragma unroll
-  for (int r0 = 0; r0 < kKeep; r0 += UN) {
+  for (int r0 = 0; r0 < KEEP; r0 += UN) {
     V vx[UN], vv[UN], vu[UN], vf[UN], vt[NTS][UN];
     T acol[UN];
     bool ok[UN];
@@ -2400,7 +2407,8 @@ static bool rhs_solve_shape_ok(const cts_op_column* op) {
   if (op->d.nlev < 2 || (op->d.nlev % 2) || (cb % 16)) return false;
   const int cpc = cb / 16;
   const int cols = op->ft == CTS_F64 ? TileShape<double>::kCols : TileShape<float>::kCols;
-  return cpc <= 32 && (cpc & (cpc - 1)) == 0 && cpc * cols <= kKeep * kFusedThreads;
+  const int keep = op->ft == CTS_F64 ? KeepOf<double>::value : KeepOf<float>::value;
+  return cpc <= 32 && (cpc & (cpc - 1)) == 0 && cpc * cols <= keep * kFusedThreads;
 }
 
 static bool rhs_solve_w_ok(const cts_op_column* op, const cts_tridiag* W) {
